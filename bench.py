@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py — trio candidate sites/sec, READ-mode BAYES inference at 30x (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]       our arm (one process per GPU under torchrun)
+  python bench.py --impl reference ...                       reference arm: the reference's CPU algorithm
+                                                            (C restatement, no JVM in this image) on host cores
+
+One "step" = one pass of the hot path over one batch: packed pileup counts resident in HBM
+-> compacted call records in HBM (+ for N>1 the NCCL gather of calls to rank 0).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "denovo-variant-caller-java_b200", "python"))
+
+METRIC = "trio candidate sites/sec (READ-mode BAYES, 30x)"
+SITES_PER_GPU = 10_000_000
+SEED = 0x5EED0003
+DEPTH, EPS, MU, LRT = 30, 1e-2, 1e-8, 1.0
+# ALGORITHMIC work per site of the form the fused kernel executes:
+#   bytes: 24 B of counts in + 1 decision bit out; flops: sparse factored form, FMA = 2
+BYTES_PER_SITE = 24.125
+FLOP_PER_SITE = 451.0
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[6]))
+            except (ValueError, IndexError):
+                continue
+            for i, nm in enumerate(names):
+                if len(r) > 2 + i and r[2 + i].lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+
+def cpu_reference_run(n_sites, threads, faithful=True):
+    """The reference's algorithm (direct form, reference operation order) on host cores."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    counts = O.synth_counts(SEED, 0, n_sites, depth=DEPTH, seq_err=EPS)
+    prm = O.params(EPS, MU, LRT)
+    O.infer(prm, counts[:1000], faithful=faithful, threads=threads)
+    t0 = time.perf_counter()
+    res = O.infer(prm, counts, faithful=faithful, threads=threads)
+    dt = time.perf_counter() - t0
+    return n_sites / dt, int(res["denovo_bayes"].sum())
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    sample = 200_000
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    counts = O.synth_counts(SEED, 0, sample, depth=DEPTH, seq_err=EPS)
+    prm = O.params(EPS, MU, LRT)
+    for _ in range(args.warmup):
+        O.infer(prm, counts[:20000], faithful=True, threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.infer(prm, counts, faithful=True, threads=threads)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "sites/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "READ-mode BAYES inference, synthetic trio pileups at 30x, eps 1e-2, mu 1e-8 "
+                                   "(BASELINE configs[2]); %d-site sample per step" % sample},
+            "cpu_baseline": {"value": value, "unit": "sites/s", "cores": threads, "kind": "port",
+                             "sample": "%d sites/step x %d steps; C restatement of the reference's direct form "
+                                       "(3 log + 1 exp per genotype triple, as DenovoBayesNet.java:220-233,269-273); "
+                                       "no JVM in this image so the Java itself cannot run" % (sample, args.steps)},
+            "e2e": {"value": value, "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--sites", type=int, default=SITES_PER_GPU)
+    ap.add_argument("--method", default="BAYES")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import denovo_b200 as D
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: there is no CPU fallback"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = args.sites
+    K, W = args.steps, max(args.warmup, 3)
+
+    eng = D.TrioEngine(EPS, MU, LRT, args.method, device=local, time_kernels=True)
+    stream = torch.cuda.Stream(device=local)
+    eng.set_stream(stream.cuda_stream)
+
+    # ---- synthetic shard of this rank (interval sharding: rank r owns sites [r*n, (r+1)*n))
+    d_counts = torch.empty((n, 12), dtype=torch.int16, device="cuda")
+    eng.synth_counts_device(SEED, rank * n, n, d_counts, depth=DEPTH)
+    cap = max(n // 50, 1024)
+    d_calls = torch.zeros((cap, D.CALL_DT.itemsize), dtype=torch.uint8, device="cuda")
+
+    def gather_calls(n_calls):
+        """NCCL gather of call records to rank 0 (the reference's shared PrintWriter, DenovoCaller.java:56-59)."""
+        if world == 1:
+            return n_calls
+        cnt = torch.tensor([n_calls], dtype=torch.int64, device="cuda")
+        allc = [torch.zeros_like(cnt) for _ in range(world)]
+        dist.all_gather(allc, cnt)
+        mx = int(max(int(c.item()) for c in allc))
+        send = d_calls[:mx].contiguous()
+        recv = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
+        dist.gather(send, recv, dst=0)
+        return sum(int(c.item()) for c in allc)
+
+    def step():
+        with torch.cuda.stream(stream):
+            nc = eng.infer_device(d_counts, n, d_calls, cap)
+            return gather_calls(nc)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        total_calls = step()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fused_ms, launches = 0.0, 0
+    e0.record(stream)
+    for _ in range(K):
+        total_calls = step()
+        st = eng.stats()
+        fused_ms += st["fused_kernel_ms"]
+        launches += st["n_launches"]
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * n * K / (ms_max * 1e-3)
+    n_hard = eng.stats()["n_hard"]
+
+    # ---- end to end through the host API: pinned host counts -> calls in pinned host memory
+    h_counts = torch.empty((n, 12), dtype=torch.int16).pin_memory()
+    h_counts.copy_(d_counts)
+    h_calls = torch.zeros((cap, D.CALL_DT.itemsize), dtype=torch.uint8).pin_memory()
+    eng.set_stream(None)
+    for _ in range(2):
+        e2e_calls = eng.infer_host_into(h_counts, n, h_calls, cap)
+    Ke = max(3, K // 4)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        e2e_calls = eng.infer_host_into(h_counts, n, h_calls, cap)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * Ke / float(te.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant (fused likelihood + posterior) kernel
+    fp64_peak, _ = eng.measure_fp64_peak()
+    hbm_peak, peak_src = load_peaks()
+    k_ms = fused_ms / K
+    ach_tf = FLOP_PER_SITE * n / (k_ms * 1e-3) / 1e12
+    ach_gbs = BYTES_PER_SITE * n / (k_ms * 1e-3) / 1e9
+    roofline = {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": ach_tf / fp64_peak if fp64_peak else None, "traffic": None,
+                "kernel": "trio_fast_kernel", "kernel_ms": k_ms, "kernel_share_of_step": k_ms / (ms_max / K),
+                "flop_per_site": FLOP_PER_SITE,
+                "peak_source": "measured in this run (dependent-free DFMA chains, all SMs; MEASURED_PEAKS.json has no FP64 figure)",
+                "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                        "bytes_per_site": BYTES_PER_SITE, "peak_source": peak_src}}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sample = 1_000_000
+        v, cpu_calls = cpu_reference_run(sample, threads, faithful=True)
+        v_hoist, _ = cpu_reference_run(sample, threads, faithful=False)
+        cpu = {"value": v, "unit": "sites/s", "cores": threads, "kind": "port",
+               "sample": "first %d sites of rank 0's shard, direct form with the reference's 3 log + 1 exp per "
+                         "triple (C restatement; no JVM here)" % sample,
+               "value_tables_hoisted": v_hoist}
+
+    line = {"metric": METRIC, "value": value, "unit": "sites/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "READ-mode %s inference, %d synthetic trio candidate sites per GPU at 30x, eps 1e-2, "
+                                   "mu 1e-8 (BASELINE configs[2]); interval-sharded, NCCL gather of calls to rank 0"
+                                   % (args.method, n),
+                       "sites_per_gpu": n, "l2": "input 240 MB per pass > 126 MB L2 (no flush needed)",
+                       "calls_per_step": int(total_calls), "hard_sites_last_step": int(n_hard)},
+            "e2e": {"value": e2e_value, "unit": "sites/s", "h2d_bytes_per_step": n * 24,
+                    "d2h_bytes_per_step": int(e2e_calls) * D.CALL_DT.itemsize + 64, "steps": Ke,
+                    "timer": "host wall clock around dnv_infer_counts (pinned host buffers), max over ranks"},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

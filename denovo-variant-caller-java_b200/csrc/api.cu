@@ -1,0 +1,239 @@
+// api.cu — the extern "C" boundary (include/denovo_b200.h): context lifecycle
+// and the READ-mode entry points.  Plain pointers and sizes only.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+
+#include "dnv_internal.cuh"
+
+namespace dnv {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+int ensure_scratch(dnv_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->scratch_bytes) return DNV_OK;
+  cudaFree(ctx->d_scratch);
+  ctx->d_scratch = nullptr;
+  ctx->scratch_bytes = 0;
+  DNV_CUDA(cudaMalloc(&ctx->d_scratch, bytes));
+  ctx->scratch_bytes = bytes;
+  return DNV_OK;
+}
+
+// sites per pipeline chunk of the device path (scratch is sized for one chunk)
+constexpr int64_t kDeviceChunk = 1ll << 27;
+// sites per H2D/compute/D2H stage of the host path
+constexpr int64_t kHostChunk = 1ll << 21;
+
+static int ensure_stage(dnv_ctx* ctx, int64_t n, bool dense, int64_t calls_cap) {
+  if (n > ctx->stage_cap) {
+    for (int i = 0; i < 2; i++) {
+      cudaFree(ctx->d_stage_counts[i]);
+      cudaFree(ctx->d_stage_dense[i]);
+      ctx->d_stage_counts[i] = nullptr;
+      ctx->d_stage_dense[i] = nullptr;
+    }
+    ctx->stage_cap = 0;
+    for (int i = 0; i < 2; i++) DNV_CUDA(cudaMalloc(&ctx->d_stage_counts[i], (size_t)n * 24));
+    ctx->stage_cap = n;
+  }
+  if (dense)
+    for (int i = 0; i < 2; i++)
+      if (!ctx->d_stage_dense[i])
+        DNV_CUDA(cudaMalloc(&ctx->d_stage_dense[i], (size_t)ctx->stage_cap * sizeof(dnv_site_result)));
+  if (calls_cap > ctx->stage_calls_cap) {
+    cudaFree(ctx->d_stage_calls);
+    ctx->d_stage_calls = nullptr;
+    ctx->stage_calls_cap = 0;
+    DNV_CUDA(cudaMalloc(&ctx->d_stage_calls, (size_t)std::max<int64_t>(calls_cap, 1) * sizeof(dnv_call)));
+    ctx->stage_calls_cap = calls_cap;
+  }
+  return DNV_OK;
+}
+
+}  // namespace dnv
+
+using namespace dnv;
+
+extern "C" {
+
+const char* dnv_last_error(void) { return g_last_error.c_str(); }
+int dnv_abi_version(void) { return DNV_ABI_VERSION; }
+
+int dnv_create(const dnv_params* p, dnv_ctx** out) {
+  if (!p || !out) { set_error("dnv_create: null argument"); return DNV_E_INVALID; }
+  *out = nullptr;
+  if (!(p->seq_err_rate > 0.0 && p->seq_err_rate < 1.0) ||
+      !(p->denovo_mut_rate > 0.0 && p->denovo_mut_rate < 1.0) || isnan(p->lrt_threshold) ||
+      p->method < DNV_METHOD_MAP || p->method > DNV_METHOD_LRT) {
+    set_error("dnv_create: seq_err_rate and denovo_mut_rate must lie in (0,1), method in {0,1,2}");
+    return DNV_E_INVALID;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_error(std::string("dnv_create: no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    return DNV_E_CUDA;
+  }
+  if (p->device < 0 || p->device >= ndev) { set_error("dnv_create: bad device ordinal"); return DNV_E_INVALID; }
+  DNV_CUDA(cudaSetDevice(p->device));
+  dnv_ctx* ctx = new (std::nothrow) dnv_ctx();
+  if (!ctx) return DNV_E_NOMEM;
+  memset(ctx, 0, sizeof(*ctx));
+  ctx->prm = *p;
+  ctx->device = p->device;
+  build_tables(*p, &ctx->h_tab);
+  DNV_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+  ctx->stream = ctx->own_stream;
+  if (p->flags & DNV_F_TIME_KERNELS)
+    for (int i = 0; i < 64; i++) {
+      DNV_CUDA(cudaEventCreate(&ctx->ev_k0[i]));
+      DNV_CUDA(cudaEventCreate(&ctx->ev_k1[i]));
+    }
+  DNV_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) {
+    DNV_CUDA(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
+    DNV_CUDA(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+  }
+  DNV_CUDA(cudaMalloc(&ctx->d_tab, sizeof(Tables)));
+  DNV_CUDA(cudaMemcpy(ctx->d_tab, &ctx->h_tab, sizeof(Tables), cudaMemcpyHostToDevice));
+  DNV_CUDA(cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)));
+  DNV_CUDA(cudaMemset(ctx->d_counters, 0, 8 * sizeof(unsigned long long)));
+  *out = ctx;
+  return DNV_OK;
+}
+
+int dnv_destroy(dnv_ctx* ctx) {
+  if (!ctx) return DNV_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->copy_stream);
+  cudaFree(ctx->d_tab); cudaFree(ctx->d_bits); cudaFree(ctx->d_hard_list); cudaFree(ctx->d_block_sums);
+  cudaFree(ctx->d_call_idx); cudaFree(ctx->d_counters); cudaFree(ctx->d_stage_calls); cudaFree(ctx->d_scratch);
+  for (int i = 0; i < 2; i++) {
+    cudaFree(ctx->d_stage_counts[i]); cudaFree(ctx->d_stage_dense[i]);
+    cudaEventDestroy(ctx->ev_h2d[i]); cudaEventDestroy(ctx->ev_done[i]);
+  }
+  if (ctx->prm.flags & DNV_F_TIME_KERNELS)
+    for (int i = 0; i < 64; i++) { cudaEventDestroy(ctx->ev_k0[i]); cudaEventDestroy(ctx->ev_k1[i]); }
+  cudaStreamDestroy(ctx->own_stream);
+  cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+  return DNV_OK;
+}
+
+int dnv_get_tables(dnv_ctx* ctx, double* rel, double* base_ll, uint8_t* is_denovo) {
+  if (!ctx) { set_error("dnv_get_tables: null ctx"); return DNV_E_INVALID; }
+  Tables t;  // read back what the device actually holds
+  DNV_CUDA(cudaSetDevice(ctx->device));
+  DNV_CUDA(cudaMemcpy(&t, ctx->d_tab, sizeof(Tables), cudaMemcpyDeviceToHost));
+  if (rel) memcpy(rel, t.rel, sizeof(t.rel));
+  if (base_ll) {
+    static const int a0[10] = {0, 0, 0, 0, 1, 1, 1, 2, 2, 3}, a1[10] = {0, 1, 2, 3, 1, 2, 3, 2, 3, 3};
+    for (int g = 0; g < 10; g++)
+      for (int a = 0; a < 4; a++)
+        base_ll[g * 4 + a] = (a == a0[g] || a == a1[g]) ? (a0[g] == a1[g] ? t.hm : t.ht) : t.mm;
+  }
+  if (is_denovo)
+    for (int i = 0; i < 1000; i++) is_denovo[i] = (t.isden[i >> 5] >> (i & 31)) & 1u;
+  return DNV_OK;
+}
+
+int dnv_set_stream(dnv_ctx* ctx, void* cuda_stream) {
+  if (!ctx) { set_error("dnv_set_stream: null ctx"); return DNV_E_INVALID; }
+  DNV_CUDA(cudaSetDevice(ctx->device));
+  DNV_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return DNV_OK;
+}
+
+int dnv_get_stats(dnv_ctx* ctx, dnv_stats* out) {
+  if (!ctx || !out) { set_error("dnv_get_stats: null argument"); return DNV_E_INVALID; }
+  *out = ctx->stats;
+  return DNV_OK;
+}
+
+static int finish_batch(dnv_ctx* ctx, int64_t n, int64_t cap, int64_t* n_calls) {
+  unsigned long long h[8];
+  DNV_CUDA(cudaMemcpyAsync(h, ctx->d_counters, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  DNV_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->stats.fused_kernel_ms = 0;
+  for (int i = 0; i < ctx->n_timed; i++) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev_k0[i], ctx->ev_k1[i]) == cudaSuccess) ctx->stats.fused_kernel_ms += ms;
+  }
+  ctx->stats.n_sites = n;
+  ctx->stats.n_calls = (int64_t)h[0];
+  ctx->stats.n_hard = (int64_t)h[4];
+  *n_calls = (int64_t)h[0];
+  if ((int64_t)h[0] > cap) {
+    set_error("call capacity too small: need " + std::to_string(h[0]) + ", have " + std::to_string(cap));
+    return DNV_E_CAPACITY;
+  }
+  return DNV_OK;
+}
+
+int dnv_infer_counts_device(dnv_ctx* ctx, const uint16_t* d_counts, int64_t n, dnv_site_result* d_dense,
+                            dnv_call* d_calls, int64_t cap, int64_t* n_calls) {
+  if (!ctx || !n_calls || n < 0 || cap < 0 || (n > 0 && !d_counts) || (cap > 0 && !d_calls)) {
+    set_error("dnv_infer_counts_device: invalid argument");
+    return DNV_E_INVALID;
+  }
+  DNV_CUDA(cudaSetDevice(ctx->device));
+  ctx->stats = dnv_stats();
+  ctx->n_timed = 0;
+  DNV_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+  for (int64_t off = 0; off < n; off += kDeviceChunk) {
+    const int64_t m = std::min(kDeviceChunk, n - off);
+    int rc = launch_trio_chunk(ctx, d_counts + off * 12, off, m, d_dense ? d_dense + off : nullptr, d_calls, cap);
+    if (rc) return rc;
+  }
+  return finish_batch(ctx, n, cap, n_calls);
+}
+
+int dnv_infer_counts(dnv_ctx* ctx, const uint16_t* counts, int64_t n, dnv_site_result* dense, dnv_call* calls,
+                     int64_t cap, int64_t* n_calls) {
+  if (!ctx || !n_calls || n < 0 || cap < 0 || (n > 0 && !counts) || (cap > 0 && !calls)) {
+    set_error("dnv_infer_counts: invalid argument");
+    return DNV_E_INVALID;
+  }
+  DNV_CUDA(cudaSetDevice(ctx->device));
+  ctx->stats = dnv_stats();
+  ctx->n_timed = 0;
+  const int64_t chunk = std::min<int64_t>(kHostChunk, std::max<int64_t>(n, 1));
+  const int64_t dev_cap = std::min(cap, n);
+  int rc = ensure_stage(ctx, chunk, dense != nullptr, dev_cap);
+  if (rc) return rc;
+  DNV_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+  // two-stage ring: H2D of chunk k+1 (copy stream) overlaps compute of chunk k
+  int k = 0;
+  for (int64_t off = 0; off < n; off += chunk, k ^= 1) {
+    const int64_t m = std::min(chunk, n - off);
+    // buffer k is free once the compute (and dense D2H) that last used it finished
+    DNV_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[k], 0));
+    DNV_CUDA(cudaMemcpyAsync(ctx->d_stage_counts[k], counts + off * 12, (size_t)m * 24, cudaMemcpyHostToDevice,
+                             ctx->copy_stream));
+    DNV_CUDA(cudaEventRecord(ctx->ev_h2d[k], ctx->copy_stream));
+    DNV_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[k], 0));
+    rc = launch_trio_chunk(ctx, ctx->d_stage_counts[k], off, m, dense ? ctx->d_stage_dense[k] : nullptr,
+                           ctx->d_stage_calls, dev_cap);
+    if (rc) return rc;
+    if (dense)
+      DNV_CUDA(cudaMemcpyAsync(dense + off, ctx->d_stage_dense[k], (size_t)m * sizeof(dnv_site_result),
+                               cudaMemcpyDeviceToHost, ctx->stream));
+    DNV_CUDA(cudaEventRecord(ctx->ev_done[k], ctx->stream));
+  }
+  rc = finish_batch(ctx, n, cap, n_calls);
+  const int64_t got = std::min<int64_t>(*n_calls, dev_cap);
+  if (got > 0) {
+    DNV_CUDA(cudaMemcpyAsync(calls, ctx->d_stage_calls, (size_t)got * sizeof(dnv_call), cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    DNV_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,86 @@
+// dnv_internal.cuh — shared declarations of the B200 trio de novo library.
+// Product code: never includes or links anything under oracle/.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "denovo_b200.h"
+
+namespace dnv {
+
+constexpr int kPowTable = 1024;  // entries of each r^k table held in shared memory
+
+// Site-invariant tables, built once per ctx on the host (tables.cpp) and kept
+// in device global memory; kernels stage what they need into shared memory.
+struct Tables {
+  // exact log-domain tables (bit-identical to the reference's arithmetic)
+  double rel[1000];       // getRelationshipLogLikelihood, M/DenovoBayesNet.java:322-330
+  double hm, ht, mm;      // getBaseLogLikelihood's three values, :159-165
+  uint32_t isden[32];     // isDenovoMap as a 1000-bit mask, M/DenovoUtil.java:37-55
+  uint8_t nden[100];      // 10 - |mendelianGenotypes(d,m)|, M/DenovoBayesNet.java:98
+  // linear-domain fast path (factored form)
+  double pw_m[2][kPowTable];   // mantissa in [1,2) of r_j^k, j=0 hom ratio, j=1 het ratio
+  int32_t pw_e[2][kPowTable];  // binary exponent of r_j^k
+  double c_hi[2], c_lo[2];     // log2(r_j) split hi/lo for k >= kPowTable
+  double mm2;                  // log2(eps/3)
+  double k_men;                // ((1-mu)/4)/64
+  double k_den[4];             // (mu/256)/nDen for nDen = 9,8,7,6
+  double lrt_thr;              // 1.0 for BAYES, lrt_threshold for LRT
+  double lrt_threshold;        // raw --lrt_threshold (exact path)
+  int32_t method;
+};
+
+void build_tables(const dnv_params& p, Tables* t);
+
+void set_error(const std::string& msg);
+
+}  // namespace dnv
+
+struct dnv_ctx {
+  dnv_params prm;
+  int device;
+  cudaStream_t stream;       // compute (own_stream unless dnv_set_stream)
+  cudaStream_t own_stream;
+  cudaEvent_t ev_k0[64], ev_k1[64];  // fused-kernel brackets (DNV_F_TIME_KERNELS)
+  int n_timed;
+  cudaStream_t copy_stream;  // H2D / D2H of the host API
+  cudaEvent_t ev_h2d[2], ev_done[2];
+  dnv::Tables h_tab;
+  dnv::Tables* d_tab;
+  // per-chunk scratch (sized for chunk_cap sites)
+  int64_t chunk_cap;
+  uint32_t* d_bits;        // decision bit per site
+  uint32_t* d_hard_list;   // chunk-relative indices of hard sites
+  uint32_t* d_block_sums;  // popcount per compaction block
+  int64_t* d_call_idx;     // global site index of every call, input order
+  int64_t call_idx_cap;
+  unsigned long long* d_counters;  // [0] calls total [1] hard in chunk [2] range lo [3] range hi [4] hard total [5] error
+  // staging of the host API
+  uint16_t* d_stage_counts[2];
+  dnv_site_result* d_stage_dense[2];
+  int64_t stage_cap;
+  dnv_call* d_stage_calls;
+  int64_t stage_calls_cap;
+  // generic scratch for pileup / mendel
+  void* d_scratch;
+  size_t scratch_bytes;
+  dnv_stats stats;
+};
+
+#define DNV_CUDA(call)                                                        \
+  do {                                                                        \
+    cudaError_t e_ = (call);                                                  \
+    if (e_ != cudaSuccess) {                                                  \
+      dnv::set_error(std::string(#call) + ": " + cudaGetErrorString(e_));     \
+      return DNV_E_CUDA;                                                      \
+    }                                                                         \
+  } while (0)
+
+namespace dnv {
+// kernels / launchers (defined in the .cu files)
+int launch_trio_chunk(dnv_ctx* ctx, const uint16_t* d_counts, int64_t site_base, int64_t n,
+                      dnv_site_result* d_dense, dnv_call* d_calls, int64_t cap);
+int ensure_chunk_scratch(dnv_ctx* ctx, int64_t n);
+int ensure_scratch(dnv_ctx* ctx, size_t bytes);
+}  // namespace dnv

@@ -1,0 +1,158 @@
+// synth.cu — device generator of synthetic trio pileups.  Replaces the
+// reference's Google Genomics API client (M/ReadCaller.java:155-186; network,
+// out of scope) as the source of read evidence.  Bit-for-bit specification:
+// oracle/synth_ref.c — counter-based splitmix64, so any
+// site can be generated independently on any rank.
+#include <algorithm>
+#include "dnv_internal.cuh"
+
+namespace dnv {
+
+#define DNV_PHI 0x9E3779B97F4A7C15ULL
+
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  uint64_t z = x + DNV_PHI;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+
+struct SynthKeys {
+  uint64_t k_class, k_ref, k_alt, k_par, k_depth[3], k_read[3];
+};
+
+constexpr int kMaxThr = 1024;
+
+__global__ void __launch_bounds__(256)
+synth_counts_kernel(SynthKeys keys, int64_t first, int64_t n, const uint64_t* __restrict__ thr, int n_thr,
+                    uint32_t err_thr, uint16_t* __restrict__ counts) {
+  __shared__ uint64_t s_thr[kMaxThr];
+  for (int i = threadIdx.x; i < n_thr; i += blockDim.x) s_thr[i] = thr[i];
+  __syncthreads();
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t i = (uint64_t)(first + s);
+    const uint32_t c100 = (uint32_t)(((splitmix64(keys.k_class ^ i) >> 32) * 100ULL) >> 32);
+    const int cls = c100 < 90 ? 0 : (c100 < 99 ? 1 : 2);
+    const int ref = (int)(splitmix64(keys.k_ref ^ i) & 3);
+    const int alt = (ref + 1 + (int)(splitmix64(keys.k_alt ^ i) % 3)) & 3;
+    const uint64_t pb = splitmix64(keys.k_par ^ i);
+    int g1[3] = {ref, ref, ref};  // second allele of DAD, MOM, CHILD (first is always ref)
+    if (cls == 1) {
+      if (pb & 1) g1[1] = alt; else g1[0] = alt;
+      if ((pb >> 1) & 1) g1[2] = alt;
+    } else if (cls == 2) {
+      g1[2] = alt;
+    }
+    uint32_t out[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) out[k] = 0;
+#pragma unroll
+    for (int p = 0; p < 3; p++) {
+      const uint64_t ud = splitmix64(keys.k_depth[p] ^ i);
+      int lo = 0, hi = n_thr;  // depth = #{k : thr[k] <= ud}, thr ascending
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (s_thr[mid] <= ud) lo = mid + 1; else hi = mid;
+      }
+      const int depth = lo;
+      uint32_t cnt[4] = {0, 0, 0, 0};
+      for (int j = 0; j < depth; j++) {
+        const uint64_t u = splitmix64(keys.k_read[p] ^ ((i << 16) | (uint64_t)j));
+        int b = (u & 1) ? g1[p] : ref;
+        if ((uint32_t)(u >> 32) < err_thr) b = (b + 1 + (int)(((u >> 8) & 0xFFFF) % 3)) & 3;
+        cnt[0] += b == 0; cnt[1] += b == 1; cnt[2] += b == 2; cnt[3] += b == 3;
+      }
+#pragma unroll
+      for (int a = 0; a < 4; a++) out[p * 4 + a] = cnt[a];
+    }
+    uint2* dst = reinterpret_cast<uint2*>(counts + s * 12);
+#pragma unroll
+    for (int q = 0; q < 3; q++)
+      dst[q] = make_uint2(out[4 * q] | (out[4 * q + 1] << 16), out[4 * q + 2] | (out[4 * q + 3] << 16));
+  }
+}
+
+// ---- FP64 peak calibration: 8 independent DFMA chains per thread ----------
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double seed) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+         a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+      a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+  }
+  const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (r == 12345.678) out[0] = r;  // never true; keeps the chains alive
+}
+
+}  // namespace dnv
+
+using namespace dnv;
+
+extern "C" {
+
+int dnv_synth_counts_device(dnv_ctx* ctx, uint64_t seed, int64_t first, int64_t n, const uint64_t* thr,
+                            int32_t n_thr, uint32_t err_thr, uint16_t* d_counts) {
+  if (!ctx || n < 0 || !thr || n_thr <= 0 || n_thr > kMaxThr || (n > 0 && !d_counts)) {
+    set_error("dnv_synth_counts_device: invalid argument (n_thr must be in 1..1024)");
+    return DNV_E_INVALID;
+  }
+  if (n == 0) return DNV_OK;
+  DNV_CUDA(cudaSetDevice(ctx->device));
+  int rc = ensure_scratch(ctx, (size_t)n_thr * 8);
+  if (rc) return rc;
+  DNV_CUDA(cudaMemcpyAsync(ctx->d_scratch, thr, (size_t)n_thr * 8, cudaMemcpyHostToDevice, ctx->stream));
+  SynthKeys k;
+  k.k_class = splitmix64(seed ^ (0 * DNV_PHI));
+  k.k_ref = splitmix64(seed ^ (1 * DNV_PHI));
+  k.k_alt = splitmix64(seed ^ (2 * DNV_PHI));
+  k.k_par = splitmix64(seed ^ (3 * DNV_PHI));
+  for (int p = 0; p < 3; p++) {
+    k.k_depth[p] = splitmix64(seed ^ ((uint64_t)(4 + p) * DNV_PHI));
+    k.k_read[p] = splitmix64(seed ^ ((uint64_t)(8 + p) * DNV_PHI));
+  }
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  const int64_t want = (n + 255) / 256;
+  const int grid = (int)std::min<int64_t>(want, (int64_t)sms * 8);
+  synth_counts_kernel<<<grid, 256, 0, ctx->stream>>>(k, first, n, (const uint64_t*)ctx->d_scratch, n_thr, err_thr,
+                                                     d_counts);
+  DNV_CUDA(cudaGetLastError());
+  DNV_CUDA(cudaStreamSynchronize(ctx->stream));
+  return DNV_OK;
+}
+
+int dnv_measure_fp64_peak(dnv_ctx* ctx, double* tflops, double* ms) {
+  if (!ctx || !tflops) { set_error("dnv_measure_fp64_peak: null argument"); return DNV_E_INVALID; }
+  DNV_CUDA(cudaSetDevice(ctx->device));
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  int rc = ensure_scratch(ctx, 64);
+  if (rc) return rc;
+  const int iters = 4096, grid = sms * 8, block = 256;
+  cudaEvent_t e0, e1;
+  DNV_CUDA(cudaEventCreate(&e0));
+  DNV_CUDA(cudaEventCreate(&e1));
+  double best = 0, best_ms = 0;
+  for (int rep = 0; rep < 5; rep++) {
+    DNV_CUDA(cudaEventRecord(e0, ctx->stream));
+    fp64_peak_kernel<<<grid, block, 0, ctx->stream>>>((double*)ctx->d_scratch, iters, 1.0 + rep);
+    DNV_CUDA(cudaEventRecord(e1, ctx->stream));
+    DNV_CUDA(cudaEventSynchronize(e1));
+    float t = 0;
+    DNV_CUDA(cudaEventElapsedTime(&t, e0, e1));
+    const double flops = 2.0 * 64.0 * iters * (double)grid * block;
+    const double tf = flops / (t * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) { best = tf; best_ms = t; }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *tflops = best;
+  if (ms) *ms = best_ms;
+  return DNV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,103 @@
+// tables.cpp — site-invariant tables of the trio Bayes net (host side, built
+// once per ctx; replaces `new DenovoBayesNet(shared)`,
+// M/DenovoBayesNet.java:52-63).  Written from the model definition:
+//   parent prior  P(g)        = (hom ? 1 : 2) / 16            (:84-85)
+//   child CPT     T(d,m,c)    = denovo ? mu / nDen(d,m)
+//                                      : ((1 - mu) / 4) * cnt(d,m,c)   (:106-109)
+//   relationship  R(d,m,c)    = (log P(d) + log P(m)) + log T(d,m,c)  (:322-330)
+//   base log-lik  hm, ht, mm                                          (:159-165)
+// Compiled with -ffp-contract=off so R/hm/ht/mm carry the same bits a JVM or
+// the CPU oracle computes from the same formulas.
+#include <cmath>
+#include <cstring>
+
+#include "dnv_internal.cuh"
+
+namespace dnv {
+
+namespace {
+// genotype g <-> unordered allele pair (a0 <= a1), ordinal order AA,AC,AG,AT,CC,CG,CT,GG,GT,TT
+const int kA0[10] = {0, 0, 0, 0, 1, 1, 1, 2, 2, 3};
+const int kA1[10] = {0, 1, 2, 3, 1, 2, 3, 2, 3, 3};
+
+int geno_of(int x, int y) {
+  if (x > y) { int t = x; x = y; y = t; }
+  for (int g = 0; g < 10; g++)
+    if (kA0[g] == x && kA1[g] == y) return g;
+  return -1;
+}
+bool has(int g, int a) { return kA0[g] == a || kA1[g] == a; }
+
+// r^k = m * 2^e with m in [1,2): computed in long double from k*log2(r)
+void pow_entry(long double log2r, int k, double* m, int32_t* e) {
+  long double t = log2r * (long double)k;
+  long double fl = floorl(t);
+  long double mant = exp2l(t - fl);
+  if (mant >= 2.0L) { mant *= 0.5L; fl += 1.0L; }
+  *m = (double)mant;
+  if (*m >= 2.0) { *m = 1.0; fl += 1.0L; }
+  *e = (int32_t)fl;
+}
+}  // namespace
+
+void build_tables(const dnv_params& p, Tables* t) {
+  std::memset(t, 0, sizeof(*t));
+  const double eps = p.seq_err_rate, mu = p.denovo_mut_rate;
+  double prior[10];
+  for (int g = 0; g < 10; g++) prior[g] = (kA0[g] == kA1[g] ? 1.0 : 2.0) / 16;
+
+  t->hm = std::log(1 - eps);
+  t->ht = std::log(1 - 2 * eps / 3) - std::log(2);
+  t->mm = std::log(eps) - std::log(3);
+
+  for (int d = 0; d < 10; d++)
+    for (int m = 0; m < 10; m++) {
+      int cnt[10] = {0};
+      const int da[2] = {kA0[d], kA1[d]}, ma[2] = {kA0[m], kA1[m]};
+      for (int i = 0; i < 2; i++)
+        for (int j = 0; j < 2; j++) cnt[geno_of(da[i], ma[j])]++;
+      int keys = 0;
+      for (int g = 0; g < 10; g++) keys += cnt[g] > 0;
+      const int n_den = 10 - keys;
+      t->nden[d * 10 + m] = (uint8_t)n_den;
+      for (int c = 0; c < 10; c++) {
+        const int c1 = kA0[c], c2 = kA1[c];
+        const bool mendel = (has(m, c1) && has(d, c2)) || (has(m, c2) && has(d, c1));
+        const int idx = d * 100 + m * 10 + c;
+        const double T = mendel ? (1.0 - mu) / 4 * cnt[c] : mu / n_den;
+        if (!mendel) t->isden[idx >> 5] |= 1u << (idx & 31);
+        double r = 0;
+        r += std::log(prior[d]);
+        r += std::log(prior[m]);
+        r += std::log(T);
+        t->rel[idx] = r;
+      }
+    }
+
+  // linear-domain path: likelihood ratios against the mismatch likelihood
+  const long double l2e = 1.442695040888963407359924681001892137L;
+  const long double le = (long double)eps;
+  const long double log2r[2] = {
+      (logl(1.0L - le) - (logl(le) - logl(3.0L))) * l2e,                       // hom match / mismatch
+      ((logl(1.0L - 2.0L * le / 3.0L) - logl(2.0L)) - (logl(le) - logl(3.0L))) * l2e};  // het match / mismatch
+  for (int j = 0; j < 2; j++) {
+    for (int k = 0; k < kPowTable; k++) pow_entry(log2r[j], k, &t->pw_m[j][k], &t->pw_e[j][k]);
+    // hi part keeps 30 significant bits so k*hi is exact for k < 2^22
+    double hi = (double)log2r[j];
+    uint64_t bits;
+    std::memcpy(&bits, &hi, 8);
+    bits &= ~((1ULL << 23) - 1);
+    std::memcpy(&hi, &bits, 8);
+    t->c_hi[j] = hi;
+    t->c_lo[j] = (double)(log2r[j] - (long double)hi);
+  }
+  t->mm2 = (double)((logl(le) - logl(3.0L)) * l2e);
+  t->k_men = (1.0 - mu) / 4 / 64;
+  const int nd[4] = {9, 8, 7, 6};
+  for (int i = 0; i < 4; i++) t->k_den[i] = mu / 256 / nd[i];
+  t->method = p.method;
+  t->lrt_threshold = p.lrt_threshold;
+  t->lrt_thr = p.method == DNV_METHOD_LRT ? p.lrt_threshold : 1.0;
+}
+
+}  // namespace dnv

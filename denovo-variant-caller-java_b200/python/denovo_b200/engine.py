@@ -1,0 +1,152 @@
+"""Host-side mirror of the reference's per-site engine seam, batched.
+
+  reference                                        here
+  ------------------------------------------------ ----------------------------------
+  new BayesInfer(shared)  (M/BayesInfer.java:39-42) TrioEngine(seq_err_rate=..., ...)
+  BayesInfer.infer(map, method) per site (:50-69)   TrioEngine.infer(counts)  per batch
+  new ReadSummary(reads, pos) (M/ReadSummary.java)  TrioEngine.pileup(...)
+  VariantsBuffer + PositionCall (M/VariantsBuffer)  TrioEngine.mendel_filter(calls)
+
+Every method goes through the C ABI (include/denovo_b200.h); host arrays are numpy,
+device arrays are torch CUDA tensors (torch is used only to own device memory).
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib as L
+
+GENOTYPES = ["AA", "AC", "AG", "AT", "CC", "CG", "CT", "GG", "GT", "TT"]
+ALLELES = "ACGT"
+
+
+def poisson_thresholds(depth, kmax=None):
+    """2^64-scaled ascending Poisson CDF thresholds for the synthetic source
+    (depth = #{k: thr[k] <= u}); exact rational arithmetic so every rank and the
+    test oracle share identical integers."""
+    from fractions import Fraction
+    if kmax is None:
+        kmax = int(depth + 12 * math.sqrt(depth) + 20)
+    lam = Fraction(depth).limit_denominator(1 << 20)
+    term, cdf, thr = Fraction(math.exp(-float(depth))).limit_denominator(1 << 200), Fraction(0), []
+    for k in range(kmax):
+        cdf += term
+        thr.append(min(int(cdf * (1 << 64)), (1 << 64) - 1))
+        term = term * lam / (k + 1)
+    return np.array(thr, np.uint64)
+
+
+class TrioEngine:
+    """One CUDA device, one set of (seq_err_rate, denovo_mut_rate, lrt_threshold, method)."""
+
+    def __init__(self, seq_err_rate=1e-2, denovo_mut_rate=1e-8, lrt_threshold=1.0, method="BAYES", device=0,
+                 force_direct=False, time_kernels=False):
+        self.lib = L.load()
+        m = L.METHODS[method.upper()] if isinstance(method, str) else int(method)
+        self.params = L.Params(seq_err_rate, denovo_mut_rate, lrt_threshold, m, device,
+                               (L.F_FORCE_DIRECT if force_direct else 0) | (L.F_TIME_KERNELS if time_kernels else 0), 0)
+        self.method = m
+        self.device = device
+        h = C.c_void_p()
+        L.check(self.lib.dnv_create(C.byref(self.params), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.dnv_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- tables / stats
+    def tables(self):
+        rel, bl, isden = np.zeros(1000), np.zeros(40), np.zeros(1000, np.uint8)
+        L.check(self.lib.dnv_get_tables(self._h, L.ptr(rel), L.ptr(bl), L.ptr(isden)))
+        return {"R": rel, "BL": bl.reshape(10, 4), "isden": isden}
+
+    def stats(self):
+        s = L.Stats()
+        L.check(self.lib.dnv_get_stats(self._h, C.byref(s)))
+        return {"n_sites": s.n_sites, "n_calls": s.n_calls, "n_hard": s.n_hard, "n_launches": s.n_launches,
+                "fused_kernel_ms": s.fused_kernel_ms}
+
+    def set_stream(self, cuda_stream):
+        """Run on the caller's CUDA stream (int handle, e.g. torch.cuda.Stream().cuda_stream); None restores."""
+        L.check(self.lib.dnv_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    # ---- READ mode
+    def infer(self, counts, dense=False, cap=None):
+        """counts: host uint16 [n,3,4] (DAD,MOM,CHILD x A,C,G,T).
+        Returns (calls CALL_DT[], dense SITE_DT[] or None)."""
+        counts = np.ascontiguousarray(counts, np.uint16).reshape(-1, 12)
+        n = counts.shape[0]
+        cap = n if cap is None else cap
+        calls = np.zeros(max(cap, 1), L.CALL_DT)
+        d = np.zeros(n, L.SITE_DT) if dense else None
+        nc = C.c_int64(0)
+        L.check(self.lib.dnv_infer_counts(self._h, L.ptr(counts), n, L.ptr(d) if dense else None,
+                                          L.ptr(calls) if cap > 0 else None, cap, C.byref(nc)))
+        return calls[:nc.value], d
+
+    def infer_host_into(self, counts_ptr, n, calls_ptr, cap):
+        """Zero-allocation host call (pinned buffers owned by the caller); returns n_calls."""
+        nc = C.c_int64(0)
+        L.check(self.lib.dnv_infer_counts(self._h, L.ptr(counts_ptr), n, None, L.ptr(calls_ptr), cap, C.byref(nc)))
+        return nc.value
+
+    def infer_device(self, d_counts, n, d_calls, cap, d_dense=None):
+        """Device-resident buffers (torch CUDA tensors or raw pointers); returns n_calls."""
+        nc = C.c_int64(0)
+        L.check(self.lib.dnv_infer_counts_device(self._h, L.ptr(d_counts), n, L.ptr(d_dense), L.ptr(d_calls), cap,
+                                                 C.byref(nc)))
+        return nc.value
+
+    def pileup(self, read_start, base_off, bases, person, site_pos):
+        read_start = np.ascontiguousarray(read_start, np.int64)
+        base_off = np.ascontiguousarray(base_off, np.int64)
+        bases = np.ascontiguousarray(bases, np.uint8)
+        person = np.ascontiguousarray(person, np.uint8)
+        site_pos = np.ascontiguousarray(site_pos, np.int64)
+        out = np.zeros((site_pos.shape[0], 3, 4), np.uint16)
+        L.check(self.lib.dnv_pileup(self._h, L.ptr(read_start), L.ptr(base_off), L.ptr(bases), L.ptr(person),
+                                    read_start.shape[0], L.ptr(site_pos), site_pos.shape[0], L.ptr(out)))
+        return out
+
+    def pileup_device(self, d_read_start, d_base_off, d_bases, d_person, n_reads, d_site_pos, n_sites, d_counts):
+        L.check(self.lib.dnv_pileup_device(self._h, L.ptr(d_read_start), L.ptr(d_base_off), L.ptr(d_bases),
+                                           L.ptr(d_person), n_reads, L.ptr(d_site_pos), n_sites, L.ptr(d_counts)))
+
+    # ---- VARIANT mode
+    def mendel_filter(self, calls, cap=None):
+        calls = np.ascontiguousarray(calls, L.VCALL_DT)
+        n = calls.shape[0]
+        cap = n if cap is None else cap
+        out = np.zeros(max(cap, 1), L.PCALL_DT)
+        no = C.c_int64(0)
+        L.check(self.lib.dnv_mendel_filter(self._h, L.ptr(calls), n, L.ptr(out) if cap > 0 else None, cap,
+                                           C.byref(no)))
+        return out[:no.value]
+
+    def mendel_filter_device(self, d_calls, n, d_out, cap):
+        no = C.c_int64(0)
+        L.check(self.lib.dnv_mendel_filter_device(self._h, L.ptr(d_calls), n, L.ptr(d_out), cap, C.byref(no)))
+        return no.value
+
+    # ---- synthetic source + calibration
+    def synth_counts_device(self, seed, first, n, d_counts, depth=30, seq_err=None, thr=None):
+        thr = poisson_thresholds(depth) if thr is None else thr
+        err_thr = int((self.params.seq_err_rate if seq_err is None else seq_err) * (1 << 32))
+        L.check(self.lib.dnv_synth_counts_device(self._h, seed, first, n, L.ptr(thr), thr.shape[0], err_thr,
+                                                 L.ptr(d_counts)))
+
+    def measure_fp64_peak(self):
+        tf, ms = C.c_double(0), C.c_double(0)
+        L.check(self.lib.dnv_measure_fp64_peak(self._h, C.byref(tf), C.byref(ms)))
+        return tf.value, ms.value

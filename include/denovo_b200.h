@@ -1,0 +1,224 @@
+/*
+ * denovo_b200.h — C ABI of the B200-native trio de novo hot path.
+ *
+ * This is the drop-in boundary: a batched replacement for the three per-site
+ * seams of alenzhao/denovo-variant-caller-java
+ * ("M/" = src/main/java/com/google/cloud/genomics/denovo/):
+ *
+ *   BayesCallResult BayesInfer.infer(Map<TrioMember,ReadSummary>, InferenceMethod)
+ *                                               M/BayesInfer.java:50-69
+ *   BayesInferenceResult DenovoBayesNet.performInference(Map<TrioMember,ReadSummary>)
+ *                                               M/DenovoBayesNet.java:247-289
+ *   new ReadSummary(List<Read>, Long)           M/ReadSummary.java:45-59
+ *   VariantsBuffer.checkAndAdd / retrieveNextCall / PositionCall.isDenovo
+ *                                               M/VariantsBuffer.java:172-222,340-355
+ *
+ * A per-site FFI call would be ~1e5x too slow, so a caller plugin
+ * (GpuReadCaller / GpuVariantCaller extends DenovoCaller, M/DenovoCaller.java:24-32)
+ * packs a whole shard and makes O(1) calls.  INTEGRATION.md shows the Java
+ * (Panama FFM) binding for every entry point below.
+ *
+ * Conventions
+ *  - plain C, no exceptions cross the ABI: every function returns DNV_OK (0) or
+ *    a negative DNV_E_* code; dnv_last_error() gives the thread-local message.
+ *  - the caller owns every buffer it passes; the library never retains caller
+ *    pointers after return and never frees them.  Device scratch lives in dnv_ctx.
+ *  - a dnv_ctx is bound to one CUDA device and is NOT re-entrant (one call in
+ *    flight per ctx); different ctxs may be driven from different host threads.
+ *  - results are returned in INPUT ORDER (deterministic), unlike the reference's
+ *    thread-race-ordered output file (M/ReadCaller.java:122-129).
+ *  - there is no CPU fallback: without a CUDA device dnv_create fails with
+ *    DNV_E_CUDA.
+ *
+ * Encodings (M/DenovoUtil.java:135-143,195-205)
+ *  - allele  A0 C1 G2 T3;  genotype AA0 AC1 AG2 AT3 CC4 CG5 CT6 GG7 GT8 TT9
+ *  - packed pileup counts: uint16 [site][person][allele], person order
+ *    DAD, MOM, CHILD (the order of maxGenoType, M/DenovoBayesNet.java:277);
+ *    24 bytes per site.
+ *  - TrioMember ordinals (used in dnv_vcall.person): CHILD0 MOM1 DAD2.
+ */
+#ifndef DENOVO_B200_H
+#define DENOVO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DNV_ABI_VERSION 1
+
+enum {
+  DNV_OK = 0,
+  DNV_E_INVALID = -1,  /* null pointer, n<0, eps/mu outside (0,1), bad enum   */
+  DNV_E_CUDA = -2,     /* CUDA runtime failure (message holds the driver string) */
+  DNV_E_CAPACITY = -3, /* output capacity too small; *n_out holds the required size */
+  DNV_E_BADBASE = -4,  /* a base outside {A,C,G,T,-}: the reference throws
+                          IllegalArgumentException (M/ReadSummary.java:55) */
+  DNV_E_UNSORTED = -5, /* VARIANT stream not sorted by start, or end <= start */
+  DNV_E_NOMEM = -6
+};
+
+/* InferenceMethod ordinals, M/DenovoUtil.java:261-288 */
+enum { DNV_METHOD_MAP = 0, DNV_METHOD_BAYES = 1, DNV_METHOD_LRT = 2 };
+
+/* dnv_params.flags */
+enum {
+  DNV_F_FORCE_DIRECT = 1u << 0, /* evaluate EVERY site with the exact direct-form
+                                   kernel (1000 exp, reference operation order);
+                                   validation only, ~30x slower */
+  DNV_F_TIME_KERNELS = 1u << 1 /* bracket the fused kernel with CUDA events on the
+                                  launching stream; read dnv_stats.fused_kernel_ms */
+};
+
+/* DenovoShared getters that reach the engine (M/DenovoShared.java:76-204). */
+typedef struct {
+  double seq_err_rate;    /* getSequenceErrorRate()  --seq_err_rate    (1e-2) */
+  double denovo_mut_rate; /* getDenovoMutationRate() --denovo_mut_rate (1e-8) */
+  double lrt_threshold;   /* getLrtThreshold()       --lrt_threshold   (1.0)  */
+  int32_t method;         /* getInferMethod()        --inference_method (BAYES) */
+  int32_t device;         /* CUDA device ordinal */
+  uint32_t flags;         /* DNV_F_* */
+  uint32_t reserved;
+} dnv_params;
+
+/* One called site = BayesCallResult + BayesInferenceResult
+ * (M/BayesInfer.java:74-106, M/BayesInferenceResult.java:23-51).  Values come
+ * from the exact direct-form evaluation of that site. */
+typedef struct {
+  int64_t site;        /* index into the input batch */
+  uint16_t counts[12]; /* DAD,MOM,CHILD x A,C,G,T (for the readCounts= field) */
+  uint8_t dad, mom, child; /* maxGenoType */
+  uint8_t is_denovo;
+  uint32_t flags;      /* bit0: decision came from the exact path (hard site) */
+  double max_ll, p, lr, log_men, log_den;
+} dnv_call; /* 80 bytes */
+
+/* Dense per-site result (optional output). */
+typedef struct {
+  double p, lr, log_men, log_den, max_ll;
+  uint8_t dad, mom, child; /* maxGenoType */
+  uint8_t is_denovo;
+  uint32_t flags;          /* bit0: exact path */
+} dnv_site_result; /* 48 bytes */
+
+/* Counters of the last inference call on this ctx. */
+typedef struct {
+  int64_t n_sites;
+  int64_t n_calls;
+  int64_t n_hard;      /* sites re-evaluated by the exact direct kernel
+                          (threshold-ambiguous or in the underflow gray zone) */
+  int64_t n_launches;  /* kernels launched by the last call */
+  double fused_kernel_ms; /* CUDA-event duration of the fused likelihood+posterior
+                             kernel(s) of the last call, summed over chunks
+                             (only when DNV_F_TIME_KERNELS is set, else 0) */
+} dnv_stats;
+
+/* One (Variant, VariantCall) pair of the VARIANT-mode stream, flattened to the
+ * fields VariantsBuffer reads (M/VariantsBuffer.java:172-306). */
+typedef struct {
+  int64_t start;       /* Variant.getStart() */
+  int64_t end;         /* Variant.getEnd() */
+  int32_t variant_id;  /* consecutive calls with equal id share one Variant */
+  int8_t gt0, gt1;     /* call.getGenotype()[0..1]; -1 = '.' */
+  uint8_t ngt;         /* call.getGenotype().size() */
+  uint8_t person;      /* TrioMember ordinal 0 CHILD, 1 MOM, 2 DAD */
+  uint8_t filter_pass; /* 1 iff info.FILTER == ["PASS"] (:245-249) */
+  uint8_t ref_len;     /* referenceBases.length(), saturated at 255 */
+  char ref_base;       /* referenceBases.charAt(0) */
+  uint8_t alt0_len;    /* length of the ALT selected by gt0 (0 if gt0 <= 0) */
+  char alt0_base;
+  uint8_t alt1_len;
+  char alt1_base;
+  uint8_t pad_[1];
+} dnv_vcall; /* 32 bytes */
+
+/* VariantsBuffer.PositionCall (M/VariantsBuffer.java:340-375) */
+typedef struct {
+  int64_t position;
+  int64_t child_index; /* index of the child record in the input stream */
+  uint8_t child, mom, dad;
+  uint8_t is_denovo;
+  uint8_t pad_[4];
+} dnv_pcall; /* 24 bytes */
+
+typedef struct dnv_ctx dnv_ctx;
+
+/* ---- lifecycle ---------------------------------------------------------- */
+/* Replaces `new BayesInfer(shared)` -> `new DenovoBayesNet(shared)`
+ * (M/ReadCaller.java:49-52, M/DenovoBayesNet.java:52-63): builds the CPTs once
+ * and uploads the site-invariant tables. */
+int dnv_create(const dnv_params *params, dnv_ctx **out);
+int dnv_destroy(dnv_ctx *ctx);
+const char *dnv_last_error(void);
+int dnv_abi_version(void);
+/* Site-invariant tables as the device holds them (for parity tests):
+ * rel[1000] = getRelationshipLogLikelihood (M/DenovoBayesNet.java:322-330),
+ * base_ll[40] = getBaseLogLikelihood[g*4+a] (:154-166),
+ * is_denovo[1000] = isDenovoMap (M/DenovoUtil.java:37-55). Any may be NULL. */
+int dnv_get_tables(dnv_ctx *ctx, double *rel, double *base_ll, uint8_t *is_denovo);
+int dnv_get_stats(dnv_ctx *ctx, dnv_stats *out);
+/* Run this ctx's kernels on the caller's CUDA stream (a cudaStream_t) so the
+ * caller can bracket calls with its own events; NULL restores the ctx's stream. */
+int dnv_set_stream(dnv_ctx *ctx, void *cuda_stream);
+
+/* ---- READ mode: pileup counts -> calls ---------------------------------- */
+/* Batched BayesInfer.infer (M/BayesInfer.java:50-69) with HOST buffers:
+ * counts[n][3][4] -> calls (input order, only is_denovo sites, like the
+ * `if (result.isDenovo())` writer, M/ReadCaller.java:122-129) and optionally a
+ * dense per-site record.  Host<->device copies are pipelined inside.
+ * *n_calls is always set; DNV_E_CAPACITY if it exceeds cap. dense may be NULL. */
+int dnv_infer_counts(dnv_ctx *ctx, const uint16_t *counts, int64_t n,
+                     dnv_site_result *dense, dnv_call *calls, int64_t cap,
+                     int64_t *n_calls);
+/* Same with DEVICE buffers already resident in HBM (d_dense may be NULL).
+ * n_calls is a host pointer.  Runs on the ctx's own stream and synchronises it. */
+int dnv_infer_counts_device(dnv_ctx *ctx, const uint16_t *d_counts, int64_t n,
+                            dnv_site_result *d_dense, dnv_call *d_calls,
+                            int64_t cap, int64_t *n_calls);
+
+/* ---- READ mode: reads -> pileup counts ---------------------------------- */
+/* Batched `new ReadSummary(reads, position)` x3 (M/ReadSummary.java:45-59,
+ * M/ReadCaller.java:138-146).  Reads are sorted by (person, start); person in
+ * packed order 0 DAD, 1 MOM, 2 CHILD.  bases = concatenated alignedSequence
+ * strings ('A','C','G','T','-'); base_off has n_reads+1 entries.  site_pos is
+ * ascending.  counts_out[n_sites][3][4] uint16. */
+int dnv_pileup(dnv_ctx *ctx, const int64_t *read_start, const int64_t *base_off,
+               const char *bases, const uint8_t *person, int64_t n_reads,
+               const int64_t *site_pos, int64_t n_sites, uint16_t *counts_out);
+int dnv_pileup_device(dnv_ctx *ctx, const int64_t *d_read_start,
+                      const int64_t *d_base_off, const char *d_bases,
+                      const uint8_t *d_person, int64_t n_reads,
+                      const int64_t *d_site_pos, int64_t n_sites,
+                      uint16_t *d_counts_out);
+
+/* ---- VARIANT mode: Mendelian-inconsistency filter ----------------------- */
+/* One shard of VariantCaller.callSimpleDenovo (M/VariantCaller.java:120-210):
+ * admission (checkAndAdd), trio interval join (retrieveNextCall) and
+ * PositionCall.isDenovo over a start-sorted stream of n (variant, call) pairs.
+ * Emits, in stream order, one dnv_pcall per child SNP for which both parents
+ * have a covering entry (is_denovo tells which ones the reference would print).
+ * *n_out is always set; DNV_E_CAPACITY if it exceeds cap. */
+int dnv_mendel_filter(dnv_ctx *ctx, const dnv_vcall *calls, int64_t n,
+                      dnv_pcall *out, int64_t cap, int64_t *n_out);
+int dnv_mendel_filter_device(dnv_ctx *ctx, const dnv_vcall *d_calls, int64_t n,
+                             dnv_pcall *d_out, int64_t cap, int64_t *n_out);
+
+/* ---- synthetic trio source (replaces the Google Genomics client) --------- */
+/* Fills d_counts[n][3][4] for global site indices first..first+n-1 with the
+ * seeded, shard-invariant generator of SURVEY.md Appendix E (specified by
+ * oracle/synth_ref.c).  thr: host array of n_thr 2^64-scaled Poisson CDF
+ * thresholds; err_thr = seq_err * 2^32. */
+int dnv_synth_counts_device(dnv_ctx *ctx, uint64_t seed, int64_t first, int64_t n,
+                            const uint64_t *thr, int32_t n_thr, uint32_t err_thr,
+                            uint16_t *d_counts);
+
+/* ---- calibration ----------------------------------------------------------- */
+/* Dependent-free DFMA chains on every SM: measured FP64 peak in TFLOP/s
+ * (MEASURED_PEAKS.json has no FP64 figure). */
+int dnv_measure_fp64_peak(dnv_ctx *ctx, double *tflops, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DENOVO_B200_H */

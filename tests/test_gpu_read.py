@@ -1,0 +1,194 @@
+"""GPU parity of the READ-mode hot path (through the C ABI) against the CPU oracle.
+
+Bar: called sites, MAP genotype triples and isDenovo bit-exact; p, LR and the
+log-likelihoods within 1e-9 relative wherever the oracle's raw sums are normal
+doubles, identical special values (0, +-inf, NaN) elsewhere."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+import denovo_b200 as D
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+G = D.GENOTYPES
+REL_TOL = 1e-9
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = json.load(open(os.path.join(HERE, "golden", "reference_junit_cases.json")))
+METHOD_FIELD = {"MAP": "denovo_map", "BAYES": "denovo_bayes", "LRT": "denovo_lrt"}
+
+
+def close(a, b, tol=REL_TOL):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    same_special = (np.isnan(a) & np.isnan(b)) | (a == b)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        rel = np.abs(a - b) <= tol * np.maximum(np.abs(a), np.abs(b))
+    return same_special | rel
+
+
+def check_against_oracle(counts, eps=1e-2, mu=1e-8, lrt=1.0, method="BAYES", force_direct=False, dense=True):
+    counts = np.ascontiguousarray(counts, np.uint16).reshape(-1, 3, 4)
+    ref = O.infer(O.params(eps, mu, lrt), counts)
+    with D.TrioEngine(eps, mu, lrt, method, force_direct=force_direct) as eng:
+        calls, d = eng.infer(counts, dense=dense)
+        stats = eng.stats()
+    want = ref[METHOD_FIELD[method]].astype(bool)
+    # ---- called sites: bit-exact set, input order
+    assert np.array_equal(calls["site"], np.nonzero(want)[0])
+    r = ref[want]
+    assert np.array_equal(calls["dad"], r["dad"]) and np.array_equal(calls["mom"], r["mom"])
+    assert np.array_equal(calls["child"], r["child"])
+    assert np.all(calls["is_denovo"] == 1) and np.all((calls["flags"] & 2) == 0)
+    assert np.array_equal(calls["counts"].reshape(-1, 3, 4), counts[want])
+    assert np.array_equal(calls["max_ll"], r["max_ll"])  # pure add/mul chain: bit-exact
+    normal = (r["l_den"] >= 2.3e-308) & (r["l_men"] >= 2.3e-308)
+    for f in ("p", "lr", "log_men", "log_den"):
+        assert np.all(close(calls[f][normal], r[f][normal])), f
+    # ---- dense record for every site
+    if dense:
+        assert np.array_equal(d["is_denovo"].astype(bool), want)
+        assert np.array_equal(d["dad"], ref["dad"]) and np.array_equal(d["mom"], ref["mom"])
+        assert np.array_equal(d["child"], ref["child"])
+        assert np.array_equal(d["max_ll"], ref["max_ll"])
+        normal = (ref["l_den"] >= 2.3e-308) & (ref["l_men"] >= 2.3e-308)
+        for f in ("p", "lr", "log_men", "log_den"):
+            ok = close(d[f][normal], ref[f][normal])
+            assert np.all(ok), (f, np.nonzero(~ok)[0][:5], d[f][normal][~ok][:5], ref[f][normal][~ok][:5])
+        # special values where the reference's raw sums flushed to exactly zero
+        z = ~normal & ((ref["l_den"] == 0) | (ref["l_men"] == 0)) & ((ref["l_den"] == 0) | (ref["l_den"] >= 2.3e-308)) \
+            & ((ref["l_men"] == 0) | (ref["l_men"] >= 2.3e-308))
+        for f in ("p", "lr"):
+            assert np.all(close(d[f][z], ref[f][z])), f
+    return ref, calls, d, stats
+
+
+def fixture_counts():
+    return np.array([[fx["DAD"], fx["MOM"], fx["CHILD"]] for fx in GOLD["fixtures"].values()], np.uint16)
+
+
+def test_tables_bit_identical_to_oracle():
+    t = O.tables(O.params())
+    with D.TrioEngine() as eng:
+        g = eng.tables()
+    assert np.array_equal(g["R"], t["R"])
+    assert np.array_equal(g["BL"], t["BL"])
+    assert np.array_equal(g["isden"], t["isden"])
+
+
+@pytest.mark.parametrize("force_direct", [False, True])
+@pytest.mark.parametrize("case", GOLD["infer_cases"], ids=lambda c: c["source"])
+def test_reference_junit_cases_through_c_abi(case, force_direct):
+    """The reference's own 21 known answers, asserted directly on the GPU path."""
+    fx = case["counts"]
+    c = np.array([[fx["DAD"], fx["MOM"], fx["CHILD"]]], np.uint16)
+    p = GOLD["params"]
+    with D.TrioEngine(p["seq_err_rate"], p["denovo_mut_rate"], p["lrt_threshold"], case["method"],
+                      force_direct=force_direct) as eng:
+        calls, d = eng.infer(c, dense=True)
+    assert [G[d["dad"][0]], G[d["mom"][0]], G[d["child"][0]]] == case["expect_map_triple"]
+    assert bool(d["is_denovo"][0]) == case["expect_is_denovo"]
+    assert len(calls) == int(case["expect_is_denovo"])
+
+
+@pytest.mark.parametrize("method", ["MAP", "BAYES", "LRT"])
+@pytest.mark.parametrize("force_direct", [False, True])
+def test_config1_10k_sites_30x(method, force_direct):
+    """BASELINE config 1: 10k synthetic sites, 30x, eps 1e-2, mu 1e-8."""
+    counts = O.synth_counts(0x5EED0001, 0, 10000, depth=30, seq_err=1e-2)
+    ref, calls, d, stats = check_against_oracle(counts, method=method, force_direct=force_direct)
+    assert len(calls) > 5
+    if not force_direct:
+        assert stats["n_hard"] <= 10
+
+
+def test_lrt_threshold_other_than_one():
+    counts = O.synth_counts(0x5EED0003, 0, 20000)
+    for thr in (10.0, 0.1, 1e6):
+        check_against_oracle(counts, lrt=thr, method="LRT")
+
+
+@pytest.mark.parametrize("mu", [1e-10, 1e-9, 1e-8, 1e-7, 1e-6])
+def test_config5_high_depth_underflow_path(mu):
+    """BASELINE config 5: 200x, eps 1e-3, mu sweep; ~4.5 % of sites have l_den == 0
+    in the reference (raw exp underflow) — decisions and special values must match."""
+    counts = O.synth_counts(0x5EED0005, 0, 20000, depth=200, seq_err=1e-3)
+    ref, calls, d, stats = check_against_oracle(counts, eps=1e-3, mu=mu, method="BAYES")
+    under = (ref["l_den"] < 2.3e-308) | (ref["l_men"] < 2.3e-308)
+    assert under.mean() > 0.01
+    zero = ref["l_den"] == 0
+    assert np.all(d["p"][zero & (ref["l_men"] > 0)] == 0.0)
+    assert np.all(np.isneginf(d["log_den"][zero]))
+    check_against_oracle(counts[:4000], eps=1e-3, mu=mu, method="LRT", lrt=3.0)
+    check_against_oracle(counts[:4000], eps=1e-3, mu=mu, method="MAP")
+
+
+def test_fixture_pileups_all_methods_and_eps():
+    c = fixture_counts()
+    for eps in (1e-2, 1e-3, 0.2):
+        for method in ("MAP", "BAYES", "LRT"):
+            check_against_oracle(c, eps=eps, method=method)
+
+
+def test_edge_cases():
+    rng = np.random.default_rng(7)
+    blocks = [np.zeros((3, 3, 4), np.uint16),                         # zero depth
+              np.full((2, 3, 4), 65535, np.uint16),                   # maximum counts: everything underflows
+              rng.integers(0, 3, (500, 3, 4)).astype(np.uint16),      # very shallow
+              rng.integers(0, 2000, (500, 3, 4)).astype(np.uint16),   # deep, noisy: gray zone / table fallback
+              rng.integers(0, 40, (2000, 3, 4)).astype(np.uint16)]    # noisy 4-allele pileups
+    one = np.zeros((64, 3, 4), np.uint16)                             # single-allele deep columns
+    for i in range(64):
+        one[i, :, i % 4] = [1000 + i, 1200, 900 + 7 * i]
+    c = np.concatenate(blocks + [one])
+    for method in ("BAYES", "MAP", "LRT"):
+        ref, calls, d, stats = check_against_oracle(c, method=method)
+    z = np.zeros((1, 3, 4), np.uint16)
+    ref, calls, d, _ = check_against_oracle(z, method="MAP")
+    assert [G[d["dad"][0]], G[d["mom"][0]], G[d["child"][0]]] == ["AC", "AC", "AC"]
+
+
+def test_threshold_knife_edge_sites_go_to_exact_path():
+    """Sites built so that p is as close to 0.5 as integer counts allow must agree
+    with the oracle; any site within 1e-9 of the threshold is decided by the
+    exact direct-form kernel (n_hard counts them)."""
+    base = np.array([[0, 58, 0, 2], [0, 51, 0, 2], [0, 28, 0, 8]], np.uint16)  # p = 0.52199 fixture
+    var = []
+    for a in range(0, 12):
+        for b in range(20, 40):
+            c = base.copy()
+            c[2, 3] = a
+            c[2, 1] = b
+            var.append(c)
+    ref, calls, d, stats = check_against_oracle(np.array(var), method="BAYES")
+    assert np.abs(ref["p"] - 0.5).min() < 0.2
+
+
+def test_empty_and_capacity():
+    with D.TrioEngine() as eng:
+        calls, d = eng.infer(np.zeros((0, 3, 4), np.uint16), dense=True)
+        assert len(calls) == 0 and len(d) == 0
+        counts = O.synth_counts(0x5EED0001, 0, 10000)
+        full, _ = eng.infer(counts)
+        assert len(full) > 3
+        with pytest.raises(D.DenovoError) as ei:
+            eng.infer(counts, cap=2)
+        assert ei.value.code == D.DNV_E_CAPACITY
+        assert str(len(full)) in str(ei.value)  # required size is reported
+        again, _ = eng.infer(counts)            # ctx still usable, idempotent
+        assert again.tobytes() == full.tobytes()
+
+
+def test_host_path_chunking_matches_single_chunk():
+    """The host API pipelines 2M-site chunks; results must not depend on chunking."""
+    counts = O.synth_counts(0x5EED0003, 0, 5000)
+    big = np.tile(counts, (1000, 1, 1))  # 5M sites > 2 chunks
+    with D.TrioEngine() as eng:
+        small, _ = eng.infer(counts)
+        calls, _ = eng.infer(big)
+    assert len(calls) == 1000 * len(small)
+    assert np.array_equal(calls["site"] % 5000, np.tile(small["site"], 1000))
+    assert np.all(np.diff(calls["site"]) > 0)
+    assert np.array_equal(calls["p"], np.tile(small["p"], 1000))

@@ -1,0 +1,63 @@
+"""Full-size (BASELINE config 3: 10M sites) checks through size-independent
+properties: shard invariance, sortedness, agreement with the exact direct-form
+kernel on the same device, and the oracle on a random subsample."""
+import numpy as np
+import pytest
+
+import denovo_b200 as D
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+N = 10_000_000
+
+
+def test_synthetic_source_matches_its_cpu_specification():
+    import torch
+    n = 50_000
+    for depth, eps, seed in ((30, 1e-2, 0x5EED0003), (200, 1e-3, 0x5EED0005)):
+        thr = D.poisson_thresholds(depth)
+        assert np.array_equal(thr, O.poisson_thresholds(depth))
+        with D.TrioEngine(eps) as eng:
+            buf = torch.empty((n, 12), dtype=torch.int16, device="cuda")
+            eng.synth_counts_device(seed, 1234567, n, buf, depth=depth)
+            got = buf.cpu().numpy().view(np.uint16).reshape(n, 3, 4)
+        want = O.synth_counts(seed, 1234567, n, depth=depth, seq_err=eps)
+        assert np.array_equal(got, want)
+        assert abs(got.sum(axis=2).mean() - depth) < 0.2
+
+
+@pytest.mark.parametrize("method", ["BAYES", "MAP"])
+def test_10m_sites_properties(method):
+    import torch
+    with D.TrioEngine(method=method) as eng, D.TrioEngine(method=method, force_direct=True) as exact:
+        counts = torch.empty((N, 12), dtype=torch.int16, device="cuda")
+        eng.synth_counts_device(0x5EED0003, 0, N, counts, depth=30)
+        cap = 200_000
+        calls = torch.zeros((cap, D.CALL_DT.itemsize), dtype=torch.uint8, device="cuda")
+        n_calls = eng.infer_device(counts, N, calls, cap)
+        st = eng.stats()
+        c_all = calls[:n_calls].cpu().numpy().view(D.CALL_DT).reshape(-1)
+        assert 0.0005 * N < n_calls < 0.02 * N
+        assert np.all(np.diff(c_all["site"]) > 0)            # input order
+        assert st["n_hard"] < 1e-4 * N
+        # shard invariance: two halves = whole (what interval sharding across ranks relies on)
+        half = N // 2
+        n1 = eng.infer_device(counts[:half], half, calls, cap)
+        a = calls[:n1].cpu().numpy().view(D.CALL_DT).reshape(-1).copy()
+        n2 = eng.infer_device(counts[half:], N - half, calls, cap)
+        b = calls[:n2].cpu().numpy().view(D.CALL_DT).reshape(-1).copy()
+        b["site"] += half
+        assert np.concatenate([a, b]).tobytes() == c_all.tobytes()
+        # fast path == exact direct-form kernel on a 1M-site window
+        lo, m = 3_000_000, 1_000_000
+        n3 = exact.infer_device(counts[lo:lo + m], m, calls, cap)
+        e = calls[:n3].cpu().numpy().view(D.CALL_DT).reshape(-1).copy()
+        e["site"] += lo
+        sel = c_all[(c_all["site"] >= lo) & (c_all["site"] < lo + m)]
+        assert e.tobytes() == sel.tobytes()
+        # oracle on a strided subsample
+        idx = np.arange(0, N, 997)[:10000]
+        sub = counts[torch.from_numpy(idx).cuda()].cpu().numpy().view(np.uint16).reshape(-1, 3, 4)
+        ref = O.infer(O.params(), sub)
+        want = ref["denovo_bayes" if method == "BAYES" else "denovo_map"].astype(bool)
+        assert np.array_equal(np.isin(idx, c_all["site"]), want)
