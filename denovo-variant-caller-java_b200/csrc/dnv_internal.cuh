@@ -20,9 +20,11 @@ struct Tables {
   uint32_t isden[32];     // isDenovoMap as a 1000-bit mask, M/DenovoUtil.java:37-55
   uint8_t nden[100];      // 10 - |mendelianGenotypes(d,m)|, M/DenovoBayesNet.java:98
   // linear-domain fast path (factored form)
-  double pw_m[2][kPowTable];   // mantissa in [1,2) of r_j^k, j=0 hom ratio, j=1 het ratio
+  double pw_inv[2][kPowTable]; // r_j^-i, j=0 hom ratio, j=1 het ratio (may underflow to 0: exact)
+  double pw_m[2][kPowTable];   // mantissa in [1,2) of r_j^k
   int32_t pw_e[2][kPowTable];  // binary exponent of r_j^k
-  double c_hi[2], c_lo[2];     // log2(r_j) split hi/lo for k >= kPowTable
+  int32_t fast_ok;             // both ratios > 1 (always, unless eps is absurdly large)
+  int32_t pad_;
   double mm2;                  // log2(eps/3)
   double k_men;                // ((1-mu)/4)/64
   double k_den[4];             // (mu/256)/nDen for nDen = 9,8,7,6

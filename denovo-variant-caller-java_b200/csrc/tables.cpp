@@ -80,17 +80,12 @@ void build_tables(const dnv_params& p, Tables* t) {
   const long double log2r[2] = {
       (logl(1.0L - le) - (logl(le) - logl(3.0L))) * l2e,                       // hom match / mismatch
       ((logl(1.0L - 2.0L * le / 3.0L) - logl(2.0L)) - (logl(le) - logl(3.0L))) * l2e};  // het match / mismatch
-  for (int j = 0; j < 2; j++) {
-    for (int k = 0; k < kPowTable; k++) pow_entry(log2r[j], k, &t->pw_m[j][k], &t->pw_e[j][k]);
-    // hi part keeps 30 significant bits so k*hi is exact for k < 2^22
-    double hi = (double)log2r[j];
-    uint64_t bits;
-    std::memcpy(&bits, &hi, 8);
-    bits &= ~((1ULL << 23) - 1);
-    std::memcpy(&hi, &bits, 8);
-    t->c_hi[j] = hi;
-    t->c_lo[j] = (double)(log2r[j] - (long double)hi);
-  }
+  for (int j = 0; j < 2; j++)
+    for (int k = 0; k < kPowTable; k++) {
+      pow_entry(log2r[j], k, &t->pw_m[j][k], &t->pw_e[j][k]);
+      t->pw_inv[j][k] = (double)exp2l(-log2r[j] * (long double)k);
+    }
+  t->fast_ok = (log2r[0] > 0.0L && log2r[1] > 0.0L) ? 1 : 0;
   t->mm2 = (double)((logl(le) - logl(3.0L)) * l2e);
   t->k_men = (1.0 - mu) / 4 / 64;
   const int nd[4] = {9, 8, 7, 6};

@@ -1,22 +1,27 @@
 // trio_fast.cuh — fused likelihood + trio-posterior kernel (kernel (b) of the
-// north star), hand-written for sm_100a.  One thread owns one site.
+// north star), hand-written for sm_100a.  One thread owns one site; a CTA walks
+// tiles of 128 sites whose 3 KB of packed counts are staged into shared memory
+// by TMA bulk copies (cp.async.bulk + mbarrier, double buffered).
 //
-// BAYES / LRT decisions use the factored LINEAR-domain form:
-//   exp(L_p[g]) = 2^(N_p*log2(eps/3)) * r_hom^k  (g = XX, k = n_X)
-//               = 2^(N_p*log2(eps/3)) * r_het^k  (g = XY, k = n_X + n_Y)
-// with r^k = mantissa * 2^exponent read from two small shared-memory tables
-// (counts are integers, so no exp() is evaluated at all), each person is
-// rescaled by a power of two (exact), and the 10x10x10 sum collapses to the
-// sparse straight-line code of trio_sparse_gen.cuh (335 FP64 instructions
-// instead of 2000 dense FMAs + 30 exp).  The unshifted magnitudes
-// log2(Lden), log2(Lmen) are tracked so the reference's raw-exp underflow
-// semantics are reproduced: a site whose decision could depend
-// on rounding (|den - T*men| <= 1e-9 relative) or on subnormal / flushed terms
-// (gray zone) is NOT decided here — it is appended to the hard list and
-// re-evaluated by the exact direct-form kernel (trio_exact.cuh).
+// BAYES / LRT decisions use the factored LINEAR-domain form.
+// With N_p reads of person p and mismatch likelihood q = eps/3,
+//   exp(L_p[XX]) = q^N_p * r_hom^(n_X)        r_hom = (1-eps)/q
+//   exp(L_p[XY]) = q^N_p * r_het^(n_X+n_Y)    r_het = ((1-2eps/3)/2)/q
+// Counts are integers, so every power comes from a shared-memory table and NO
+// exp() is evaluated: inside a zygosity class values are taken relative to the
+// class maximum (r^-(kmax-k), one LDS.64), and the two class maxima r^kmax are
+// read as (mantissa, exponent) pairs so each person is rescaled by an exact
+// power of two.  The 10x10x10 sum then collapses to the sparse straight-line
+// code of trio_sparse_gen.cuh (335 FP64 instructions instead of 2000 dense FMAs
+// + 30 exp).  The unshifted magnitudes log2(Lden), log2(Lmen) are tracked so the
+// reference's raw-exp underflow semantics are reproduced: a site
+// whose decision could depend on rounding (|den - T*men| <= 1e-9 relative), on
+// subnormal / flushed terms (gray zone), or whose depth exceeds the tables is
+// NOT decided here — it goes to the hard list and is re-evaluated by the exact
+// direct-form kernel (trio_exact.cuh).
 //
-// MAP decisions (and the maxGenoType of the dense record) use the exact
-// log-domain sweep: bit-identical lls, strict '>' in dad-major order.
+// MAP decisions (and maxGenoType of the dense record) use the exact log-domain
+// sweep: bit-identical lls, strict '>' in dad-major order.
 #pragma once
 #include "dnv_internal.cuh"
 #include "trio_exact.cuh"
@@ -24,50 +29,70 @@
 namespace dnv {
 
 constexpr int kFastThreads = 128;
+constexpr int kTileBytes = kFastThreads * 24;
 
 struct FastShared {
-  double pw_m[2][kPowTable];
-  int32_t pw_e[2][kPowTable];
+  double pw_inv[2][kPowTable];  // r_j^-i
+  double pw_m[2][kPowTable];    // mantissa of r_j^k
+  int32_t pw_e[2][kPowTable];   // exponent of r_j^k
+  alignas(16) unsigned char tile[2][kTileBytes];
+  alignas(8) unsigned long long bar[2];
 };
 
-// r_j^k as (mantissa, exponent)
-__device__ __forceinline__ void pow_lookup(const FastShared& s, const Tables* __restrict__ tab, int j,
-                                           int k, double& m, int& e) {
-  if (k < kPowTable) {
-    m = s.pw_m[j][k];
-    e = s.pw_e[j][k];
-  } else {  // deep pileup: k*log2(r) in hi/lo parts, k*hi is exact
-    const double kd = (double)k;
-    const double t_hi = kd * tab->c_hi[j];
-    const double t_lo = kd * tab->c_lo[j];
-    const double fl = floor(t_hi + t_lo);
-    m = exp2((t_hi - fl) + t_lo);
-    e = (int)fl;
-  }
+// ---- TMA bulk copy + mbarrier (PTX; SASS: UBLKCP / SYNCS) -------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                             unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
-// per-person scaled genotype likelihoods ev[10] (max in [1,4)), returns the
-// binary exponent that was divided out.
-__device__ __forceinline__ int person_linear(const FastShared& s, const Tables* __restrict__ tab,
-                                             const uint16_t* n, double* ev) {
-  double m[10];
-  int e[10];
-#pragma unroll
-  for (int g = 0; g < 10; g++) {
-    const int a0 = kGenoA0[g], a1 = kGenoA1[g];
-    const bool hom = a0 == a1;
-    const int k = hom ? (int)n[a0] : (int)n[a0] + (int)n[a1];
-    pow_lookup(s, tab, hom ? 0 : 1, k, m[g], e[g]);
-  }
-  int emax = e[0];
-#pragma unroll
-  for (int g = 1; g < 10; g++) emax = max(emax, e[g]);
-#pragma unroll
-  for (int g = 0; g < 10; g++) {
-    const int sh = e[g] - emax;  // <= 0
-    const int hi = __double2hiint(m[g]) + (sh << 20);
-    ev[g] = (sh < -1000) ? 0.0 : __hiloint2double(hi, __double2loint(m[g]));
-  }
+// 2^sh * m for m in [1,2), sh <= 0 (flushes below 2^-1000: irrelevant at 1e-9, see zone logic)
+__device__ __forceinline__ double scale_pow2(double m, int sh) {
+  const int hi = __double2hiint(m) + (sh << 20);
+  return (sh < -1000) ? 0.0 : __hiloint2double(hi, __double2loint(m));
+}
+
+// Scaled genotype likelihoods ev[10] of one person (largest entry in [1,2));
+// returns the binary exponent divided out.  All k < kPowTable (checked by caller).
+__device__ __forceinline__ int person_linear(const FastShared& s, const int* n, double* ev) {
+  const int k_hom = max(max(n[0], n[1]), max(n[2], n[3]));
+  const int s01 = n[0] + n[1], s02 = n[0] + n[2], s03 = n[0] + n[3], s12 = n[1] + n[2], s13 = n[1] + n[3],
+            s23 = n[2] + n[3];
+  const int k_het = max(max(max(s01, s02), max(s03, s12)), max(s13, s23));
+  const int e1 = s.pw_e[0][k_hom], e2 = s.pw_e[1][k_het];
+  const int emax = max(e1, e2);
+  const double sc1 = scale_pow2(s.pw_m[0][k_hom], e1 - emax);
+  const double sc2 = scale_pow2(s.pw_m[1][k_het], e2 - emax);
+  ev[0] = sc1 * s.pw_inv[0][k_hom - n[0]];
+  ev[1] = sc2 * s.pw_inv[1][k_het - s01];
+  ev[2] = sc2 * s.pw_inv[1][k_het - s02];
+  ev[3] = sc2 * s.pw_inv[1][k_het - s03];
+  ev[4] = sc1 * s.pw_inv[0][k_hom - n[1]];
+  ev[5] = sc2 * s.pw_inv[1][k_het - s12];
+  ev[6] = sc2 * s.pw_inv[1][k_het - s13];
+  ev[7] = sc1 * s.pw_inv[0][k_hom - n[2]];
+  ev[8] = sc2 * s.pw_inv[1][k_het - s23];
+  ev[9] = sc1 * s.pw_inv[0][k_hom - n[3]];
   return emax;
 }
 
@@ -84,93 +109,160 @@ __device__ __forceinline__ int magnitude_zone(double v, int s2_floor) {
   return (s2_floor - 899 + 1 < -1077) ? 1 : 2;
 }
 
-template <bool kDense>
-__global__ void __launch_bounds__(kFastThreads)
+struct LinOut {
+  double den_s, men_s, s2;
+  bool dn, hard;
+  int zd, zm;
+};
+
+// the factored linear-domain evaluation of one site (BAYES / LRT decision)
+__device__ __forceinline__ void linear_site(const FastShared& s, const int* c, double k_men, double kd9,
+                                            double kd8, double kd7, double kd6, double thr, double mm2,
+                                            int method, double lrt_threshold, LinOut& o) {
+  const int nd = (c[0] + c[1]) + (c[2] + c[3]), nm = (c[4] + c[5]) + (c[6] + c[7]),
+            nc = (c[8] + c[9]) + (c[10] + c[11]);
+  if (max(nd, max(nm, nc)) >= kPowTable) {  // deeper than the tables: exact path decides
+    o.hard = true; o.dn = false; o.zd = o.zm = 2; o.den_s = o.men_s = o.s2 = 0.0;
+    return;
+  }
+  double a[10], b[10], e[10];
+  const int ed = person_linear(s, c + 0, a);
+  const int em = person_linear(s, c + 4, b);
+  const int ec = person_linear(s, c + 8, e);
+  const double s2 = fma((double)(nd + nm + nc), mm2, (double)(ed + em + ec));
+  const int s2_floor = (int)floor(s2);
+  double men_s, den_s;
+  {
+#include "trio_sparse_gen.cuh"
+  }
+  const int zd = magnitude_zone(den_s, s2_floor), zm = magnitude_zone(men_s, s2_floor);
+  bool dn = false, hard = false;
+  if (zd == 2 || zm == 2) {
+    hard = true;
+  } else if (zd == 0 && zm == 0) {
+    const double rhs = thr * men_s;
+    dn = den_s > rhs;
+    hard = fabs(den_s - rhs) <= 1e-9 * fabs(rhs);
+  } else {
+    // reference special values: l_den == 0 and/or l_men == 0
+    const bool den0 = zd == 1, men0 = zm == 1;
+    if (method == DNV_METHOD_LRT) {
+      const double lr = den0 ? (men0 ? NAN : 0.0) : INFINITY;
+      dn = lr > lrt_threshold;
+    } else {
+      dn = !den0 && men0;  // p = 1 > 0.5 ; p = 0 or NaN -> false
+    }
+  }
+  o.den_s = den_s; o.men_s = men_s; o.s2 = s2; o.dn = dn; o.hard = hard; o.zd = zd; o.zm = zm;
+}
+
+__device__ __forceinline__ void unpack_counts(const uint2* p, int* c) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const uint2 v = p[i];
+    c[4 * i + 0] = (int)(v.x & 0xFFFF);
+    c[4 * i + 1] = (int)(v.x >> 16);
+    c[4 * i + 2] = (int)(v.y & 0xFFFF);
+    c[4 * i + 3] = (int)(v.y >> 16);
+  }
+}
+
+// kLin: evaluate the linear-domain posterior (BAYES/LRT decision, dense values)
+// kMap: evaluate the exact log-domain argmax (MAP decision, dense maxGenoType)
+template <bool kLin, bool kMap, bool kDense>
+__global__ void __launch_bounds__(kFastThreads, kLin && !kMap ? 3 : 2)
 trio_fast_kernel(const Tables* __restrict__ tab, const uint16_t* __restrict__ counts, int64_t n,
                  uint32_t* __restrict__ bits, uint32_t* __restrict__ hard_list,
                  unsigned long long* __restrict__ counters, dnv_site_result* __restrict__ dense) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FastShared& s = *reinterpret_cast<FastShared*>(smem_raw);
-  double* s_rel = reinterpret_cast<double*>(smem_raw + sizeof(FastShared));  // only when MAP/dense
+  double* s_rel = reinterpret_cast<double*>(smem_raw + sizeof(FastShared));  // kMap only
   uint32_t* s_isden = reinterpret_cast<uint32_t*>(s_rel + 1000);
 
-  const int method = tab->method;
-  const bool need_map = kDense || method == DNV_METHOD_MAP;
-  const bool need_lin = kDense || method != DNV_METHOD_MAP;
-  if (need_lin) {
+  const int64_t n_tiles = (n + kFastThreads - 1) / kFastThreads;
+  const bool tma_ok = (reinterpret_cast<uintptr_t>(counts) & 15) == 0;
+  if (threadIdx.x == 0) {
+    mbar_init(&s.bar[0], 1);
+    mbar_init(&s.bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (kLin) {
     for (int i = threadIdx.x; i < 2 * kPowTable; i += blockDim.x) {
+      (&s.pw_inv[0][0])[i] = (&tab->pw_inv[0][0])[i];
       (&s.pw_m[0][0])[i] = (&tab->pw_m[0][0])[i];
       (&s.pw_e[0][0])[i] = (&tab->pw_e[0][0])[i];
     }
   }
-  if (need_map) stage_exact_tables(tab, s_rel, s_isden);
+  if (kMap) stage_exact_tables(tab, s_rel, s_isden);
   __syncthreads();
 
+  const int method = tab->method;
+  const bool lin_ok = tab->fast_ok != 0;
   const double k_men = tab->k_men;
   const double kd9 = tab->k_den[0], kd8 = 2.0 * tab->k_den[1], kd7 = 4.0 * tab->k_den[2],
                kd6 = 4.0 * tab->k_den[3];
-  const double thr = tab->lrt_thr, mm2 = tab->mm2;
-  const double hm = tab->hm, ht = tab->ht, mm = tab->mm;
+  const double thr = tab->lrt_thr, mm2 = tab->mm2, lrt_threshold = tab->lrt_threshold;
 
-  for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n; base += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t site = base + threadIdx.x;
+  // tile t is bulk-copied when it is full (its byte count is a multiple of 16)
+  auto issue = [&](int64_t t, int buf) {
+    if (threadIdx.x == 0 && tma_ok && (t + 1) * kFastThreads <= n) {
+      mbar_expect_tx(&s.bar[buf], kTileBytes);
+      tma_bulk_g2s(s.tile[buf], counts + t * kFastThreads * 12, kTileBytes, &s.bar[buf]);
+    }
+  };
+  uint32_t phase[2] = {0, 0};
+  int buf = 0;
+  int64_t t = blockIdx.x;
+  if (t < n_tiles) issue(t, 0);
+  for (; t < n_tiles; t += gridDim.x, buf ^= 1) {
+    const int64_t t_next = t + gridDim.x;
+    if (t_next < n_tiles) issue(t_next, buf ^ 1);
+    const int64_t site = t * kFastThreads + threadIdx.x;
+    int c[12];
+    if (tma_ok && (t + 1) * kFastThreads <= n) {
+      mbar_wait(&s.bar[buf], phase[buf]);
+      phase[buf] ^= 1;
+      unpack_counts(reinterpret_cast<const uint2*>(s.tile[buf] + threadIdx.x * 24), c);
+    } else if (site < n) {
+      unpack_counts(reinterpret_cast<const uint2*>(counts + site * 12), c);
+    }
+    __syncthreads();  // every thread has its counts in registers: the buffer may be refilled
+
     bool dn = false, hard = false;
     if (site < n) {
-      uint16_t c[12];
-      load_counts(counts, site, c);
       dnv_site_result o;
-      if (need_lin) {
-        double a[10], b[10], e[10];
-        const int ed = person_linear(s, tab, c + 0, a);
-        const int em = person_linear(s, tab, c + 4, b);
-        const int ec = person_linear(s, tab, c + 8, e);
-        int ntot = 0;
-#pragma unroll
-        for (int k = 0; k < 12; k++) ntot += c[k];
-        const double s2 = fma((double)ntot, mm2, (double)(ed + em + ec));
-        const int s2_floor = (int)floor(fmax(s2, -2.0e9));
-        double men_s, den_s;
-        {
-#include "trio_sparse_gen.cuh"
+      if (kLin) {
+        LinOut lo;
+        if (lin_ok) {
+          linear_site(s, c, k_men, kd9, kd8, kd7, kd6, thr, mm2, method, lrt_threshold, lo);
+        } else {  // eps so large that r <= 1: the table scheme does not apply
+          lo.hard = true; lo.dn = false; lo.zd = lo.zm = 2; lo.den_s = lo.men_s = lo.s2 = 0.0;
         }
-        const int zd = magnitude_zone(den_s, s2_floor), zm = magnitude_zone(men_s, s2_floor);
-        if (zd == 2 || zm == 2) {
-          hard = true;
-        } else if (zd == 0 && zm == 0) {
-          const double rhs = thr * men_s;
-          dn = den_s > rhs;
-          hard = fabs(den_s - rhs) <= 1e-9 * fabs(rhs);
-          if (kDense) {
-            o.p = den_s / (den_s + men_s);
-            o.lr = den_s / men_s;
-            const double ln2 = 0.693147180559945309417;
-            o.log_den = fma(s2, ln2, log(den_s));
-            o.log_men = fma(s2, ln2, log(men_s));
-          }
-        } else {
-          // reference special values: l_den == 0 and/or l_men == 0
-          const bool den0 = zd == 1, men0 = zm == 1;
-          if (method == DNV_METHOD_LRT) {
-            const double lr = den0 ? (men0 ? NAN : 0.0) : INFINITY;
-            dn = lr > tab->lrt_threshold;
+        dn = lo.dn;
+        hard = lo.hard;
+        if (kDense && !hard) {
+          const double ln2 = 0.693147180559945309417;
+          const bool den0 = lo.zd == 1, men0 = lo.zm == 1;
+          if (!den0 && !men0) {
+            o.p = lo.den_s / (lo.den_s + lo.men_s);
+            o.lr = lo.den_s / lo.men_s;
           } else {
-            dn = !den0 && men0;  // p = 1 > 0.5 ; p = 0 or NaN -> false
-          }
-          if (kDense) {
-            const double ln2 = 0.693147180559945309417;
             o.p = den0 ? (men0 ? NAN : 0.0) : 1.0;
             o.lr = den0 ? (men0 ? NAN : 0.0) : INFINITY;
-            o.log_den = den0 ? -INFINITY : fma(s2, ln2, log(den_s));
-            o.log_men = men0 ? -INFINITY : fma(s2, ln2, log(men_s));
           }
+          o.log_den = den0 ? -INFINITY : fma(lo.s2, ln2, log(lo.den_s));
+          o.log_men = men0 ? -INFINITY : fma(lo.s2, ln2, log(lo.men_s));
         }
       }
-      if (need_map) {
+      if (kMap) {
         // exact log-domain sweep, M/DenovoBayesNet.java:260-278
+        uint16_t cu[12];
+#pragma unroll
+        for (int k = 0; k < 12; k++) cu[k] = (uint16_t)c[k];
         double Ld[10], Lm[10], Lc[10];
-        exact_read_loglik(c + 0, hm, ht, mm, Ld);
-        exact_read_loglik(c + 4, hm, ht, mm, Lm);
-        exact_read_loglik(c + 8, hm, ht, mm, Lc);
+        exact_read_loglik(cu + 0, tab->hm, tab->ht, tab->mm, Ld);
+        exact_read_loglik(cu + 4, tab->hm, tab->ht, tab->mm, Lm);
+        exact_read_loglik(cu + 8, tab->hm, tab->ht, tab->mm, Lc);
         double max_ll = -INFINITY;
         int best = 0;
 #pragma unroll 1
@@ -186,8 +278,7 @@ trio_fast_kernel(const Tables* __restrict__ tab, const uint16_t* __restrict__ co
             }
           }
         }
-        const bool map_dn = (s_isden[best >> 5] >> (best & 31)) & 1u;
-        if (method == DNV_METHOD_MAP) dn = map_dn;
+        if (method == DNV_METHOD_MAP) dn = (s_isden[best >> 5] >> (best & 31)) & 1u;
         if (kDense) {
           o.max_ll = max_ll;
           o.dad = (uint8_t)(best / 100); o.mom = (uint8_t)((best / 10) % 10); o.child = (uint8_t)(best % 10);
@@ -212,27 +303,30 @@ trio_fast_kernel(const Tables* __restrict__ tab, const uint16_t* __restrict__ co
   }
 }
 
-inline int launch_trio_fast(dnv_ctx* ctx, const uint16_t* d_counts, int64_t n, dnv_site_result* d_dense) {
+template <bool kLin, bool kMap, bool kDense>
+static int launch_fast_variant(dnv_ctx* ctx, const uint16_t* d_counts, int64_t n, dnv_site_result* d_dense) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-  const size_t smem = sizeof(FastShared) + 1000 * sizeof(double) + 32 * sizeof(uint32_t);
-  static bool attr_set = false;
-  if (!attr_set) {
-    DNV_CUDA(cudaFuncSetAttribute(trio_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    DNV_CUDA(cudaFuncSetAttribute(trio_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  const size_t smem = sizeof(FastShared) + (kMap ? 1000 * sizeof(double) + 32 * sizeof(uint32_t) : 0);
+  auto kern = trio_fast_kernel<kLin, kMap, kDense>;
+  DNV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  DNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFastThreads, smem));
+  if (per_sm < 1) per_sm = 1;
   const int64_t want = (n + kFastThreads - 1) / kFastThreads;
-  const int64_t persistent = (int64_t)sms * 4;
+  const int64_t persistent = (int64_t)sms * per_sm;  // one resident wave, each CTA walks its tiles
   const int grid = (int)(want < persistent ? want : persistent);
-  if (d_dense)
-    trio_fast_kernel<true><<<grid, kFastThreads, smem, ctx->stream>>>(ctx->d_tab, d_counts, n, ctx->d_bits,
-                                                                     ctx->d_hard_list, ctx->d_counters, d_dense);
-  else
-    trio_fast_kernel<false><<<grid, kFastThreads, smem, ctx->stream>>>(ctx->d_tab, d_counts, n, ctx->d_bits,
-                                                                      ctx->d_hard_list, ctx->d_counters, d_dense);
+  kern<<<grid, kFastThreads, smem, ctx->stream>>>(ctx->d_tab, d_counts, n, ctx->d_bits, ctx->d_hard_list,
+                                                  ctx->d_counters, d_dense);
   DNV_CUDA(cudaGetLastError());
   return DNV_OK;
+}
+
+inline int launch_trio_fast(dnv_ctx* ctx, const uint16_t* d_counts, int64_t n, dnv_site_result* d_dense) {
+  const bool map = ctx->prm.method == DNV_METHOD_MAP;
+  if (d_dense) return launch_fast_variant<true, true, true>(ctx, d_counts, n, d_dense);
+  if (map) return launch_fast_variant<false, true, false>(ctx, d_counts, n, nullptr);
+  return launch_fast_variant<true, false, false>(ctx, d_counts, n, nullptr);
 }
 
 }  // namespace dnv

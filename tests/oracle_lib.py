@@ -128,9 +128,8 @@ def poisson_thresholds(depth, kmax=None):
     import math
     if kmax is None:
         kmax = int(depth + 12 * math.sqrt(depth) + 20)
-    lam = Fraction(depth).limit_denominator(1 << 20)
-    e_neg = Fraction(math.exp(-float(depth))).limit_denominator(1 << 200)
-    term, cdf, thr = e_neg, Fraction(0), []
+    lam = Fraction(depth).limit_denominator(1 << 20)  # exact rationals: no underflow at depth 200+
+    term, cdf, thr = Fraction(math.exp(-float(depth))), Fraction(0), []
     for k in range(kmax):
         cdf += term
         thr.append(min(int(cdf * (1 << 64)), (1 << 64) - 1))
