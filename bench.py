@@ -178,18 +178,14 @@ def main():
     cap = max(n // 50, 1024)
     d_calls = torch.zeros((cap, D.CALL_DT.itemsize), dtype=torch.uint8, device="cuda")
 
+    from denovo_b200 import sharding
+
     def gather_calls(n_calls):
         """NCCL gather of call records to rank 0 (the reference's shared PrintWriter, DenovoCaller.java:56-59)."""
         if world == 1:
             return n_calls
-        cnt = torch.tensor([n_calls], dtype=torch.int64, device="cuda")
-        allc = [torch.zeros_like(cnt) for _ in range(world)]
-        dist.all_gather(allc, cnt)
-        mx = int(max(int(c.item()) for c in allc))
-        send = d_calls[:mx].contiguous()
-        recv = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
-        dist.gather(send, recv, dst=0)
-        return sum(int(c.item()) for c in allc)
+        _, counts = sharding.gather_records(d_calls[:n_calls], dist)
+        return sum(counts)
 
     def step():
         with torch.cuda.stream(stream):

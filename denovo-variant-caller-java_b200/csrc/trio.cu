@@ -107,39 +107,78 @@ scatter_calls_kernel(const uint32_t* __restrict__ bits, int64_t n_words,
 }
 
 // ---------------------------------------------------------------- K4 call records
+// One WARP per called site: lanes split the 1000 genotype triples (idx = lane + 32*i),
+// every ll is the reference's exact add chain, so maxGenoType / max_ll are
+// bit-exact (ties -> lowest dad-major index, as the reference's strict '>');
+// the two exp() sums are lane partials combined in a fixed shuffle order
+// (values agree with the sequential reference sum to ~1e-15 relative).
 __global__ void __launch_bounds__(kExactThreads)
 call_details_kernel(const Tables* __restrict__ tab, const uint16_t* __restrict__ counts,
                     int64_t site_base, const int64_t* __restrict__ call_idx,
-                    const unsigned long long* __restrict__ counters,
-                    const uint32_t* __restrict__ hard_list, dnv_call* __restrict__ calls, int64_t cap) {
+                    const unsigned long long* __restrict__ counters, dnv_call* __restrict__ calls, int64_t cap) {
   const unsigned long long lo = counters[2];
   unsigned long long hi = counters[3];
   if (hi > (unsigned long long)cap) hi = (unsigned long long)cap;
-  if (lo + (unsigned long long)blockIdx.x * blockDim.x >= hi) return;
+  constexpr int kWarps = kExactThreads / 32;
+  if (lo + (unsigned long long)blockIdx.x * kWarps >= hi) return;
   __shared__ double s_rel[1000];
   __shared__ uint32_t s_isden[32];
+  __shared__ double s_L[kWarps][32];
   stage_exact_tables(tab, s_rel, s_isden);
   __syncthreads();
-  const double hm = tab->hm, ht = tab->ht, mm = tab->mm, thr = tab->lrt_threshold;
-  const int method = tab->method;
-  for (unsigned long long i = lo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi;
-       i += (unsigned long long)gridDim.x * blockDim.x) {
+  const double hm = tab->hm, ht = tab->ht, mm = tab->mm;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (unsigned long long i = lo + (unsigned long long)blockIdx.x * kWarps + warp; i < hi;
+       i += (unsigned long long)gridDim.x * kWarps) {
     const int64_t gsite = call_idx[i];
     uint16_t c[12];
     load_counts(counts, gsite - site_base, c);
-    ExactOut r;
-    exact_site(c, s_rel, s_isden, hm, ht, mm, method, thr, &r);
-    dnv_call o;
-    o.site = gsite;
+    if (lane < 30) {  // lane = person*10 + genotype: one exact read log-likelihood each
+      const int p = lane / 10, g = lane % 10;
+      const int a0 = kGenoA0[g], a1 = kGenoA1[g];
+      double acc = 0.0;
 #pragma unroll
-    for (int k = 0; k < 12; k++) o.counts[k] = c[k];
-    o.dad = (uint8_t)r.dad; o.mom = (uint8_t)r.mom; o.child = (uint8_t)r.child;
-    o.is_denovo = 1;  // the decision that put the site on the list stands
-    o.flags = r.is_denovo ? 0u : 2u;  // bit1: exact re-evaluation disagrees (never expected)
-    o.max_ll = r.max_ll; o.p = r.p; o.lr = r.lr; o.log_men = r.log_men; o.log_den = r.log_den;
-    calls[i] = o;
+      for (int a = 0; a < 4; a++) {
+        const double bl = (a == a0 || a == a1) ? (a0 == a1 ? hm : ht) : mm;
+        acc = __dadd_rn(acc, __dmul_rn((double)(int)c[p * 4 + a], bl));
+      }
+      s_L[warp][lane] = acc;
+    }
+    __syncwarp();
+    double max_ll = -INFINITY, l_den = 0.0, l_men = 0.0;
+    int best = 0x7fffffff;
+    for (int idx = lane; idx < 1000; idx += 32) {
+      const int d = idx / 100, m = (idx / 10) % 10, ch = idx % 10;
+      const double ll = __dadd_rn(__dadd_rn(__dadd_rn(s_L[warp][d], s_L[warp][10 + m]), s_L[warp][20 + ch]), s_rel[idx]);
+      const double e = exp(ll);
+      if ((s_isden[idx >> 5] >> (idx & 31)) & 1u) l_den += e; else l_men += e;
+      if (ll > max_ll) { max_ll = ll; best = idx; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double oll = __shfl_xor_sync(0xffffffffu, max_ll, o);
+      const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+      if (oll > max_ll || (oll == max_ll && ob < best)) { max_ll = oll; best = ob; }
+      l_den += __shfl_xor_sync(0xffffffffu, l_den, o);
+      l_men += __shfl_xor_sync(0xffffffffu, l_men, o);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      dnv_call o;
+      o.site = gsite;
+#pragma unroll
+      for (int k = 0; k < 12; k++) o.counts[k] = c[k];
+      o.dad = (uint8_t)(best / 100); o.mom = (uint8_t)((best / 10) % 10); o.child = (uint8_t)(best % 10);
+      o.is_denovo = 1;  // the decision that put the site on the list stands
+      o.flags = 0;
+      o.max_ll = max_ll;
+      o.p = l_den / (l_den + l_men);
+      o.lr = l_den / l_men;
+      o.log_men = log(l_men);
+      o.log_den = log(l_den);
+      calls[i] = o;
+    }
   }
-  (void)hard_list;
 }
 
 // ---------------------------------------------------------------- launcher
@@ -205,8 +244,8 @@ int launch_trio_chunk(dnv_ctx* ctx, const uint16_t* d_counts, int64_t site_base,
   scatter_calls_kernel<<<n_blocks, kScanThreads, 0, st>>>(ctx->d_bits, n_words, ctx->d_block_sums,
                                                          ctx->d_counters, site_base, ctx->d_call_idx,
                                                          ctx->call_idx_cap);
-  call_details_kernel<<<sms * 2, kExactThreads, 0, st>>>(ctx->d_tab, d_counts, site_base, ctx->d_call_idx,
-                                                        ctx->d_counters, ctx->d_hard_list, d_calls, cap);
+  call_details_kernel<<<sms * 8, kExactThreads, 0, st>>>(ctx->d_tab, d_counts, site_base, ctx->d_call_idx,
+                                                        ctx->d_counters, d_calls, cap);
   ctx->stats.n_launches += 4;
   DNV_CUDA(cudaGetLastError());
   return DNV_OK;

@@ -23,6 +23,8 @@
 // MAP decisions (and maxGenoType of the dense record) use the exact log-domain
 // sweep: bit-identical lls, strict '>' in dad-major order.
 #pragma once
+#include <stdlib.h>
+
 #include "dnv_internal.cuh"
 #include "trio_exact.cuh"
 
@@ -169,8 +171,8 @@ __device__ __forceinline__ void unpack_counts(const uint2* p, int* c) {
 
 // kLin: evaluate the linear-domain posterior (BAYES/LRT decision, dense values)
 // kMap: evaluate the exact log-domain argmax (MAP decision, dense maxGenoType)
-template <bool kLin, bool kMap, bool kDense>
-__global__ void __launch_bounds__(kFastThreads, kLin && !kMap ? 3 : 2)
+template <bool kLin, bool kMap, bool kDense, int kMinBlocks>
+__global__ void __launch_bounds__(kFastThreads, kMinBlocks)
 trio_fast_kernel(const Tables* __restrict__ tab, const uint16_t* __restrict__ counts, int64_t n,
                  uint32_t* __restrict__ bits, uint32_t* __restrict__ hard_list,
                  unsigned long long* __restrict__ counters, dnv_site_result* __restrict__ dense) {
@@ -303,12 +305,12 @@ trio_fast_kernel(const Tables* __restrict__ tab, const uint16_t* __restrict__ co
   }
 }
 
-template <bool kLin, bool kMap, bool kDense>
+template <bool kLin, bool kMap, bool kDense, int kMinBlocks>
 static int launch_fast_variant(dnv_ctx* ctx, const uint16_t* d_counts, int64_t n, dnv_site_result* d_dense) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
   const size_t smem = sizeof(FastShared) + (kMap ? 1000 * sizeof(double) + 32 * sizeof(uint32_t) : 0);
-  auto kern = trio_fast_kernel<kLin, kMap, kDense>;
+  auto kern = trio_fast_kernel<kLin, kMap, kDense, kMinBlocks>;
   DNV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
   DNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFastThreads, smem));
@@ -324,9 +326,13 @@ static int launch_fast_variant(dnv_ctx* ctx, const uint16_t* d_counts, int64_t n
 
 inline int launch_trio_fast(dnv_ctx* ctx, const uint16_t* d_counts, int64_t n, dnv_site_result* d_dense) {
   const bool map = ctx->prm.method == DNV_METHOD_MAP;
-  if (d_dense) return launch_fast_variant<true, true, true>(ctx, d_counts, n, d_dense);
-  if (map) return launch_fast_variant<false, true, false>(ctx, d_counts, n, nullptr);
-  return launch_fast_variant<true, false, false>(ctx, d_counts, n, nullptr);
+  if (d_dense) return launch_fast_variant<true, true, true, 2>(ctx, d_counts, n, d_dense);
+  if (map) return launch_fast_variant<false, true, false, 2>(ctx, d_counts, n, nullptr);
+  static const int tune = getenv("DNV_FAST_MINBLOCKS") ? atoi(getenv("DNV_FAST_MINBLOCKS")) : 3;  // tuning knob
+  if (tune == 2) return launch_fast_variant<true, false, false, 2>(ctx, d_counts, n, nullptr);
+  if (tune == 4) return launch_fast_variant<true, false, false, 4>(ctx, d_counts, n, nullptr);
+  if (tune == 5) return launch_fast_variant<true, false, false, 5>(ctx, d_counts, n, nullptr);
+  return launch_fast_variant<true, false, false, 3>(ctx, d_counts, n, nullptr);
 }
 
 }  // namespace dnv

@@ -1,0 +1,106 @@
+"""GPU parity (bit-exact) of the pileup kernel and the VARIANT-mode Mendelian filter
+against the CPU oracle, through the C ABI."""
+import numpy as np
+import pytest
+
+import denovo_b200 as D
+import oracle_lib as O
+import synth_inputs as S
+
+pytestmark = pytest.mark.gpu
+
+
+def pcalls_equal(a, b):
+    return all(np.array_equal(a[f], b[f]) for f in ("position", "child_index", "child", "mom", "dad", "is_denovo"))
+
+
+@pytest.mark.parametrize("var_len", [False, True])
+def test_pileup_dense_sites(var_len):
+    rs, bo, ba, pe = S.make_reads(11, 5000, 3000, depth=30, read_len=100, var_len=var_len)
+    pos = np.arange(4900, 8200, dtype=np.int64)  # includes uncovered flanks (zero depth)
+    rc, want = O.pileup(rs, bo, ba, pe, pos)
+    assert rc == 0
+    with D.TrioEngine() as eng:
+        got = eng.pileup(rs, bo, ba, pe, pos)
+    assert np.array_equal(got, want)
+    assert got[0].sum() == 0 and got[-50:].sum() == 0 and 15 < got[500:2500].sum(axis=2).mean() < 35
+
+
+def test_pileup_sparse_sites_and_edges():
+    rs, bo, ba, pe = S.make_reads(12, 100000, 20000, depth=200, read_len=150, gap_rate=0.01)
+    rng = np.random.default_rng(1)
+    pos = np.unique(rng.integers(100000, 120000, 300)).astype(np.int64)
+    rc, want = O.pileup(rs, bo, ba, pe, pos)
+    with D.TrioEngine() as eng:
+        assert np.array_equal(eng.pileup(rs, bo, ba, pe, pos), want)
+        # no reads at all / one person missing
+        z = eng.pileup(np.zeros(0, np.int64), np.zeros(1, np.int64), np.zeros(0, np.uint8), np.zeros(0, np.uint8), pos)
+        assert z.sum() == 0
+        keep = pe != 1
+        bo2 = np.zeros(keep.sum() + 1, np.int64)
+        lens = np.diff(bo)[keep]
+        np.cumsum(lens, out=bo2[1:])
+        ba2 = np.concatenate([ba[bo[i]:bo[i + 1]] for i in np.nonzero(keep)[0]])
+        got = eng.pileup(rs[keep], bo2, ba2, pe[keep], pos)
+        assert np.array_equal(got[:, [0, 2]], want[:, [0, 2]]) and got[:, 1].sum() == 0
+        # a base outside ACGT- is the reference's IllegalArgumentException
+        bad = ba.copy()
+        r = int(np.searchsorted(rs[pe == 0], pos[5], side="right")) - 1
+        bad[bo[r] + (pos[5] - rs[r])] = ord("N")
+        with pytest.raises(D.DenovoError) as ei:
+            eng.pileup(rs, bo, bad, pe, pos)
+        assert ei.value.code == D.DNV_E_BADBASE
+        with pytest.raises(D.DenovoError) as ei:
+            eng.pileup(rs[::-1].copy(), bo, ba, pe, pos)
+        assert ei.value.code == D.DNV_E_UNSORTED
+
+
+def test_pileup_then_inference_end_to_end():
+    """reads -> counts -> calls on the device equals oracle pileup -> oracle inference."""
+    rs, bo, ba, pe = S.make_reads(13, 1, 20000, depth=30, err=2e-2)
+    pos = np.arange(1, 20001, dtype=np.int64)
+    rc, counts = O.pileup(rs, bo, ba, pe, pos)
+    ref = O.infer(O.params(), counts)
+    with D.TrioEngine() as eng:
+        got_counts = eng.pileup(rs, bo, ba, pe, pos)
+        calls, _ = eng.infer(got_counts)
+    assert np.array_equal(got_counts, counts)
+    assert np.array_equal(calls["site"], np.nonzero(ref["denovo_bayes"])[0])
+
+
+@pytest.mark.parametrize("seed,n,adv", [(1, 200, False), (2, 200, True), (3, 5000, False), (4, 5000, True),
+                                        (5, 60000, False)])
+def test_mendel_filter_matches_streaming_oracle(seed, n, adv):
+    calls = S.make_callset(seed, n, adversarial=adv)
+    n_ref, want = O.mendel_stream(calls)
+    assert n_ref >= 0
+    with D.TrioEngine() as eng:
+        got = eng.mendel_filter(calls)
+    assert len(got) == n_ref and pcalls_equal(got, want)
+    if n >= 5000:
+        assert got["is_denovo"].sum() > 0
+
+
+def test_mendel_filter_edges():
+    with D.TrioEngine() as eng:
+        assert len(eng.mendel_filter(np.zeros(0, D.VCALL_DT))) == 0
+        calls = S.make_callset(7, 3000)
+        only_child = calls[calls["person"] == 0]
+        assert len(eng.mendel_filter(only_child)) == 0        # no parents: no PositionCall at all
+        n_ref, want = O.mendel_stream(calls)
+        with pytest.raises(D.DenovoError) as ei:
+            eng.mendel_filter(calls, cap=3)
+        assert ei.value.code == D.DNV_E_CAPACITY and str(n_ref) in str(ei.value)
+        with pytest.raises(D.DenovoError) as ei:
+            eng.mendel_filter(calls[::-1].copy())
+        assert ei.value.code == D.DNV_E_UNSORTED
+        bad = calls.copy()
+        i = np.nonzero((bad["person"] == 0) & (bad["end"] == bad["start"] + 1) & (bad["filter_pass"] == 1)
+                       & (bad["ngt"] == 2) & (bad["gt0"] >= 0) & (bad["gt1"] >= 0) & (bad["ref_len"] == 1)
+                       & (bad["alt0_len"] <= 1) & (bad["alt1_len"] <= 1))[0][0]
+        bad["ref_base"][i] = b"N"
+        bad["gt0"][i] = 0
+        assert O.mendel_stream(bad)[0] < 0
+        with pytest.raises(D.DenovoError) as ei:
+            eng.mendel_filter(bad)
+        assert ei.value.code == D.DNV_E_BADBASE
