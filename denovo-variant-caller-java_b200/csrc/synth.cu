@@ -24,13 +24,13 @@ struct SynthKeys {
 constexpr int kMaxThr = 1024;
 
 __global__ void __launch_bounds__(256)
-synth_counts_kernel(SynthKeys keys, int64_t first, int64_t n, const uint64_t* __restrict__ thr, int n_thr,
-                    uint32_t err_thr, uint16_t* __restrict__ counts) {
+synth_counts_kernel(SynthKeys keys, int64_t first, const int64_t* __restrict__ index, int64_t n,
+                    const uint64_t* __restrict__ thr, int n_thr, uint32_t err_thr, uint16_t* __restrict__ counts) {
   __shared__ uint64_t s_thr[kMaxThr];
   for (int i = threadIdx.x; i < n_thr; i += blockDim.x) s_thr[i] = thr[i];
   __syncthreads();
   for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n; s += (int64_t)gridDim.x * blockDim.x) {
-    const uint64_t i = (uint64_t)(first + s);
+    const uint64_t i = index ? (uint64_t)index[s] : (uint64_t)(first + s);
     const uint32_t c100 = (uint32_t)(((splitmix64(keys.k_class ^ i) >> 32) * 100ULL) >> 32);
     const int cls = c100 < 90 ? 0 : (c100 < 99 ? 1 : 2);
     const int ref = (int)(splitmix64(keys.k_ref ^ i) & 3);
@@ -94,17 +94,17 @@ using namespace dnv;
 
 extern "C" {
 
-int dnv_synth_counts_device(dnv_ctx* ctx, uint64_t seed, int64_t first, int64_t n, const uint64_t* thr,
-                            int32_t n_thr, uint32_t err_thr, uint16_t* d_counts) {
+static int synth_launch(dnv_ctx* ctx, uint64_t seed, int64_t first, const int64_t* d_index, int64_t n,
+                        const uint64_t* thr, int32_t n_thr, uint32_t err_thr, uint16_t* d_counts) {
   if (!ctx || n < 0 || !thr || n_thr <= 0 || n_thr > kMaxThr || (n > 0 && !d_counts)) {
-    set_error("dnv_synth_counts_device: invalid argument (n_thr must be in 1..1024)");
+    set_error("dnv_synth_counts: invalid argument (n_thr must be in 1..1024)");
     return DNV_E_INVALID;
   }
   if (n == 0) return DNV_OK;
   DNV_CUDA(cudaSetDevice(ctx->device));
-  int rc = ensure_scratch(ctx, (size_t)n_thr * 8);
-  if (rc) return rc;
-  DNV_CUDA(cudaMemcpyAsync(ctx->d_scratch, thr, (size_t)n_thr * 8, cudaMemcpyHostToDevice, ctx->stream));
+  uint64_t* d_thr = nullptr;
+  DNV_CUDA(cudaMalloc(&d_thr, (size_t)n_thr * 8));
+  cudaError_t e = cudaMemcpyAsync(d_thr, thr, (size_t)n_thr * 8, cudaMemcpyHostToDevice, ctx->stream);
   SynthKeys k;
   k.k_class = splitmix64(seed ^ (0 * DNV_PHI));
   k.k_ref = splitmix64(seed ^ (1 * DNV_PHI));
@@ -118,11 +118,47 @@ int dnv_synth_counts_device(dnv_ctx* ctx, uint64_t seed, int64_t first, int64_t 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
   const int64_t want = (n + 255) / 256;
   const int grid = (int)std::min<int64_t>(want, (int64_t)sms * 8);
-  synth_counts_kernel<<<grid, 256, 0, ctx->stream>>>(k, first, n, (const uint64_t*)ctx->d_scratch, n_thr, err_thr,
-                                                     d_counts);
-  DNV_CUDA(cudaGetLastError());
-  DNV_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (e == cudaSuccess) {
+    synth_counts_kernel<<<grid, 256, 0, ctx->stream>>>(k, first, d_index, n, d_thr, n_thr, err_thr, d_counts);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_thr);
+  if (e != cudaSuccess) { set_error(std::string("dnv_synth_counts: ") + cudaGetErrorString(e)); return DNV_E_CUDA; }
   return DNV_OK;
+}
+
+int dnv_synth_counts_device(dnv_ctx* ctx, uint64_t seed, int64_t first, int64_t n, const uint64_t* thr,
+                            int32_t n_thr, uint32_t err_thr, uint16_t* d_counts) {
+  return synth_launch(ctx, seed, first, nullptr, n, thr, n_thr, err_thr, d_counts);
+}
+
+int dnv_synth_counts_at_device(dnv_ctx* ctx, uint64_t seed, const int64_t* d_index, int64_t n, const uint64_t* thr,
+                               int32_t n_thr, uint32_t err_thr, uint16_t* d_counts) {
+  if (n > 0 && !d_index) { set_error("dnv_synth_counts_at_device: null index"); return DNV_E_INVALID; }
+  return synth_launch(ctx, seed, 0, d_index, n, thr, n_thr, err_thr, d_counts);
+}
+
+int dnv_synth_counts_at(dnv_ctx* ctx, uint64_t seed, const int64_t* index, int64_t n, const uint64_t* thr,
+                        int32_t n_thr, uint32_t err_thr, uint16_t* counts) {
+  if (!ctx || n < 0 || (n > 0 && (!index || !counts))) { set_error("dnv_synth_counts_at: invalid argument"); return DNV_E_INVALID; }
+  if (n == 0) return DNV_OK;
+  DNV_CUDA(cudaSetDevice(ctx->device));
+  int64_t* d_index = nullptr;
+  uint16_t* d_counts = nullptr;
+  int rc = DNV_OK;
+  if (cudaMalloc(&d_index, (size_t)n * 8) != cudaSuccess || cudaMalloc(&d_counts, (size_t)n * 24) != cudaSuccess) {
+    set_error("dnv_synth_counts_at: device allocation failed"); rc = DNV_E_NOMEM;
+  }
+  if (rc == DNV_OK && cudaMemcpy(d_index, index, (size_t)n * 8, cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error("dnv_synth_counts_at: H2D copy failed"); rc = DNV_E_CUDA;
+  }
+  if (rc == DNV_OK) rc = synth_launch(ctx, seed, 0, d_index, n, thr, n_thr, err_thr, d_counts);
+  if (rc == DNV_OK && cudaMemcpy(counts, d_counts, (size_t)n * 24, cudaMemcpyDeviceToHost) != cudaSuccess) {
+    set_error("dnv_synth_counts_at: D2H copy failed"); rc = DNV_E_CUDA;
+  }
+  cudaFree(d_index); cudaFree(d_counts);
+  return rc;
 }
 
 int dnv_measure_fp64_peak(dnv_ctx* ctx, double* tflops, double* ms) {

@@ -22,7 +22,8 @@ F_TIME_KERNELS = 2
 EXPORTS = ["dnv_create", "dnv_destroy", "dnv_last_error", "dnv_abi_version", "dnv_get_tables", "dnv_get_stats",
            "dnv_set_stream",
            "dnv_infer_counts", "dnv_infer_counts_device", "dnv_pileup", "dnv_pileup_device",
-           "dnv_mendel_filter", "dnv_mendel_filter_device", "dnv_synth_counts_device", "dnv_measure_fp64_peak"]
+           "dnv_mendel_filter", "dnv_mendel_filter_device", "dnv_synth_counts_device", "dnv_synth_counts_at_device",
+           "dnv_synth_counts_at", "dnv_measure_fp64_peak"]
 
 
 class Params(C.Structure):
@@ -86,6 +87,8 @@ def load():
     L.dnv_mendel_filter.argtypes = [vp, vp, i64, vp, i64, C.POINTER(i64)]
     L.dnv_mendel_filter_device.argtypes = [vp, vp, i64, vp, i64, C.POINTER(i64)]
     L.dnv_synth_counts_device.argtypes = [vp, u64, i64, i64, vp, i32, u32, vp]
+    L.dnv_synth_counts_at_device.argtypes = [vp, u64, vp, i64, vp, i32, u32, vp]
+    L.dnv_synth_counts_at.argtypes = [vp, u64, vp, i64, vp, i32, u32, vp]
     L.dnv_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     for name in EXPORTS:
         if name != "dnv_last_error":

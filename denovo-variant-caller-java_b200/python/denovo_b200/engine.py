@@ -22,18 +22,19 @@ ALLELES = "ACGT"
 
 
 def poisson_thresholds(depth, kmax=None):
-    """2^64-scaled ascending Poisson CDF thresholds for the synthetic source
-    (depth = #{k: thr[k] <= u}); exact rational arithmetic so every rank and the
-    test oracle share identical integers."""
-    from fractions import Fraction
+    """2^64-scaled ascending Poisson CDF thresholds (depth = #{k: thr[k] <= u}).
+    Plain IEEE double recurrence in a fixed operation order, so the Python host, the C++
+    host (host/denovo_host.hpp: poisson_thresholds) and the tests build identical integers."""
+    import math
+    depth = float(depth)
     if kmax is None:
-        kmax = int(depth + 12 * math.sqrt(depth) + 20)
-    lam = Fraction(depth).limit_denominator(1 << 20)  # exact rationals: no underflow at depth 200+
-    term, cdf, thr = Fraction(math.exp(-float(depth))), Fraction(0), []
+        kmax = int(depth + 12.0 * math.sqrt(depth) + 20.0)
+    term, cdf, thr = math.exp(-depth), 0.0, []
     for k in range(kmax):
         cdf += term
-        thr.append(min(int(cdf * (1 << 64)), (1 << 64) - 1))
-        term = term * lam / (k + 1)
+        x = cdf * 18446744073709551616.0
+        thr.append((1 << 64) - 1 if x >= 18446744073709551616.0 else int(x))
+        term = term * depth / (k + 1)
     return np.array(thr, np.uint64)
 
 
@@ -145,6 +146,16 @@ class TrioEngine:
         err_thr = int((self.params.seq_err_rate if seq_err is None else seq_err) * (1 << 32))
         L.check(self.lib.dnv_synth_counts_device(self._h, seed, first, n, L.ptr(thr), thr.shape[0], err_thr,
                                                  L.ptr(d_counts)))
+
+    def synth_counts_at(self, seed, index, depth=30, seq_err=None, thr=None):
+        """Host arrays: counts of the synthetic trio at arbitrary global site indices."""
+        thr = poisson_thresholds(depth) if thr is None else thr
+        index = np.ascontiguousarray(index, np.int64)
+        err_thr = int((self.params.seq_err_rate if seq_err is None else seq_err) * (1 << 32))
+        out = np.zeros((index.shape[0], 3, 4), np.uint16)
+        L.check(self.lib.dnv_synth_counts_at(self._h, seed, L.ptr(index), index.shape[0], L.ptr(thr), thr.shape[0],
+                                             err_thr, L.ptr(out)))
+        return out
 
     def measure_fp64_peak(self):
         tf, ms = C.c_double(0), C.c_double(0)

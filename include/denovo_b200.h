@@ -213,6 +213,15 @@ int dnv_synth_counts_device(dnv_ctx *ctx, uint64_t seed, int64_t first, int64_t 
                             const uint64_t *thr, int32_t n_thr, uint32_t err_thr,
                             uint16_t *d_counts);
 
+/* Same generator for an arbitrary list of global site indices (candidate sites of
+ * READ mode: index = contig offset + position).  d_index: device int64[n]. */
+int dnv_synth_counts_at_device(dnv_ctx *ctx, uint64_t seed, const int64_t *d_index, int64_t n,
+                               const uint64_t *thr, int32_t n_thr, uint32_t err_thr,
+                               uint16_t *d_counts);
+/* Host-buffer convenience wrapper of the above (index and counts on the host). */
+int dnv_synth_counts_at(dnv_ctx *ctx, uint64_t seed, const int64_t *index, int64_t n,
+                        const uint64_t *thr, int32_t n_thr, uint32_t err_thr, uint16_t *counts);
+
 /* ---- calibration ----------------------------------------------------------- */
 /* Dependent-free DFMA chains on every SM: measured FP64 peak in TFLOP/s
  * (MEASURED_PEAKS.json has no FP64 figure). */

@@ -36,15 +36,15 @@ static uint64_t skey(uint64_t seed, uint64_t stream) {
 
 /* counts: [n][3][4] uint16 (DAD, MOM, CHILD × A,C,G,T) for global site indices
  * first .. first+n-1.  thr: n_thr ascending thresholds, depth = #{k: thr[k] <= u}. */
-void synth_ref_counts(uint64_t seed, int64_t first, int64_t n,
-                      const uint64_t *thr, int32_t n_thr, uint32_t err_thr,
-                      uint16_t *counts) {
+static void synth_ref_impl(uint64_t seed, int64_t first, const int64_t *index, int64_t n,
+                           const uint64_t *thr, int32_t n_thr, uint32_t err_thr,
+                           uint16_t *counts) {
   uint64_t k_class = skey(seed, 0), k_ref = skey(seed, 1), k_alt = skey(seed, 2),
            k_par = skey(seed, 3);
   uint64_t k_depth[3] = {skey(seed, 4), skey(seed, 5), skey(seed, 6)};
   uint64_t k_read[3] = {skey(seed, 8), skey(seed, 9), skey(seed, 10)};
   for (int64_t s = 0; s < n; s++) {
-    uint64_t i = (uint64_t)(first + s);
+    uint64_t i = index ? (uint64_t)index[s] : (uint64_t)(first + s);
     uint32_t c100 = (uint32_t)(((splitmix64(k_class ^ i) >> 32) * 100ULL) >> 32);
     int cls = c100 < 90 ? 0 : (c100 < 99 ? 1 : 2);
     int ref = (int)(splitmix64(k_ref ^ i) & 3);
@@ -74,4 +74,14 @@ void synth_ref_counts(uint64_t seed, int64_t first, int64_t n,
       }
     }
   }
+}
+
+void synth_ref_counts(uint64_t seed, int64_t first, int64_t n, const uint64_t *thr,
+                      int32_t n_thr, uint32_t err_thr, uint16_t *counts) {
+  synth_ref_impl(seed, first, 0, n, thr, n_thr, err_thr, counts);
+}
+/* arbitrary global site indices (READ-mode candidate sites) */
+void synth_ref_counts_at(uint64_t seed, const int64_t *index, int64_t n, const uint64_t *thr,
+                         int32_t n_thr, uint32_t err_thr, uint16_t *counts) {
+  synth_ref_impl(seed, 0, index, n, thr, n_thr, err_thr, counts);
 }

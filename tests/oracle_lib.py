@@ -122,18 +122,19 @@ def mendel_admit(calls):
 
 
 def poisson_thresholds(depth, kmax=None):
-    """2^64-scaled ascending Poisson CDF thresholds: depth = #{k: thr[k] <= u}.
-    Integer table shared verbatim by the CPU and GPU generators."""
-    from fractions import Fraction
+    """2^64-scaled ascending Poisson CDF thresholds (depth = #{k: thr[k] <= u}).
+    Plain IEEE double recurrence in a fixed operation order, so the Python host, the C++
+    host (host/denovo_host.hpp: poisson_thresholds) and the tests build identical integers."""
     import math
+    depth = float(depth)
     if kmax is None:
-        kmax = int(depth + 12 * math.sqrt(depth) + 20)
-    lam = Fraction(depth).limit_denominator(1 << 20)  # exact rationals: no underflow at depth 200+
-    term, cdf, thr = Fraction(math.exp(-float(depth))), Fraction(0), []
+        kmax = int(depth + 12.0 * math.sqrt(depth) + 20.0)
+    term, cdf, thr = math.exp(-depth), 0.0, []
     for k in range(kmax):
         cdf += term
-        thr.append(min(int(cdf * (1 << 64)), (1 << 64) - 1))
-        term = term * lam / (k + 1)
+        x = cdf * 18446744073709551616.0
+        thr.append((1 << 64) - 1 if x >= 18446744073709551616.0 else int(x))
+        term = term * depth / (k + 1)
     return np.array(thr, np.uint64)
 
 
@@ -144,4 +145,15 @@ def synth_counts(seed, first, n, depth=30, seq_err=1e-2, thr=None):
     out = np.zeros((n, 3, 4), np.uint16)
     lib().synth_ref_counts(C.c_uint64(seed), C.c_int64(first), C.c_int64(n), _p(thr),
                            C.c_int32(thr.shape[0]), C.c_uint32(err_thr), _p(out))
+    return out
+
+
+def synth_counts_at(seed, index, depth=30, seq_err=1e-2, thr=None):
+    if thr is None:
+        thr = poisson_thresholds(depth)
+    index = np.ascontiguousarray(index, np.int64)
+    err_thr = int(seq_err * (1 << 32))
+    out = np.zeros((index.shape[0], 3, 4), np.uint16)
+    lib().synth_ref_counts_at(C.c_uint64(seed), _p(index), C.c_int64(index.shape[0]), _p(thr),
+                              C.c_int32(thr.shape[0]), C.c_uint32(err_thr), _p(out))
     return out
