@@ -12,6 +12,7 @@
 // writes it once — no atomics, no inter-thread contention, deterministic.  For
 // dense candidate lists neighbouring threads walk the same reads at neighbouring
 // byte offsets, so the byte loads of a warp fall in the same 128-byte lines.
+#include <stdlib.h>
 #include <algorithm>
 #include "dnv_internal.cuh"
 
@@ -97,6 +98,112 @@ pileup_gather_kernel(const int64_t* __restrict__ read_start, const int64_t* __re
   }
 }
 
+// Warp-cooperative variant for dense candidate lists (the every-position / dense-candidate
+// layouts of SURVEY.md E.3): a warp owns 32 consecutive sites whose positions span less than
+// ~2 read lengths.  The reads overlapping the warp's window are walked ONCE per warp: lanes
+// load 32 read descriptors at a time (coalesced), each descriptor is broadcast by shuffle, and
+// every lane fetches its own base of that read — 32 neighbouring bytes, one sector, and the
+// loads of successive reads are independent (no pointer chasing), so they pipeline.
+__global__ void __launch_bounds__(256)
+pileup_warp_kernel(const int64_t* __restrict__ read_start, const int64_t* __restrict__ base_off,
+                   const char* __restrict__ bases, long long* meta, const int64_t* __restrict__ site_pos,
+                   int64_t n_sites, uint16_t* __restrict__ counts) {
+  const long long lmax = meta[4];
+  const int lane = threadIdx.x & 31;
+  const int64_t n_tiles = (n_sites + 31) / 32;
+  const int64_t warps_total = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < n_tiles; tile += warps_total) {
+    const int64_t s = tile * 32 + lane;
+    const bool live = s < n_sites;
+    const int64_t pos = site_pos[live ? s : n_sites - 1];
+    const int64_t pmin = __shfl_sync(0xffffffffu, pos, 0);
+    const int64_t pmax = __shfl_sync(0xffffffffu, pos, 31);
+    uint32_t out[12];
+    if (pmax - pmin <= 2 * lmax + 64) {
+      const int my = (int)(pos - pmin);
+      bool bad = false;
+#pragma unroll
+      for (int p = 0; p < 3; p++) {
+        const int64_t r0 = meta[p], r1 = meta[p + 1];
+        int64_t lo = r0, hi = r1;
+        while (lo < hi) {  // first read with start > pmin - lmax (warp-uniform search)
+          const int64_t mid = (lo + hi) >> 1;
+          if (__ldg(read_start + mid) <= pmin - lmax) lo = mid + 1; else hi = mid;
+        }
+        const int64_t first = lo;
+        hi = r1;
+        while (lo < hi) {  // first read with start > pmax
+          const int64_t mid = (lo + hi) >> 1;
+          if (__ldg(read_start + mid) <= pmax) lo = mid + 1; else hi = mid;
+        }
+        const int64_t last = lo;
+        uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+        for (int64_t c = first; c < last; c += 32) {
+          const int64_t r = c + lane;
+          const bool v = r < last;
+          const int64_t b0 = v ? __ldg(base_off + r) : 0;
+          const int len = v ? (int)(__ldg(base_off + r + 1) - b0) : 0;
+          const int rel = v ? (int)(__ldg(read_start + r) - pmin) : 0;
+          const int m = (int)min((int64_t)32, last - c);
+#pragma unroll 4
+          for (int j = 0; j < m; j++) {
+            const int o = my - __shfl_sync(0xffffffffu, rel, j);         // M/ReadSummary.java:48
+            const int l = __shfl_sync(0xffffffffu, len, j);
+            const int64_t bb = __shfl_sync(0xffffffffu, b0, j);
+            if ((unsigned)o < (unsigned)l) {
+              const char b = __ldg(bases + bb + o);                       // :49
+              const bool iA = b == 'A', iC = b == 'C', iG = b == 'G', iT = b == 'T';
+              c0 += iA; c1 += iC; c2 += iG; c3 += iT;
+              bad |= !(iA | iC | iG | iT | (b == '-'));                   // :51-55
+            }
+          }
+        }
+        out[p * 4 + 0] = c0; out[p * 4 + 1] = c1; out[p * 4 + 2] = c2; out[p * 4 + 3] = c3;
+      }
+      if (bad && live) { atomicMax((unsigned long long*)&meta[5], (unsigned long long)(s + 1)); meta[6] = DNV_E_BADBASE; meta[7] = 1; }
+    } else {
+      // sparse candidates: every lane walks only its own window
+#pragma unroll
+      for (int p = 0; p < 3; p++) {
+        const int64_t r0 = meta[p], r1 = meta[p + 1];
+        int64_t lo = r0, hi = r1;
+        const int64_t key = pos - lmax;
+        while (lo < hi) {
+          const int64_t mid = (lo + hi) >> 1;
+          if (__ldg(read_start + mid) <= key) lo = mid + 1; else hi = mid;
+        }
+        uint32_t cnt[4] = {0, 0, 0, 0};
+        for (int64_t r = lo; r < r1; r++) {
+          const int64_t st = __ldg(read_start + r);
+          if (st > pos) break;
+          const int64_t b0 = __ldg(base_off + r);
+          const int64_t off = pos - st;
+          if (off >= __ldg(base_off + r + 1) - b0) continue;
+          const char b = __ldg(bases + b0 + off);
+          if (b == '-') continue;
+          const int a = b == 'A' ? 0 : b == 'C' ? 1 : b == 'G' ? 2 : b == 'T' ? 3 : -1;
+          if (a < 0) {
+            if (live) { atomicMax((unsigned long long*)&meta[5], (unsigned long long)(r + 1)); meta[6] = DNV_E_BADBASE; }
+            continue;
+          }
+          cnt[0] += a == 0; cnt[1] += a == 1; cnt[2] += a == 2; cnt[3] += a == 3;
+        }
+#pragma unroll
+        for (int a = 0; a < 4; a++) out[p * 4 + a] = cnt[a];
+      }
+    }
+    if (live) {
+#pragma unroll
+      for (int k = 0; k < 12; k++)
+        if (out[k] > 65535u) { meta[6] = DNV_E_INVALID; atomicMax((unsigned long long*)&meta[5], 1ull); out[k] = 65535u; }
+      uint2* dst = reinterpret_cast<uint2*>(counts + s * 12);
+#pragma unroll
+      for (int q = 0; q < 3; q++)
+        dst[q] = make_uint2(out[4 * q] | (out[4 * q + 1] << 16), out[4 * q + 2] | (out[4 * q + 3] << 16));
+    }
+  }
+}
+
 }  // namespace dnv
 
 using namespace dnv;
@@ -124,7 +231,12 @@ int dnv_pileup_device(dnv_ctx* ctx, const int64_t* d_read_start, const int64_t* 
     pileup_prep_kernel<<<grid, 256, 0, ctx->stream>>>(d_read_start, d_base_off, d_person, n_reads, meta);
   }
   const int grid = (int)std::min<int64_t>((n_sites + 255) / 256, (int64_t)sms * 16);
-  pileup_gather_kernel<<<grid, 256, 0, ctx->stream>>>(d_read_start, d_base_off, d_bases, meta, d_site_pos, n_sites,
+  static const bool legacy = getenv("DNV_PILEUP_LEGACY") != nullptr;  // per-site gather (first version), kept for A/B runs
+  if (legacy)
+    pileup_gather_kernel<<<grid, 256, 0, ctx->stream>>>(d_read_start, d_base_off, d_bases, meta, d_site_pos, n_sites,
+                                                        d_counts_out);
+  else
+    pileup_warp_kernel<<<grid, 256, 0, ctx->stream>>>(d_read_start, d_base_off, d_bases, meta, d_site_pos, n_sites,
                                                       d_counts_out);
   DNV_CUDA(cudaGetLastError());
   long long h[8];
@@ -133,7 +245,7 @@ int dnv_pileup_device(dnv_ctx* ctx, const int64_t* d_read_start, const int64_t* 
   if (h[5] != 0) {
     const int kind = (int)h[6] ? (int)h[6] : DNV_E_INVALID;
     set_error(kind == DNV_E_BADBASE
-                  ? "pileup: base outside {A,C,G,T,-} in read " + std::to_string(h[5] - 1) +
+                  ? std::string("pileup: base outside {A,C,G,T,-} ") + (h[7] ? "at site " : "in read ") + std::to_string(h[5] - 1) +
                         " (the reference throws IllegalArgumentException, M/ReadSummary.java:55)"
                   : kind == DNV_E_UNSORTED ? "pileup: reads must be sorted by (person, start); first violation at read " +
                                                  std::to_string(h[5] - 1)

@@ -34,19 +34,24 @@ def stride_shards(start, end, num_threads):
 
 def gather_records(local, dist=None, dst=0):
     """Gather variable-length record arrays (torch uint8 [k, itemsize], CPU or CUDA) to `dst`
-    in rank order.  Returns (records on dst | None, per-rank counts)."""
+    in rank order.  Two collectives and ONE host sync: an all-gather of the per-rank counts,
+    then a gather padded to the largest count.  Returns (records on dst | None, per-rank counts)."""
     import torch
     if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
         return local, [int(local.shape[0])]
     world, rank = dist.get_world_size(), dist.get_rank()
-    cnt = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
-    allc = [torch.zeros_like(cnt) for _ in range(world)]
-    dist.all_gather(allc, cnt)
-    counts = [int(c.item()) for c in allc]
+    cnt = torch.full((1,), local.shape[0], dtype=torch.int64, device=local.device)
+    allc = torch.empty((world,), dtype=torch.int64, device=local.device)
+    dist.all_gather_into_tensor(allc, cnt)
+    counts = allc.tolist()
     mx = max(max(counts), 1)
-    send = torch.zeros((mx, local.shape[1]), dtype=local.dtype, device=local.device)
-    send[:local.shape[0]] = local
-    recv = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
+    if local.shape[0] == mx:
+        send = local.contiguous()
+    else:
+        send = torch.empty((mx, local.shape[1]), dtype=local.dtype, device=local.device)
+        send[:local.shape[0]] = local
+    recv = list(torch.empty((world, mx, local.shape[1]), dtype=local.dtype, device=local.device).unbind(0)) \
+        if rank == dst else None
     dist.gather(send, recv, dst=dst)
     if rank != dst:
         return None, counts
