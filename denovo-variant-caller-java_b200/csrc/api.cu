@@ -111,7 +111,7 @@ int dnv_destroy(dnv_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->copy_stream);
-  cudaFree(ctx->d_tab); cudaFree(ctx->d_bits); cudaFree(ctx->d_hard_list); cudaFree(ctx->d_block_sums);
+  cudaFree(ctx->d_tab); cudaFree(ctx->d_bits); cudaFree(ctx->d_tile_status);
   cudaFree(ctx->d_call_idx); cudaFree(ctx->d_counters); cudaFree(ctx->d_stage_calls); cudaFree(ctx->d_scratch);
   for (int i = 0; i < 2; i++) {
     cudaFree(ctx->d_stage_counts[i]); cudaFree(ctx->d_stage_dense[i]);
@@ -166,11 +166,12 @@ static int finish_batch(dnv_ctx* ctx, int64_t n, int64_t cap, int64_t* n_calls) 
     if (cudaEventElapsedTime(&ms, ctx->ev_k0[i], ctx->ev_k1[i]) == cudaSuccess) ctx->stats.fused_kernel_ms += ms;
   }
   ctx->stats.n_sites = n;
-  ctx->stats.n_calls = (int64_t)h[0];
+  const unsigned long long total = h[ctx->calls_slot];
+  ctx->stats.n_calls = (int64_t)total;
   ctx->stats.n_hard = (int64_t)h[4];
-  *n_calls = (int64_t)h[0];
-  if ((int64_t)h[0] > cap) {
-    set_error("call capacity too small: need " + std::to_string(h[0]) + ", have " + std::to_string(cap));
+  *n_calls = (int64_t)total;
+  if ((int64_t)total > cap) {
+    set_error("call capacity too small: need " + std::to_string(total) + ", have " + std::to_string(cap));
     return DNV_E_CAPACITY;
   }
   return DNV_OK;
@@ -185,6 +186,7 @@ int dnv_infer_counts_device(dnv_ctx* ctx, const uint16_t* d_counts, int64_t n, d
   DNV_CUDA(cudaSetDevice(ctx->device));
   ctx->stats = dnv_stats();
   ctx->n_timed = 0;
+  ctx->calls_slot = 0;
   DNV_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
   for (int64_t off = 0; off < n; off += kDeviceChunk) {
     const int64_t m = std::min(kDeviceChunk, n - off);
@@ -203,6 +205,7 @@ int dnv_infer_counts(dnv_ctx* ctx, const uint16_t* counts, int64_t n, dnv_site_r
   DNV_CUDA(cudaSetDevice(ctx->device));
   ctx->stats = dnv_stats();
   ctx->n_timed = 0;
+  ctx->calls_slot = 0;
   const int64_t chunk = std::min<int64_t>(kHostChunk, std::max<int64_t>(n, 1));
   const int64_t dev_cap = std::min(cap, n);
   int rc = ensure_stage(ctx, chunk, dense != nullptr, dev_cap);

@@ -19,6 +19,8 @@ struct Tables {
   double hm, ht, mm;      // getBaseLogLikelihood's three values, :159-165
   uint32_t isden[32];     // isDenovoMap as a 1000-bit mask, M/DenovoUtil.java:37-55
   uint8_t nden[100];      // 10 - |mendelianGenotypes(d,m)|, M/DenovoBayesNet.java:98
+  double rmax_dm[100];    // max over child of rel[d][m][c]  (exact-MAP pruning bounds)
+  double rmax_d[10];      // max over mom, child of rel[d][m][c]
   // linear-domain fast path (factored form)
   double pw_inv[2][kPowTable]; // r_j^-i, j=0 hom ratio, j=1 het ratio (may underflow to 0: exact)
   double pw_m[2][kPowTable];   // mantissa in [1,2) of r_j^k
@@ -53,11 +55,12 @@ struct dnv_ctx {
   // per-chunk scratch (sized for chunk_cap sites)
   int64_t chunk_cap;
   uint32_t* d_bits;        // decision bit per site
-  uint32_t* d_hard_list;   // chunk-relative indices of hard sites
-  uint32_t* d_block_sums;  // popcount per compaction block
+  unsigned long long* d_tile_status;  // decoupled look-back status per compaction block
+  unsigned long long epoch;           // launch counter tagging d_tile_status entries
+  int calls_slot;                     // counters[] slot holding the running call total (0 or 3)
   int64_t* d_call_idx;     // global site index of every call, input order
   int64_t call_idx_cap;
-  unsigned long long* d_counters;  // [0] calls total [1] hard in chunk [2] range lo [3] range hi [4] hard total [5] error
+  unsigned long long* d_counters;  // [0]/[3] running call total (ping-pong per chunk) [4] hard sites [6] block ticket
   // staging of the host API
   uint16_t* d_stage_counts[2];
   dnv_site_result* d_stage_dense[2];

@@ -8,6 +8,7 @@
 //   base log-lik  hm, ht, mm                                          (:159-165)
 // Compiled with -ffp-contract=off so R/hm/ht/mm carry the same bits a JVM or
 // the CPU oracle computes from the same formulas.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -74,6 +75,15 @@ void build_tables(const dnv_params& p, Tables* t) {
       }
     }
 
+  for (int d = 0; d < 10; d++) {
+    t->rmax_d[d] = -INFINITY;
+    for (int m = 0; m < 10; m++) {
+      double mx = -INFINITY;
+      for (int c = 0; c < 10; c++) mx = std::max(mx, t->rel[d * 100 + m * 10 + c]);
+      t->rmax_dm[d * 10 + m] = mx;
+      t->rmax_d[d] = std::max(t->rmax_d[d], mx);
+    }
+  }
   // linear-domain path: likelihood ratios against the mismatch likelihood
   const long double l2e = 1.442695040888963407359924681001892137L;
   const long double le = (long double)eps;

@@ -33,13 +33,34 @@ namespace dnv {
 constexpr int kFastThreads = 128;
 constexpr int kTileBytes = kFastThreads * 24;
 
+constexpr int kFastWarps = kFastThreads / 32;
+constexpr int kWarpTileBytes = 32 * 24;  // one warp's tile: 32 sites x 24 B
+
 struct FastShared {
   double pw_inv[2][kPowTable];  // r_j^-i
   double pw_m[2][kPowTable];    // mantissa of r_j^k
   int32_t pw_e[2][kPowTable];   // exponent of r_j^k
-  alignas(16) unsigned char tile[2][kTileBytes];
-  alignas(8) unsigned long long bar[2];
+  double rel[1000];             // exact path: getRelationshipLogLikelihood
+  uint32_t isden[32];           // exact path: isDenovoMap
+  double rmax[110];             // exact MAP pruning bounds
+  double warp_L[kFastWarps][32];  // exact path: per-warp read log-likelihoods
+  alignas(16) unsigned char tile[kFastWarps][2][kWarpTileBytes];
+  alignas(8) unsigned long long bar[kFastWarps][2];
 };
+
+// site-invariant scalars, passed by value (constant bank: no global loads in the hot loop)
+struct FastConsts {
+  double k_men, kd9, kd8, kd7, kd6, thr, mm2, lrt_threshold, hm, ht, mm;
+  int method, lin_ok;
+};
+
+inline FastConsts make_fast_consts(const Tables& t) {
+  FastConsts k;
+  k.k_men = t.k_men; k.kd9 = t.k_den[0]; k.kd8 = 2.0 * t.k_den[1]; k.kd7 = 4.0 * t.k_den[2]; k.kd6 = 4.0 * t.k_den[3];
+  k.thr = t.lrt_thr; k.mm2 = t.mm2; k.lrt_threshold = t.lrt_threshold; k.hm = t.hm; k.ht = t.ht; k.mm = t.mm;
+  k.method = t.method; k.lin_ok = t.fast_ok;
+  return k;
+}
 
 // ---- TMA bulk copy + mbarrier (PTX; SASS: UBLKCP / SYNCS) -------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -74,27 +95,42 @@ __device__ __forceinline__ double scale_pow2(double m, int sh) {
   return (sh < -1000) ? 0.0 : __hiloint2double(hi, __double2loint(m));
 }
 
+// power-table accessors: shared memory (hot kernel) or global/L1 (per-call records)
+struct SmemPow {
+  const FastShared& s;
+  __device__ __forceinline__ double inv(int j, int i) const { return s.pw_inv[j][i]; }
+  __device__ __forceinline__ double mant(int j, int i) const { return s.pw_m[j][i]; }
+  __device__ __forceinline__ int expo(int j, int i) const { return s.pw_e[j][i]; }
+};
+struct GmemPow {
+  const Tables* t;
+  __device__ __forceinline__ double inv(int j, int i) const { return __ldg(&t->pw_inv[j][i]); }
+  __device__ __forceinline__ double mant(int j, int i) const { return __ldg(&t->pw_m[j][i]); }
+  __device__ __forceinline__ int expo(int j, int i) const { return __ldg(&t->pw_e[j][i]); }
+};
+
 // Scaled genotype likelihoods ev[10] of one person (largest entry in [1,2));
 // returns the binary exponent divided out.  All k < kPowTable (checked by caller).
-__device__ __forceinline__ int person_linear(const FastShared& s, const int* n, double* ev) {
+template <typename Pow>
+__device__ __forceinline__ int person_linear(const Pow& s, const int* n, double* ev) {
   const int k_hom = max(max(n[0], n[1]), max(n[2], n[3]));
   const int s01 = n[0] + n[1], s02 = n[0] + n[2], s03 = n[0] + n[3], s12 = n[1] + n[2], s13 = n[1] + n[3],
             s23 = n[2] + n[3];
   const int k_het = max(max(max(s01, s02), max(s03, s12)), max(s13, s23));
-  const int e1 = s.pw_e[0][k_hom], e2 = s.pw_e[1][k_het];
+  const int e1 = s.expo(0, k_hom), e2 = s.expo(1, k_het);
   const int emax = max(e1, e2);
-  const double sc1 = scale_pow2(s.pw_m[0][k_hom], e1 - emax);
-  const double sc2 = scale_pow2(s.pw_m[1][k_het], e2 - emax);
-  ev[0] = sc1 * s.pw_inv[0][k_hom - n[0]];
-  ev[1] = sc2 * s.pw_inv[1][k_het - s01];
-  ev[2] = sc2 * s.pw_inv[1][k_het - s02];
-  ev[3] = sc2 * s.pw_inv[1][k_het - s03];
-  ev[4] = sc1 * s.pw_inv[0][k_hom - n[1]];
-  ev[5] = sc2 * s.pw_inv[1][k_het - s12];
-  ev[6] = sc2 * s.pw_inv[1][k_het - s13];
-  ev[7] = sc1 * s.pw_inv[0][k_hom - n[2]];
-  ev[8] = sc2 * s.pw_inv[1][k_het - s23];
-  ev[9] = sc1 * s.pw_inv[0][k_hom - n[3]];
+  const double sc1 = scale_pow2(s.mant(0, k_hom), e1 - emax);
+  const double sc2 = scale_pow2(s.mant(1, k_het), e2 - emax);
+  ev[0] = sc1 * s.inv(0, k_hom - n[0]);
+  ev[1] = sc2 * s.inv(1, k_het - s01);
+  ev[2] = sc2 * s.inv(1, k_het - s02);
+  ev[3] = sc2 * s.inv(1, k_het - s03);
+  ev[4] = sc1 * s.inv(0, k_hom - n[1]);
+  ev[5] = sc2 * s.inv(1, k_het - s12);
+  ev[6] = sc2 * s.inv(1, k_het - s13);
+  ev[7] = sc1 * s.inv(0, k_hom - n[2]);
+  ev[8] = sc2 * s.inv(1, k_het - s23);
+  ev[9] = sc1 * s.inv(0, k_hom - n[3]);
   return emax;
 }
 
@@ -118,7 +154,8 @@ struct LinOut {
 };
 
 // the factored linear-domain evaluation of one site (BAYES / LRT decision)
-__device__ __forceinline__ void linear_site(const FastShared& s, const int* c, double k_men, double kd9,
+template <typename Pow>
+__device__ __forceinline__ void linear_site(const Pow& s, const int* c, double k_men, double kd9,
                                             double kd8, double kd7, double kd6, double thr, double mm2,
                                             int method, double lrt_threshold, LinOut& o) {
   const int nd = (c[0] + c[1]) + (c[2] + c[3]), nm = (c[4] + c[5]) + (c[6] + c[7]),
@@ -158,6 +195,23 @@ __device__ __forceinline__ void linear_site(const FastShared& s, const int* c, d
   o.den_s = den_s; o.men_s = men_s; o.s2 = s2; o.dn = dn; o.hard = hard; o.zd = zd; o.zm = zm;
 }
 
+// p, LR and the two log-likelihoods from the factored form (reference special values where a
+// raw sum is exactly zero); only valid when !lo.hard
+__device__ __forceinline__ void linear_values(const LinOut& lo, double& p, double& lr, double& log_men,
+                                              double& log_den) {
+  const double ln2 = 0.693147180559945309417;
+  const bool den0 = lo.zd == 1, men0 = lo.zm == 1;
+  if (!den0 && !men0) {
+    p = lo.den_s / (lo.den_s + lo.men_s);
+    lr = lo.den_s / lo.men_s;
+  } else {
+    p = den0 ? (men0 ? NAN : 0.0) : 1.0;
+    lr = den0 ? (men0 ? NAN : 0.0) : INFINITY;
+  }
+  log_den = den0 ? -INFINITY : fma(lo.s2, ln2, log(lo.den_s));
+  log_men = men0 ? -INFINITY : fma(lo.s2, ln2, log(lo.men_s));
+}
+
 __device__ __forceinline__ void unpack_counts(const uint2* p, int* c) {
 #pragma unroll
   for (int i = 0; i < 3; i++) {
@@ -171,21 +225,22 @@ __device__ __forceinline__ void unpack_counts(const uint2* p, int* c) {
 
 // kLin: evaluate the linear-domain posterior (BAYES/LRT decision, dense values)
 // kMap: evaluate the exact log-domain argmax (MAP decision, dense maxGenoType)
+// Each WARP walks its own tiles of 32 sites (768 B of counts per tile, TMA bulk copy into a
+// warp-private double buffer, warp-private mbarriers): no block-wide barrier in the loop.
 template <bool kLin, bool kMap, bool kDense, int kMinBlocks>
 __global__ void __launch_bounds__(kFastThreads, kMinBlocks)
-trio_fast_kernel(const Tables* __restrict__ tab, const uint16_t* __restrict__ counts, int64_t n,
-                 uint32_t* __restrict__ bits, uint32_t* __restrict__ hard_list,
-                 unsigned long long* __restrict__ counters, dnv_site_result* __restrict__ dense) {
+trio_fast_kernel(const Tables* __restrict__ tab, const FastConsts k, const uint16_t* __restrict__ counts, int64_t n,
+                 uint32_t* __restrict__ bits, unsigned long long* __restrict__ counters,
+                 dnv_site_result* __restrict__ dense) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FastShared& s = *reinterpret_cast<FastShared*>(smem_raw);
-  double* s_rel = reinterpret_cast<double*>(smem_raw + sizeof(FastShared));  // kMap only
-  uint32_t* s_isden = reinterpret_cast<uint32_t*>(s_rel + 1000);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-  const int64_t n_tiles = (n + kFastThreads - 1) / kFastThreads;
+  const int64_t n_tiles = (n + 31) / 32;
   const bool tma_ok = (reinterpret_cast<uintptr_t>(counts) & 15) == 0;
-  if (threadIdx.x == 0) {
-    mbar_init(&s.bar[0], 1);
-    mbar_init(&s.bar[1], 1);
+  if (lane == 0) {
+    mbar_init(&s.bar[warp][0], 1);
+    mbar_init(&s.bar[warp][1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (kLin) {
@@ -195,92 +250,65 @@ trio_fast_kernel(const Tables* __restrict__ tab, const uint16_t* __restrict__ co
       (&s.pw_e[0][0])[i] = (&tab->pw_e[0][0])[i];
     }
   }
-  if (kMap) stage_exact_tables(tab, s_rel, s_isden);
+  stage_exact_tables(tab, s.rel, s.isden);
+  if (kMap) stage_map_bounds(tab, s.rmax);
   __syncthreads();
 
-  const int method = tab->method;
-  const bool lin_ok = tab->fast_ok != 0;
-  const double k_men = tab->k_men;
-  const double kd9 = tab->k_den[0], kd8 = 2.0 * tab->k_den[1], kd7 = 4.0 * tab->k_den[2],
-               kd6 = 4.0 * tab->k_den[3];
-  const double thr = tab->lrt_thr, mm2 = tab->mm2, lrt_threshold = tab->lrt_threshold;
-
-  // tile t is bulk-copied when it is full (its byte count is a multiple of 16)
+  // a full tile (32 sites, 768 B: a multiple of 16) is bulk-copied; the ragged last one is not
   auto issue = [&](int64_t t, int buf) {
-    if (threadIdx.x == 0 && tma_ok && (t + 1) * kFastThreads <= n) {
-      mbar_expect_tx(&s.bar[buf], kTileBytes);
-      tma_bulk_g2s(s.tile[buf], counts + t * kFastThreads * 12, kTileBytes, &s.bar[buf]);
+    if (lane == 0 && tma_ok && (t + 1) * 32 <= n) {
+      mbar_expect_tx(&s.bar[warp][buf], kWarpTileBytes);
+      tma_bulk_g2s(s.tile[warp][buf], counts + t * 32 * 12, kWarpTileBytes, &s.bar[warp][buf]);
     }
   };
-  uint32_t phase[2] = {0, 0};
+  const int64_t warps_total = (int64_t)gridDim.x * kFastWarps;
+  uint32_t phase0 = 0, phase1 = 0;
   int buf = 0;
-  int64_t t = blockIdx.x;
+  int64_t t = (int64_t)blockIdx.x * kFastWarps + warp;
   if (t < n_tiles) issue(t, 0);
-  for (; t < n_tiles; t += gridDim.x, buf ^= 1) {
-    const int64_t t_next = t + gridDim.x;
-    if (t_next < n_tiles) issue(t_next, buf ^ 1);
-    const int64_t site = t * kFastThreads + threadIdx.x;
+  for (; t < n_tiles; t += warps_total, buf ^= 1) {
+    const int64_t site = t * 32 + lane;
     int c[12];
-    if (tma_ok && (t + 1) * kFastThreads <= n) {
-      mbar_wait(&s.bar[buf], phase[buf]);
-      phase[buf] ^= 1;
-      unpack_counts(reinterpret_cast<const uint2*>(s.tile[buf] + threadIdx.x * 24), c);
+    if (tma_ok && (t + 1) * 32 <= n) {
+      if (buf == 0) { mbar_wait(&s.bar[warp][0], phase0); phase0 ^= 1; }
+      else { mbar_wait(&s.bar[warp][1], phase1); phase1 ^= 1; }
+      unpack_counts(reinterpret_cast<const uint2*>(s.tile[warp][buf] + lane * 24), c);
     } else if (site < n) {
       unpack_counts(reinterpret_cast<const uint2*>(counts + site * 12), c);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 12; q++) c[q] = 0;
     }
-    __syncthreads();  // every thread has its counts in registers: the buffer may be refilled
+    __syncwarp();  // the whole warp has read the buffer that the next-but-one tile will overwrite
+    if (t + warps_total < n_tiles) issue(t + warps_total, buf ^ 1);
 
     bool dn = false, hard = false;
+    dnv_site_result o;
     if (site < n) {
-      dnv_site_result o;
       if (kLin) {
         LinOut lo;
-        if (lin_ok) {
-          linear_site(s, c, k_men, kd9, kd8, kd7, kd6, thr, mm2, method, lrt_threshold, lo);
+        if (k.lin_ok) {
+          linear_site(SmemPow{s}, c, k.k_men, k.kd9, k.kd8, k.kd7, k.kd6, k.thr, k.mm2, k.method, k.lrt_threshold, lo);
         } else {  // eps so large that r <= 1: the table scheme does not apply
           lo.hard = true; lo.dn = false; lo.zd = lo.zm = 2; lo.den_s = lo.men_s = lo.s2 = 0.0;
         }
         dn = lo.dn;
         hard = lo.hard;
-        if (kDense && !hard) {
-          const double ln2 = 0.693147180559945309417;
-          const bool den0 = lo.zd == 1, men0 = lo.zm == 1;
-          if (!den0 && !men0) {
-            o.p = lo.den_s / (lo.den_s + lo.men_s);
-            o.lr = lo.den_s / lo.men_s;
-          } else {
-            o.p = den0 ? (men0 ? NAN : 0.0) : 1.0;
-            o.lr = den0 ? (men0 ? NAN : 0.0) : INFINITY;
-          }
-          o.log_den = den0 ? -INFINITY : fma(lo.s2, ln2, log(lo.den_s));
-          o.log_men = men0 ? -INFINITY : fma(lo.s2, ln2, log(lo.men_s));
-        }
+        if (kDense && !hard) linear_values(lo, o.p, o.lr, o.log_men, o.log_den);
       }
       if (kMap) {
-        // exact log-domain sweep, M/DenovoBayesNet.java:260-278
+        // exact log-domain argmax (pruned; bit-identical to the sweep of M/DenovoBayesNet.java:260-278)
         uint16_t cu[12];
 #pragma unroll
-        for (int k = 0; k < 12; k++) cu[k] = (uint16_t)c[k];
+        for (int q = 0; q < 12; q++) cu[q] = (uint16_t)c[q];
         double Ld[10], Lm[10], Lc[10];
-        exact_read_loglik(cu + 0, tab->hm, tab->ht, tab->mm, Ld);
-        exact_read_loglik(cu + 4, tab->hm, tab->ht, tab->mm, Lm);
-        exact_read_loglik(cu + 8, tab->hm, tab->ht, tab->mm, Lc);
-        double max_ll = -INFINITY;
-        int best = 0;
-#pragma unroll 1
-        for (int d = 0; d < 10; d++) {
-#pragma unroll 1
-          for (int m = 0; m < 10; m++) {
-            const double dm = __dadd_rn(Ld[d], Lm[m]);
-            const int b0 = d * 100 + m * 10;
-#pragma unroll
-            for (int ch = 0; ch < 10; ch++) {
-              const double ll = __dadd_rn(__dadd_rn(dm, Lc[ch]), s_rel[b0 + ch]);
-              if (ll > max_ll) { max_ll = ll; best = b0 + ch; }
-            }
-          }
-        }
-        if (method == DNV_METHOD_MAP) dn = (s_isden[best >> 5] >> (best & 31)) & 1u;
+        exact_read_loglik(cu + 0, k.hm, k.ht, k.mm, Ld);
+        exact_read_loglik(cu + 4, k.hm, k.ht, k.mm, Lm);
+        exact_read_loglik(cu + 8, k.hm, k.ht, k.mm, Lc);
+        double max_ll;
+        int best;
+        exact_map_pruned(Ld, Lm, Lc, s.rel, s.rmax, &best, &max_ll);
+        if (k.method == DNV_METHOD_MAP) dn = (s.isden[best >> 5] >> (best & 31)) & 1u;
         if (kDense) {
           o.max_ll = max_ll;
           o.dad = (uint8_t)(best / 100); o.mom = (uint8_t)((best / 10) % 10); o.child = (uint8_t)(best % 10);
@@ -292,16 +320,27 @@ trio_fast_kernel(const Tables* __restrict__ tab, const uint16_t* __restrict__ co
         dense[site] = o;
       }
     }
-    const uint32_t word = __ballot_sync(0xffffffffu, dn && !hard);
-    const uint32_t hword = __ballot_sync(0xffffffffu, hard);
-    const int lane = threadIdx.x & 31;
-    if (lane == 0 && site < n) bits[site >> 5] = word;
+    // hard sites (threshold-ambiguous, underflow gray zone, deeper than the tables): the whole
+    // warp evaluates them one at a time with the exact direct form
+    uint32_t hword = __ballot_sync(0xffffffffu, hard);
     if (hword) {
-      unsigned long long slot = 0;
-      if (lane == 0) slot = atomicAdd(&counters[1], (unsigned long long)__popc(hword));
-      slot = __shfl_sync(0xffffffffu, slot, 0);
-      if (hard) hard_list[slot + __popc(hword & ((1u << lane) - 1))] = (uint32_t)site;
+      if (lane == 0) atomicAdd(&counters[4], (unsigned long long)__popc(hword));
+      while (hword) {
+        const int h = __ffs(hword) - 1;
+        hword &= hword - 1;
+        uint16_t cu[12];
+#pragma unroll
+        for (int q = 0; q < 12; q++) cu[q] = (uint16_t)__shfl_sync(0xffffffffu, c[q], h);
+        ExactOut r;
+        exact_site_warp(cu, s.rel, s.isden, s.warp_L[warp], k.hm, k.ht, k.mm, k.method, k.lrt_threshold, &r);
+        if (lane == h) {
+          dn = r.is_denovo;
+          if (kDense) store_dense(dense, site, r, 1u);
+        }
+      }
     }
+    const uint32_t word = __ballot_sync(0xffffffffu, dn);
+    if (lane == 0) bits[t] = word;
   }
 }
 
@@ -309,17 +348,17 @@ template <bool kLin, bool kMap, bool kDense, int kMinBlocks>
 static int launch_fast_variant(dnv_ctx* ctx, const uint16_t* d_counts, int64_t n, dnv_site_result* d_dense) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-  const size_t smem = sizeof(FastShared) + (kMap ? 1000 * sizeof(double) + 32 * sizeof(uint32_t) : 0);
+  const size_t smem = sizeof(FastShared);
   auto kern = trio_fast_kernel<kLin, kMap, kDense, kMinBlocks>;
   DNV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
   DNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFastThreads, smem));
   if (per_sm < 1) per_sm = 1;
   const int64_t want = (n + kFastThreads - 1) / kFastThreads;
-  const int64_t persistent = (int64_t)sms * per_sm;  // one resident wave, each CTA walks its tiles
+  const int64_t persistent = (int64_t)sms * per_sm;  // one resident wave; every warp walks its tiles
   const int grid = (int)(want < persistent ? want : persistent);
-  kern<<<grid, kFastThreads, smem, ctx->stream>>>(ctx->d_tab, d_counts, n, ctx->d_bits, ctx->d_hard_list,
-                                                  ctx->d_counters, d_dense);
+  const FastConsts k = make_fast_consts(ctx->h_tab);
+  kern<<<grid, kFastThreads, smem, ctx->stream>>>(ctx->d_tab, k, d_counts, n, ctx->d_bits, ctx->d_counters, d_dense);
   DNV_CUDA(cudaGetLastError());
   return DNV_OK;
 }
