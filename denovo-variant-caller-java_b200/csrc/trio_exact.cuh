@@ -172,16 +172,32 @@ __device__ __forceinline__ void exact_map_pruned(const double* Ld, const double*
       if (ll > best_v) { best_v = ll; best = b0 + ch; }
     }
   }
-#pragma unroll 1
+  // all ten row bounds at once (independent chains), then only the surviving rows
+  uint32_t mask_d = 0;
+#pragma unroll
   for (int d = 0; d < 10; d++) {
-    const double ld = Ld[d];
-    const double ud = __dadd_rn(__dadd_rn(__dadd_rn(ld, LmX), LcX), s_rmax[100 + d]);
-    if (ud < best_v) continue;
-#pragma unroll 1
+    const double ud = __dadd_rn(__dadd_rn(__dadd_rn(Ld[d], LmX), LcX), s_rmax[100 + d]);
+    mask_d |= (ud >= best_v ? 1u : 0u) << d;
+  }
+  while (mask_d) {
+    const int d = __ffs(mask_d) - 1;
+    mask_d &= mask_d - 1;
+    double ld = Ld[0];  // select chain: keeps Ld[] in registers (no dynamic indexing)
+#pragma unroll
+    for (int g = 1; g < 10; g++) ld = (d == g) ? Ld[g] : ld;
+    uint32_t mask_m = 0;
+#pragma unroll
     for (int m = 0; m < 10; m++) {
-      const double dm = __dadd_rn(ld, Lm[m]);
-      const double udm = __dadd_rn(__dadd_rn(dm, LcX), s_rmax[d * 10 + m]);
-      if (udm < best_v) continue;
+      const double udm = __dadd_rn(__dadd_rn(__dadd_rn(ld, Lm[m]), LcX), s_rmax[d * 10 + m]);
+      mask_m |= (udm >= best_v ? 1u : 0u) << m;
+    }
+    while (mask_m) {
+      const int m = __ffs(mask_m) - 1;
+      mask_m &= mask_m - 1;
+      double lm = Lm[0];
+#pragma unroll
+      for (int g = 1; g < 10; g++) lm = (m == g) ? Lm[g] : lm;
+      const double dm = __dadd_rn(ld, lm);
       const int b0 = d * 100 + m * 10;
 #pragma unroll
       for (int ch = 0; ch < 10; ch++) {

@@ -366,7 +366,7 @@ static int launch_fast_variant(dnv_ctx* ctx, const uint16_t* d_counts, int64_t n
 inline int launch_trio_fast(dnv_ctx* ctx, const uint16_t* d_counts, int64_t n, dnv_site_result* d_dense) {
   const bool map = ctx->prm.method == DNV_METHOD_MAP;
   if (d_dense) return launch_fast_variant<true, true, true, 2>(ctx, d_counts, n, d_dense);
-  if (map) return launch_fast_variant<false, true, false, 2>(ctx, d_counts, n, nullptr);
+  if (map) return launch_fast_variant<false, true, false, 4>(ctx, d_counts, n, nullptr);
   static const int tune = getenv("DNV_FAST_MINBLOCKS") ? atoi(getenv("DNV_FAST_MINBLOCKS")) : 3;  // tuning knob
   if (tune == 2) return launch_fast_variant<true, false, false, 2>(ctx, d_counts, n, nullptr);
   if (tune == 4) return launch_fast_variant<true, false, false, 4>(ctx, d_counts, n, nullptr);
