@@ -19,6 +19,13 @@
 //                    an entry with end > pos, and every earlier entry has end <= pos)
 // The input-domain conditions (sorted, end > start for admitted entries) are
 // CHECKED on the device and violations fail loudly with DNV_E_UNSORTED.
+//
+// Two kernels, each ONE pass with decoupled look-back (no separate scan passes):
+//   A  mendel_admit_compact_kernel : reads each 32-byte record once; admission; ordered
+//      compaction into the CHILD/MOM/DAD queues (3 sum chains) and the running max of
+//      `end` of each parent queue (2 max chains), written straight from registers
+//   B  mendel_join_emit_kernel     : per child SNP the two searches per parent, confined to
+//      the block's window; truth-table lookup; ordered emission of PositionCalls
 #include <limits.h>
 #include <algorithm>
 
@@ -39,248 +46,342 @@ __device__ __forceinline__ int geno_of(int x, int y) {  // Genotype.valueOfPairA
   return x * 4 - (x * (x - 1)) / 2 + (y - x);
 }
 
+constexpr int kMB = 256;  // records (kernel A) / child SNPs (kernel B) per block
+
 struct MendelArrays {
-  // per-person admitted entries in stream order
+  // per-person admitted entries in stream order (SoA queues)
   int64_t* start[3];
-  int64_t* end[3];      // parents: running max of end after the scan
+  int64_t* runmax[3];   // parents: running max of `end` over the queue up to and including the entry
   uint8_t* code[3];
   uint8_t* ref;         // child only: allele index of the reference base (or 0xFF)
   int64_t* src;         // child only: index in the input stream
-  uint32_t* bits[3];    // admission masks
-  uint32_t* block_sums[3];
-  unsigned long long* totals;  // [0..2] per-person admitted, [3] found, [4] error index+1, [5] error kind
-  // join outputs
-  uint32_t* found_bits;
-  uint32_t* found_block_sums;
-  uint32_t* packed;     // per child: child | mom<<8 | dad<<16
+  // decoupled look-back status, zeroed before every call: [63:62] 1 aggregate / 2 inclusive prefix, [61:0] value
+  unsigned long long* st_sum[3];   // admitted counts per person
+  unsigned long long* st_max[3];   // running max of end (+1; 0 = none) per parent
+  unsigned long long* st_found;    // PositionCalls
+  unsigned long long* totals;      // [0..2] admitted per person, [3] PositionCalls, [4] error index+1, [5] error kind, [6],[7] tickets
 };
 
-// ---- pass A: admission (checkAndAdd) + domain checks
-__global__ void __launch_bounds__(kScanThreads)
-mendel_admit_kernel(const dnv_vcall* __restrict__ calls, int64_t n, MendelArrays A) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool adm = false;
-  int person = 3;
-  if (i < n) {
-    const dnv_vcall v = calls[i];
-    person = v.person;
-    const bool ins = (v.ngt >= 1 && v.gt0 > 0 && v.alt0_len != 1) || (v.ngt >= 2 && v.gt1 > 0 && v.alt1_len != 1);
-    const bool del = v.ref_len != 1;
-    const bool snp = (v.end == v.start + 1) && !del && !ins;
-    const bool dot = (v.ngt >= 1 && v.gt0 == -1) || (v.ngt >= 2 && v.gt1 == -1);
-    adm = person <= 2 && !((person == kChild && !snp) || dot || v.ngt != 2 || !v.filter_pass || ins || del);
-    bool bad = false;
-    if (i > 0 && calls[i - 1].start > v.start) bad = true;  // stream must be sorted by start
-    if (adm && v.end <= v.start) bad = true;                // empty interval: outside the batch-equivalence domain
-    if (bad) { atomicMax(&A.totals[4], (unsigned long long)(i + 1)); A.totals[5] = (unsigned long long)(-DNV_E_UNSORTED); }
-  }
+constexpr unsigned long long kStAgg = 1ull << 62, kStPre = 2ull << 62, kStVal = (1ull << 62) - 1;
+
+// one warp: exclusive combination (sum or max) of all predecessor blocks' values
+template <bool kMax>
+__device__ __forceinline__ unsigned long long lookback(unsigned long long* status, unsigned int b,
+                                                       unsigned long long mine, int lane) {
+  unsigned long long excl = 0;
+  if (b > 0) {
+    if (lane == 0) atomicExch(&status[b], kStAgg | mine);
+    int hi = (int)b - 1;
+    for (;;) {
+      const int p = hi - lane;
+      unsigned long long v = kStPre;  // before block 0: empty inclusive prefix
+      if (p >= 0) {
+        do { v = *(volatile unsigned long long*)&status[p]; } while ((v >> 62) == 0);
+      }
+      const uint32_t is_pre = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
+      const int stop = is_pre ? __ffs(is_pre) - 1 : 31;
+      unsigned long long val = lane <= stop ? (v & kStVal) : 0ull;
 #pragma unroll
-  for (int p = 0; p < 3; p++) {
-    const uint32_t w = __ballot_sync(0xffffffffu, adm && person == p);
-    if ((threadIdx.x & 31) == 0 && i < n) A.bits[p][i >> 5] = w;
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long y = __shfl_xor_sync(0xffffffffu, val, o);
+        val = kMax ? (y > val ? y : val) : val + y;
+      }
+      excl = kMax ? (val > excl ? val : excl) : excl + val;
+      if (is_pre) break;
+      hi -= 32;
+    }
   }
+  if (lane == 0) {
+    const unsigned long long incl = kMax ? (mine > excl ? mine : excl) : excl + mine;
+    atomicExch(&status[b], kStPre | incl);
+  }
+  return excl;
 }
 
-// ---- pass C: scatter admitted entries into per-person SoA queues (stream order)
-__global__ void __launch_bounds__(kScanThreads)
-mendel_scatter_kernel(const dnv_vcall* __restrict__ calls, int64_t n_words, MendelArrays A) {
-  const int64_t w = (int64_t)blockIdx.x * kScanThreads + threadIdx.x;
-#pragma unroll 1
-  for (int p = 0; p < 3; p++) {
-    uint32_t word = (w < n_words) ? A.bits[p][w] : 0u;
-    int64_t pos = word_rank(word, A.block_sums[p]);
-    while (word) {
-      const int b = __ffs(word) - 1;
-      word &= word - 1;
-      const int64_t i = w * 32 + b;
-      const dnv_vcall v = calls[i];
-      const bool snp = v.end == v.start + 1;  // admitted => ref_len == 1 and no insertion
-      uint8_t code = kCodeBlock;
-      if (snp) {  // getGenotypeFromSNP, :228-239
+// ---- kernel A: admission (checkAndAdd) + domain checks + ordered compaction into the three
+// queues + running max of end for the parents, in ONE pass over the 32-byte records.
+// A block owns kMI * kMB consecutive records (round j: record b*kMI*kMB + j*kMB + thread, so
+// every load is coalesced); the essentials of its records stay in registers while the block's
+// totals go through the look-back chains.
+constexpr int kMI = 8;                    // records (A) / child SNPs (B) per thread
+constexpr int kMTile = kMI * kMB;
+constexpr int kMW = kMB / 32;             // warps per block
+
+__global__ void __launch_bounds__(kMB)
+mendel_admit_compact_kernel(const dnv_vcall* __restrict__ calls, int64_t n, MendelArrays A) {
+  __shared__ unsigned int s_bid;
+  __shared__ int s_cnt[3][kMI * kMW + 1];                 // per (round, warp) admitted counts -> exclusive offsets
+  __shared__ unsigned long long s_max[2][kMI * kMW + 1];  // per (round, warp) max of end+1 -> exclusive running max
+  __shared__ unsigned long long s_excl[5];
+  if (threadIdx.x == 0) s_bid = (unsigned int)atomicAdd(&A.totals[6], 1ull);
+  __syncthreads();
+  const unsigned int b = s_bid;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int64_t st[kMI];
+  uint32_t meta[kMI];  // bit0 admitted, bits 2:1 person, bits 15:8 genotype code, bits 23:16 ref allele, bits 31:24 rank in warp
+  unsigned long long myrun[kMI];  // warp-inclusive running max (end+1) over entries of my own parent queue
+#pragma unroll
+  for (int j = 0; j < kMI; j++) {
+    const int64_t i = (int64_t)b * kMTile + (int64_t)j * kMB + threadIdx.x;
+    bool adm = false;
+    int person = 3;
+    dnv_vcall v;
+    v.start = 0; v.end = 0; v.gt0 = v.gt1 = 0; v.ref_base = 0; v.alt0_base = v.alt1_base = 0;
+    if (i < n) {
+      v = calls[i];
+      person = v.person;
+      const bool ins = (v.ngt >= 1 && v.gt0 > 0 && v.alt0_len != 1) || (v.ngt >= 2 && v.gt1 > 0 && v.alt1_len != 1);
+      const bool del = v.ref_len != 1;
+      const bool snp = (v.end == v.start + 1) && !del && !ins;
+      const bool dot = (v.ngt >= 1 && v.gt0 == -1) || (v.ngt >= 2 && v.gt1 == -1);
+      adm = person <= 2 && !((person == kChild && !snp) || dot || v.ngt != 2 || !v.filter_pass || ins || del);
+      bool bad = false;
+      if (i > 0 && calls[i - 1].start > v.start) bad = true;  // stream must be sorted by start
+      if (adm && (v.end <= v.start || v.start < 0 || v.end >= (1ll << 60))) bad = true;  // outside the batch-equivalence domain
+      if (bad) { atomicMax(&A.totals[4], (unsigned long long)(i + 1)); A.totals[5] = (unsigned long long)(-DNV_E_UNSORTED); }
+    }
+    uint32_t code = kCodeBlock, ref = 0xFF;
+    if (adm) {
+      if (v.end == v.start + 1) {  // admitted => ref_len == 1 and no insertion: getGenotypeFromSNP, :228-239
         const int a0 = allele_of(v.gt0 > 0 ? v.alt0_base : v.ref_base);
         const int a1 = allele_of(v.gt1 > 0 ? v.alt1_base : v.ref_base);
-        code = (a0 < 0 || a1 < 0) ? kCodeBad : (uint8_t)geno_of(a0, a1);
+        code = (a0 < 0 || a1 < 0) ? kCodeBad : (uint32_t)geno_of(a0, a1);
       }
-      A.start[p][pos] = v.start;
-      A.end[p][pos] = v.end;
-      A.code[p][pos] = code;
-      if (p == kChild) {
-        const int r = allele_of(v.ref_base);
-        A.ref[pos] = r < 0 ? 0xFF : (uint8_t)r;
-        A.src[pos] = i;
+      const int r = allele_of(v.ref_base);
+      ref = r < 0 ? 0xFFu : (uint32_t)r;
+    }
+    int rank = 0;
+#pragma unroll
+    for (int p = 0; p < 3; p++) {
+      const uint32_t m = __ballot_sync(0xffffffffu, adm && person == p);
+      if (person == p) rank = __popc(m & ((1u << lane) - 1));
+      if (lane == 0) s_cnt[p][j * kMW + warp] = __popc(m);
+    }
+    unsigned long long mine = 0;
+#pragma unroll
+    for (int par = 0; par < 2; par++) {
+      unsigned long long x = (adm && person == par + 1) ? (unsigned long long)v.end + 1ull : 0ull;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x = y > x ? y : x;
       }
-      pos++;
+      if (person == par + 1) mine = x;
+      if (lane == 31) s_max[par][j * kMW + warp] = x;
+    }
+    st[j] = v.start; myrun[j] = mine;
+    meta[j] = (adm ? 1u : 0u) | ((uint32_t)(person & 3) << 1) | (code << 8) | (ref << 16) | ((uint32_t)rank << 24);
+  }
+  __syncthreads();
+  // exclusive scans over the kMI*kMW (round, warp) cells: five small scans, one warp each
+  unsigned long long block_total = 0;
+  if (warp < 3) {
+    int carry = 0;
+    for (int c0 = 0; c0 < kMI * kMW; c0 += 32) {
+      const int v0 = s_cnt[warp][c0 + lane];
+      int x = v0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+      s_cnt[warp][c0 + lane] = carry + x - v0;
+      carry += __shfl_sync(0xffffffffu, x, 31);
+    }
+    block_total = (unsigned long long)carry;
+  } else if (warp < 5) {
+    unsigned long long carry = 0;
+    for (int c0 = 0; c0 < kMI * kMW; c0 += 32) {
+      const unsigned long long v0 = s_max[warp - 3][c0 + lane];
+      unsigned long long x = v0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x = y > x ? y : x; }
+      unsigned long long ex = __shfl_up_sync(0xffffffffu, x, 1);
+      if (lane == 0) ex = 0;
+      s_max[warp - 3][c0 + lane] = ex > carry ? ex : carry;
+      const unsigned long long last = __shfl_sync(0xffffffffu, x, 31);
+      carry = last > carry ? last : carry;
+    }
+    block_total = carry;
+  }
+  // five look-back chains, one warp each
+  if (warp < 3) {
+    const unsigned long long e = lookback<false>(A.st_sum[warp], b, block_total, lane);
+    if (lane == 0) { s_excl[warp] = e; if (b == gridDim.x - 1) A.totals[warp] = e + block_total; }
+  } else if (warp < 5) {
+    const unsigned long long e = lookback<true>(A.st_max[warp - 2], b, block_total, lane);
+    if (lane == 0) s_excl[warp] = e;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kMI; j++) {
+    if (!(meta[j] & 1u)) continue;
+    const int p = (meta[j] >> 1) & 3;
+    const int64_t pos = (int64_t)s_excl[p] + s_cnt[p][j * kMW + warp] + (int)(meta[j] >> 24);
+    A.start[p][pos] = st[j];
+    A.code[p][pos] = (uint8_t)(meta[j] >> 8);
+    if (p == kChild) {
+      A.ref[pos] = (uint8_t)(meta[j] >> 16);
+      A.src[pos] = (int64_t)b * kMTile + (int64_t)j * kMB + threadIdx.x;
+    } else {
+      unsigned long long rm = myrun[j];
+      const unsigned long long e1 = s_max[p - 1][j * kMW + warp], e2 = s_excl[2 + p];
+      rm = e1 > rm ? e1 : rm;
+      rm = e2 > rm ? e2 : rm;
+      A.runmax[p][pos] = (int64_t)rm - 1;
     }
   }
 }
 
-// ---- pass D: inclusive running max of end[] (three-phase scan)
-constexpr int kMaxScanThreads = 256, kMaxScanItems = 8, kMaxScanTile = kMaxScanThreads * kMaxScanItems;
-
-__device__ __forceinline__ long long block_inclusive_max(long long v, long long* s_warp) {
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const long long y = __shfl_up_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) >= o) v = y > v ? y : v;
+// ---- kernel B: join every admitted child SNP against both parents and emit the PositionCalls
+// in stream order (one pass; ordered compaction by look-back).  The binary searches of a block
+// are confined to the window spanned by its first and last child position (both bounds are
+// monotone in the position), so they run out of L1/L2.
+// first index in [lo, hi) with a[idx] > key: 32-ary search by one warp (5 dependent probes per 32M entries)
+__device__ __forceinline__ int64_t warp_upper_bound64(const int64_t* __restrict__ a, int64_t lo, int64_t hi,
+                                                      int64_t key, int lane) {
+  while (hi - lo > 32) {
+    const int64_t step = (hi - lo + 32) / 33;
+    const int64_t idx = lo + (int64_t)(lane + 1) * step - 1;
+    const bool le = idx < hi ? (__ldg(a + idx) <= key) : false;
+    const int c = __popc(__ballot_sync(0xffffffffu, le));
+    const int64_t new_lo = c ? lo + (int64_t)c * step : lo;
+    const int64_t new_hi = c < 32 ? min(hi, lo + (int64_t)(c + 1) * step - 1) : hi;
+    lo = new_lo; hi = new_hi;
   }
-  if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = v;
+  const bool le = lo + lane < hi ? (__ldg(a + lo + lane) <= key) : false;
+  return lo + __popc(__ballot_sync(0xffffffffu, le));
+}
+
+__device__ __forceinline__ int64_t upper_bound_le(const int64_t* __restrict__ a, int64_t lo, int64_t hi, int64_t key) {
+  while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (__ldg(a + mid) <= key) lo = mid + 1; else hi = mid; }
+  return lo;  // first index with a[idx] > key
+}
+
+constexpr int kJI = 2;                 // child SNPs per thread in kernel B
+constexpr int kJTile = kJI * kMB;      // 512 children per block
+constexpr int kJCap = 1536;            // parent entries staged per parent (start + running max: 24 KB)
+
+__device__ __forceinline__ int smem_upper_bound_le(const int64_t* a, int lo, int hi, int64_t key) {
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] <= key) lo = mid + 1; else hi = mid; }
+  return lo;
+}
+
+__global__ void __launch_bounds__(kMB)
+mendel_join_emit_kernel(const Tables* __restrict__ tab, MendelArrays A, dnv_pcall* __restrict__ out, int64_t cap) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int64_t* s_start = reinterpret_cast<int64_t*>(smem_raw);  // [2][kJCap]
+  int64_t* s_rmax = s_start + 2 * kJCap;                      // [2][kJCap]
+  __shared__ unsigned int s_bid;
+  __shared__ long long s_win[2][4];
+  __shared__ int s_cnt[kJI * kMW + 32];
+  __shared__ unsigned long long s_excl;
+  if (threadIdx.x == 0) s_bid = (unsigned int)atomicAdd(&A.totals[7], 1ull);
   __syncthreads();
-  long long carry = LLONG_MIN;
-  for (int i = 0; i < (int)(threadIdx.x >> 5); i++) carry = s_warp[i] > carry ? s_warp[i] : carry;
-  __syncthreads();
-  return carry > v ? carry : v;
-}
-
-__global__ void __launch_bounds__(kMaxScanThreads)
-runmax_tile_kernel(int64_t* __restrict__ end, const unsigned long long* __restrict__ n_ptr,
-                   long long* __restrict__ tile_max) {
-  const int64_t n = (int64_t)*n_ptr;
-  const int64_t base = (int64_t)blockIdx.x * kMaxScanTile + (int64_t)threadIdx.x * kMaxScanItems;
-  if ((int64_t)blockIdx.x * kMaxScanTile >= n) return;
-  __shared__ long long s_warp[kMaxScanThreads / 32];
-  long long v[kMaxScanItems];
-  long long run = LLONG_MIN;
-#pragma unroll
-  for (int k = 0; k < kMaxScanItems; k++) {
-    const long long x = (base + k < n) ? end[base + k] : LLONG_MIN;
-    run = x > run ? x : run;
-    v[k] = run;
-  }
-  const long long incl = block_inclusive_max(run, s_warp);
-  // exclusive prefix of this thread = max over previous threads' totals
-  long long prev = __shfl_up_sync(0xffffffffu, incl, 1);
-  __shared__ long long s_last[kMaxScanThreads / 32];
-  if ((threadIdx.x & 31) == 31) s_last[threadIdx.x >> 5] = incl;
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) prev = threadIdx.x ? s_last[(threadIdx.x >> 5) - 1] : LLONG_MIN;
-#pragma unroll
-  for (int k = 0; k < kMaxScanItems; k++)
-    if (base + k < n) end[base + k] = v[k] > prev ? v[k] : prev;
-  if (threadIdx.x == kMaxScanThreads - 1) tile_max[blockIdx.x] = incl;
-}
-
-__global__ void __launch_bounds__(1024)
-runmax_carry_kernel(long long* __restrict__ tile_max, const unsigned long long* __restrict__ n_ptr) {
-  // serial over chunks of 1024 tiles; converts tile maxima to exclusive carries
-  const int64_t n = (int64_t)*n_ptr;
-  const int n_tiles = (int)((n + kMaxScanTile - 1) / kMaxScanTile);
-  __shared__ long long s_warp[32];
-  __shared__ long long s_carry;
-  if (threadIdx.x == 0) s_carry = LLONG_MIN;
-  __syncthreads();
-  for (int base = 0; base < n_tiles; base += 1024) {
-    const int i = base + threadIdx.x;
-    const long long v = i < n_tiles ? tile_max[i] : LLONG_MIN;
-    const long long incl = block_inclusive_max(v, s_warp);
-    long long prev = __shfl_up_sync(0xffffffffu, incl, 1);
-    __shared__ long long s_last[32];
-    if ((threadIdx.x & 31) == 31) s_last[threadIdx.x >> 5] = incl;
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) prev = threadIdx.x ? s_last[(threadIdx.x >> 5) - 1] : LLONG_MIN;
-    const long long carry = s_carry;
-    if (i < n_tiles) tile_max[i] = prev > carry ? prev : carry;
-    __syncthreads();
-    if (threadIdx.x == 1023) s_carry = incl > carry ? incl : carry;
-    __syncthreads();
-  }
-}
-
-__global__ void __launch_bounds__(kMaxScanThreads)
-runmax_apply_kernel(int64_t* __restrict__ end, const unsigned long long* __restrict__ n_ptr,
-                    const long long* __restrict__ tile_carry) {
-  const int64_t n = (int64_t)*n_ptr;
-  if ((int64_t)blockIdx.x * kMaxScanTile >= n) return;
-  const long long carry = tile_carry[blockIdx.x];
-  if (carry == LLONG_MIN) return;
-  const int64_t base = (int64_t)blockIdx.x * kMaxScanTile;
-  for (int k = threadIdx.x; k < kMaxScanTile; k += kMaxScanThreads)
-    if (base + k < n) { const long long x = end[base + k]; if (carry > x) end[base + k] = carry; }
-}
-
-// ---- pass E: join every admitted child SNP against both parents
-__device__ __forceinline__ int parent_code(const int64_t* __restrict__ start, const int64_t* __restrict__ runmax,
-                                           const uint8_t* __restrict__ code, int64_t n, int64_t pos) {
-  int64_t lo = 0, hi = n;  // ub = #entries with start <= pos
-  while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (__ldg(start + mid) <= pos) lo = mid + 1; else hi = mid; }
-  const int64_t ub = lo;
-  lo = 0; hi = ub;         // first i < ub with runmax[i] > pos
-  while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (__ldg(runmax + mid) > pos) hi = mid; else lo = mid + 1; }
-  return lo < ub ? (int)code[lo] : -1;
-}
-
-__global__ void __launch_bounds__(kScanThreads)
-mendel_join_kernel(MendelArrays A) {
+  const unsigned int b = s_bid;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t n_child = (int64_t)A.totals[kChild];
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool found = false;
-  if (i < n_child) {
-    const int64_t pos = A.start[kChild][i];
-    const int cg = A.code[kChild][i];
-    const int rb = A.ref[i];
-    int g[3] = {cg, -1, -1};
-    bool bad = cg == kCodeBad;
-    found = true;
-    for (int par = kMom; par <= kDad && found; par++) {  // MOM then DAD, :203-220
-      const int c = parent_code(A.start[par], A.end[par], A.code[par], (int64_t)A.totals[par], pos);
-      if (c < 0) { found = false; break; }                // no covering entry -> no PositionCall
-      if (c == kCodeBlock) { if (rb == 0xFF) bad = true; g[par] = geno_of(rb & 3, rb & 3); }
-      else { if (c == kCodeBad) bad = true; g[par] = c; }
+  const int64_t i0 = (int64_t)b * kJTile;
+  if (i0 >= n_child) {  // no child SNP here: nothing to publish, later blocks never look at this one
+    if (n_child == 0 && b == 0 && threadIdx.x == 0) A.totals[3] = 0;
+    return;
+  }
+  const bool live_block = true;
+  const bool last_live = n_child <= i0 + kJTile;
+  // window of each parent queue that the block's children can touch: one warp per bound
+  if (live_block) {
+    const int par = 1 + (warp >> 2), kind = warp & 3;
+    const int64_t np = (int64_t)A.totals[par];
+    const int64_t key = (kind & 1) ? A.start[kChild][min(n_child, i0 + kJTile) - 1] : A.start[kChild][i0];
+    const int64_t r = warp_upper_bound64(kind < 2 ? A.start[par] : A.runmax[par], 0, np, key, lane);
+    if (lane == 0) s_win[par - 1][kind] = r;
+  }
+  __syncthreads();
+  // stage [lo, hi) of both arrays of both parents when the windows fit
+  long long wlo[2], whi[2];
+  bool staged = live_block;
+#pragma unroll
+  for (int q = 0; q < 2; q++) {
+    wlo[q] = min(s_win[q][0], s_win[q][2]);
+    whi[q] = max(s_win[q][1], s_win[q][3]);
+    if (live_block && whi[q] - wlo[q] > kJCap) staged = false;
+  }
+  if (staged) {
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      const int m = (int)(whi[q] - wlo[q]);
+      for (int k = threadIdx.x; k < m; k += kMB) {
+        s_start[q * kJCap + k] = A.start[q + 1][wlo[q] + k];
+        s_rmax[q * kJCap + k] = A.runmax[q + 1][wlo[q] + k];
+      }
     }
-    // the reference evaluates the child genotype first, so a bad child base throws even without parents
-    if (bad) { atomicMax(&A.totals[4], (unsigned long long)(A.src[i] + 1)); A.totals[5] = (unsigned long long)(-DNV_E_BADBASE); found = false; }
-    if (found) A.packed[i] = (uint32_t)g[kChild] | ((uint32_t)g[kMom] << 8) | ((uint32_t)g[kDad] << 16);
   }
-  const uint32_t w = __ballot_sync(0xffffffffu, found);
-  if ((threadIdx.x & 31) == 0 && i < n_child) A.found_bits[i >> 5] = w;
-}
-
-// ---- pass F: PositionCalls in stream order
-__global__ void __launch_bounds__(kScanThreads)
-mendel_emit_kernel(const Tables* __restrict__ tab, MendelArrays A, dnv_pcall* __restrict__ out, int64_t cap) {
-  const int64_t n_child = (int64_t)A.totals[kChild];
-  const int64_t n_words = (n_child + 31) / 32;
-  const int64_t w = (int64_t)blockIdx.x * kScanThreads + threadIdx.x;
-  if ((int64_t)blockIdx.x * kScanThreads >= n_words) return;
-  uint32_t word = (w < n_words) ? A.found_bits[w] : 0u;
-  int64_t pos = word_rank(word, A.found_block_sums);
-  while (word) {
-    const int b = __ffs(word) - 1;
-    word &= word - 1;
-    const int64_t i = w * 32 + b;
-    if (pos < cap) {
-      const uint32_t pk = A.packed[i];
-      const int c = pk & 0xFF, m = (pk >> 8) & 0xFF, d = (pk >> 16) & 0xFF;
-      const int idx = d * 100 + m * 10 + c;
+  __syncthreads();
+  uint32_t packed[kJI];  // bit31 found | rank<<24 | dad<<16 | mom<<8 | child
+#pragma unroll
+  for (int j = 0; j < kJI; j++) {
+    const int64_t i = i0 + (int64_t)j * kMB + threadIdx.x;
+    bool found = false;
+    uint32_t pk = 0;
+    if (i < n_child) {
+      const int64_t pos = A.start[kChild][i];
+      const int cg = A.code[kChild][i];
+      const int rb = A.ref[i];
+      int g[3] = {cg, -1, -1};
+      bool bad = cg == kCodeBad;
+      found = true;
+#pragma unroll
+      for (int par = kMom; par <= kDad; par++) {  // MOM then DAD, :203-220
+        if (!found) break;
+        const int q = par - 1;
+        int64_t ub, is;
+        if (staged) {
+          const int64_t* ss = s_start + q * kJCap;
+          const int64_t* sr = s_rmax + q * kJCap;
+          ub = wlo[q] + smem_upper_bound_le(ss, (int)(s_win[q][0] - wlo[q]), (int)(s_win[q][1] - wlo[q]), pos);  // #entries with start <= pos
+          is = wlo[q] + smem_upper_bound_le(sr, (int)(s_win[q][2] - wlo[q]), (int)(s_win[q][3] - wlo[q]), pos);  // first with running max of end > pos
+        } else {
+          ub = upper_bound_le(A.start[par], s_win[q][0], s_win[q][1], pos);
+          is = upper_bound_le(A.runmax[par], s_win[q][2], s_win[q][3], pos);
+        }
+        if (is >= ub) { found = false; break; }  // no covering entry -> no PositionCall (:211-213)
+        const int c = A.code[par][is];
+        if (c == kCodeBlock) { if (rb == 0xFF) bad = true; g[par] = geno_of(rb & 3, rb & 3); }  // ref+ref of the CHILD's base (:217-219)
+        else { if (c == kCodeBad) bad = true; g[par] = c; }
+      }
+      // the reference evaluates the child genotype first, so a bad child base throws even without parents
+      if (bad) { atomicMax(&A.totals[4], (unsigned long long)(A.src[i] + 1)); A.totals[5] = (unsigned long long)(-DNV_E_BADBASE); found = false; }
+      if (found) pk = (uint32_t)g[kChild] | ((uint32_t)g[kMom] << 8) | ((uint32_t)g[kDad] << 16);
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, found);
+    if (lane == 0) s_cnt[j * kMW + warp] = __popc(m);
+    packed[j] = pk | ((uint32_t)__popc(m & ((1u << lane) - 1)) << 24) | (found ? 0x80000000u : 0u);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int v0 = lane < kJI * kMW ? s_cnt[lane] : 0;
+    int x = v0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    s_cnt[lane] = x - v0;
+    const int total = __shfl_sync(0xffffffffu, x, 31);
+    const unsigned long long e = lookback<false>(A.st_found, b, (unsigned long long)total, lane);
+    if (lane == 0) { s_excl = e; if (last_live) A.totals[3] = e + (unsigned long long)total; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kJI; j++) {
+    if (!(packed[j] & 0x80000000u)) continue;
+    const int64_t i = i0 + (int64_t)j * kMB + threadIdx.x;
+    const int64_t o_pos = (int64_t)s_excl + s_cnt[j * kMW + warp] + (int)((packed[j] >> 24) & 0x7F);
+    if (o_pos < cap) {
+      const int c = packed[j] & 0xFF, mo = (packed[j] >> 8) & 0xFF, d = (packed[j] >> 16) & 0xFF;
+      const int idx = d * 100 + mo * 10 + c;
       dnv_pcall o;
       o.position = A.start[kChild][i];
       o.child_index = A.src[i];
-      o.child = (uint8_t)c; o.mom = (uint8_t)m; o.dad = (uint8_t)d;
+      o.child = (uint8_t)c; o.mom = (uint8_t)mo; o.dad = (uint8_t)d;
       o.is_denovo = (tab->isden[idx >> 5] >> (idx & 31)) & 1u;  // PositionCall.isDenovo, :352-355
       o.pad_[0] = o.pad_[1] = o.pad_[2] = o.pad_[3] = 0;
-      out[pos] = o;
+      out[o_pos] = o;
     }
-    pos++;
-  }
-}
-
-// found_block_sums of child blocks past the live range must be defined for the scan
-__global__ void mendel_found_popc_kernel(MendelArrays A, int n_blocks_cap) {
-  const int64_t n_child = (int64_t)A.totals[kChild];
-  const int64_t n_words = (n_child + 31) / 32;
-  for (int b = blockIdx.x; b < n_blocks_cap; b += gridDim.x) {
-    const int64_t w = (int64_t)b * kScanThreads + threadIdx.x;
-    int v = (w < n_words) ? __popc(A.found_bits[w]) : 0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    __shared__ int s[kScanThreads / 32];
-    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int t = 0;
-      for (int k = 0; k < kScanThreads / 32; k++) t += s[k];
-      A.found_block_sums[b] = (uint32_t)t;
-    }
-    __syncthreads();
   }
 }
 
@@ -300,55 +401,35 @@ int dnv_mendel_filter_device(dnv_ctx* ctx, const dnv_vcall* d_calls, int64_t n, 
   if (n == 0) return DNV_OK;
   DNV_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  const int64_t n_words = (n + 31) / 32;
-  const int n_blocks = (int)((n_words + kScanThreads - 1) / kScanThreads);
-  const int64_t n_tiles = (n + kMaxScanTile - 1) / kMaxScanTile;
-
   // carve the scratch arena (every person's queue is sized for n entries)
+  const int n_blocks = (int)((n + kMTile - 1) / kMTile);
   size_t off = 0;
   auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-  size_t o_start[3], o_end[3], o_code[3], o_bits[3], o_bsum[3];
-  for (int p = 0; p < 3; p++) {
-    o_start[p] = take((size_t)n * 8); o_end[p] = take((size_t)n * 8); o_code[p] = take((size_t)n);
-    o_bits[p] = take((size_t)(n_words + 1) * 4); o_bsum[p] = take((size_t)(n_blocks + 1) * 4);
-  }
-  const size_t o_ref = take((size_t)n), o_src = take((size_t)n * 8), o_tot = take(64);
-  const size_t o_fbits = take((size_t)(n_words + 1) * 4), o_fbsum = take((size_t)(n_blocks + 1) * 4);
-  const size_t o_packed = take((size_t)n * 4), o_tmax = take((size_t)(n_tiles + 1) * 8);
+  size_t o_start[3], o_rmax[3], o_code[3];
+  for (int p = 0; p < 3; p++) { o_start[p] = take((size_t)n * 8); o_rmax[p] = take((size_t)n * 8); o_code[p] = take((size_t)n); }
+  const size_t o_ref = take((size_t)n), o_src = take((size_t)n * 8);
+  const size_t status_bytes = (size_t)((n + kJTile - 1) / kJTile + 1) * 8;  // sized for the finer of the two grids
+  const size_t o_status = take(7 * status_bytes + 64);  // 3 sums, 3 maxima (child unused), found, then the totals
   int rc = ensure_scratch(ctx, off);
   if (rc) return rc;
   char* base = (char*)ctx->d_scratch;
   MendelArrays A;
   for (int p = 0; p < 3; p++) {
-    A.start[p] = (int64_t*)(base + o_start[p]); A.end[p] = (int64_t*)(base + o_end[p]);
-    A.code[p] = (uint8_t*)(base + o_code[p]); A.bits[p] = (uint32_t*)(base + o_bits[p]);
-    A.block_sums[p] = (uint32_t*)(base + o_bsum[p]);
+    A.start[p] = (int64_t*)(base + o_start[p]); A.runmax[p] = (int64_t*)(base + o_rmax[p]);
+    A.code[p] = (uint8_t*)(base + o_code[p]);
+    A.st_sum[p] = (unsigned long long*)(base + o_status + (size_t)p * status_bytes);
+    A.st_max[p] = (unsigned long long*)(base + o_status + (size_t)(3 + p) * status_bytes);
   }
+  A.st_found = (unsigned long long*)(base + o_status + 6 * status_bytes);
+  A.totals = (unsigned long long*)(base + o_status + 7 * status_bytes);
   A.ref = (uint8_t*)(base + o_ref); A.src = (int64_t*)(base + o_src);
-  A.totals = (unsigned long long*)(base + o_tot);
-  A.found_bits = (uint32_t*)(base + o_fbits); A.found_block_sums = (uint32_t*)(base + o_fbsum);
-  A.packed = (uint32_t*)(base + o_packed);
-  long long* tile_max = (long long*)(base + o_tmax);
 
-  DNV_CUDA(cudaMemsetAsync(A.totals, 0, 64, st));
-  const int grid_n = (int)((n + kScanThreads - 1) / kScanThreads);
-  mendel_admit_kernel<<<grid_n, kScanThreads, 0, st>>>(d_calls, n, A);
-  for (int p = 0; p < 3; p++) {
-    popc_blocks_kernel<<<n_blocks, kScanThreads, 0, st>>>(A.bits[p], n_words, A.block_sums[p]);
-    scan_blocks_generic_kernel<<<1, 1024, 0, st>>>(A.block_sums[p], n_blocks, A.totals + p);
-  }
-  mendel_scatter_kernel<<<n_blocks, kScanThreads, 0, st>>>(d_calls, n_words, A);
-  for (int par = kMom; par <= kDad; par++) {
-    runmax_tile_kernel<<<(int)n_tiles, kMaxScanThreads, 0, st>>>(A.end[par], A.totals + par, tile_max);
-    runmax_carry_kernel<<<1, 1024, 0, st>>>(tile_max, A.totals + par);
-    runmax_apply_kernel<<<(int)n_tiles, kMaxScanThreads, 0, st>>>(A.end[par], A.totals + par, tile_max);
-  }
-  mendel_join_kernel<<<grid_n, kScanThreads, 0, st>>>(A);
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-  mendel_found_popc_kernel<<<std::min(n_blocks, sms * 8), kScanThreads, 0, st>>>(A, n_blocks);
-  scan_blocks_generic_kernel<<<1, 1024, 0, st>>>(A.found_block_sums, n_blocks, A.totals + 3);
-  mendel_emit_kernel<<<n_blocks, kScanThreads, 0, st>>>(ctx->d_tab, A, d_out, cap);
+  DNV_CUDA(cudaMemsetAsync(base + o_status, 0, 7 * status_bytes + 64, st));
+  mendel_admit_compact_kernel<<<n_blocks, kMB, 0, st>>>(d_calls, n, A);
+  const int j_blocks = (int)((n + kJTile - 1) / kJTile);  // children <= records; empty blocks retire at once
+  const size_t j_smem = (size_t)4 * kJCap * sizeof(int64_t);
+  DNV_CUDA(cudaFuncSetAttribute(mendel_join_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)j_smem));
+  mendel_join_emit_kernel<<<j_blocks, kMB, j_smem, st>>>(ctx->d_tab, A, d_out, cap);
   DNV_CUDA(cudaGetLastError());
   unsigned long long h[8];
   DNV_CUDA(cudaMemcpyAsync(h, A.totals, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -356,7 +437,7 @@ int dnv_mendel_filter_device(dnv_ctx* ctx, const dnv_vcall* d_calls, int64_t n, 
   ctx->stats = dnv_stats();
   ctx->stats.n_sites = (int64_t)h[0];
   ctx->stats.n_calls = (int64_t)h[3];
-  ctx->stats.n_launches = 18;
+  ctx->stats.n_launches = 2;
   if (h[4] != 0) {
     const int kind = -(int)h[5];
     set_error(kind == DNV_E_BADBASE
