@@ -141,8 +141,38 @@ def pileup(n_sites, depth=30):
                       "bit_exact_vs_oracle_window": bool(rc == 0 and np.array_equal(got[sel], want))}), flush=True)
 
 
+def genome(total=3_095_693_983, chunk=1 << 26, depth=30):
+    """BASELINE config 4 on ONE GPU: every position of an hg19-sized axis, counts generated procedurally
+    per 67M-site chunk on the device (74 GB of counts are never materialised at once); inference time
+    only (generation excluded), plus the generator's own time."""
+    stream = torch.cuda.Stream()
+    with D.TrioEngine(1e-2, 1e-8, 1.0, "BAYES", time_kernels=True) as eng:
+        eng.set_stream(stream.cuda_stream)
+        counts = torch.empty((chunk, 12), dtype=torch.int16, device="cuda")
+        cap = chunk // 50
+        calls = torch.zeros((cap, D.CALL_DT.itemsize), dtype=torch.uint8, device="cuda")
+        infer_ms = gen_ms = 0.0
+        n_calls = hard = 0
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        for first in range(0, total, chunk):
+            m = min(chunk, total - first)
+            with torch.cuda.stream(stream):
+                e0.record(stream)
+                eng.synth_counts_device(0x5EED0004, first, m, counts, depth=depth)
+                e1.record(stream)
+                n_calls += eng.infer_device(counts, m, calls, cap)
+                e2.record(stream)
+            torch.cuda.synchronize()
+            gen_ms += e0.elapsed_time(e1)
+            infer_ms += e1.elapsed_time(e2)
+            hard += eng.stats()["n_hard"]
+    print(json.dumps({"bench": "genome_every_position_1gpu", "sites": total, "depth": depth, "infer_ms": infer_ms,
+                      "sites_per_s": total / infer_ms * 1e3, "generator_ms": gen_ms, "calls": n_calls,
+                      "hard_sites": hard}), flush=True)
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["read", "stress", "mendel", "pileup"]
+    what = sys.argv[1:] or ["read", "stress", "mendel", "pileup", "genome"]
     N = 10_000_000
     if "read" in what:
         read_mode(N, "BAYES", 30, 1e-2, 1e-8)
@@ -156,3 +186,5 @@ if __name__ == "__main__":
         mendel(6_000_000)
     if "pileup" in what:
         pileup(2_000_000)
+    if "genome" in what:
+        genome()

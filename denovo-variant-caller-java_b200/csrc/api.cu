@@ -28,7 +28,7 @@ constexpr int64_t kDeviceChunk = 1ll << 27;
 // sites per H2D/compute/D2H stage of the host path
 constexpr int64_t kHostChunk = 1ll << 21;
 
-static int ensure_stage(dnv_ctx* ctx, int64_t n, bool dense, int64_t calls_cap) {
+static int ensure_stage(dnv_ctx* ctx, int64_t n, bool dense, int64_t calls_cap) {  // stage buffers hold the uint16 layout
   if (n > ctx->stage_cap) {
     for (int i = 0; i < 2; i++) {
       cudaFree(ctx->d_stage_counts[i]);
@@ -177,8 +177,8 @@ static int finish_batch(dnv_ctx* ctx, int64_t n, int64_t cap, int64_t* n_calls) 
   return DNV_OK;
 }
 
-int dnv_infer_counts_device(dnv_ctx* ctx, const uint16_t* d_counts, int64_t n, dnv_site_result* d_dense,
-                            dnv_call* d_calls, int64_t cap, int64_t* n_calls) {
+static int infer_device_impl(dnv_ctx* ctx, const void* d_counts, int bps, int64_t n, dnv_site_result* d_dense,
+                             dnv_call* d_calls, int64_t cap, int64_t* n_calls) {
   if (!ctx || !n_calls || n < 0 || cap < 0 || (n > 0 && !d_counts) || (cap > 0 && !d_calls)) {
     set_error("dnv_infer_counts_device: invalid argument");
     return DNV_E_INVALID;
@@ -187,17 +187,19 @@ int dnv_infer_counts_device(dnv_ctx* ctx, const uint16_t* d_counts, int64_t n, d
   ctx->stats = dnv_stats();
   ctx->n_timed = 0;
   ctx->calls_slot = 0;
+  ctx->count_bytes = bps;
   DNV_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
   for (int64_t off = 0; off < n; off += kDeviceChunk) {
     const int64_t m = std::min(kDeviceChunk, n - off);
-    int rc = launch_trio_chunk(ctx, d_counts + off * 12, off, m, d_dense ? d_dense + off : nullptr, d_calls, cap);
+    int rc = launch_trio_chunk(ctx, (const unsigned char*)d_counts + off * bps, off, m,
+                               d_dense ? d_dense + off : nullptr, d_calls, cap);
     if (rc) return rc;
   }
   return finish_batch(ctx, n, cap, n_calls);
 }
 
-int dnv_infer_counts(dnv_ctx* ctx, const uint16_t* counts, int64_t n, dnv_site_result* dense, dnv_call* calls,
-                     int64_t cap, int64_t* n_calls) {
+static int infer_host_impl(dnv_ctx* ctx, const void* counts, int bps, int64_t n, dnv_site_result* dense,
+                           dnv_call* calls, int64_t cap, int64_t* n_calls) {
   if (!ctx || !n_calls || n < 0 || cap < 0 || (n > 0 && !counts) || (cap > 0 && !calls)) {
     set_error("dnv_infer_counts: invalid argument");
     return DNV_E_INVALID;
@@ -206,6 +208,7 @@ int dnv_infer_counts(dnv_ctx* ctx, const uint16_t* counts, int64_t n, dnv_site_r
   ctx->stats = dnv_stats();
   ctx->n_timed = 0;
   ctx->calls_slot = 0;
+  ctx->count_bytes = bps;
   const int64_t chunk = std::min<int64_t>(kHostChunk, std::max<int64_t>(n, 1));
   const int64_t dev_cap = std::min(cap, n);
   int rc = ensure_stage(ctx, chunk, dense != nullptr, dev_cap);
@@ -217,8 +220,8 @@ int dnv_infer_counts(dnv_ctx* ctx, const uint16_t* counts, int64_t n, dnv_site_r
     const int64_t m = std::min(chunk, n - off);
     // buffer k is free once the compute (and dense D2H) that last used it finished
     DNV_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[k], 0));
-    DNV_CUDA(cudaMemcpyAsync(ctx->d_stage_counts[k], counts + off * 12, (size_t)m * 24, cudaMemcpyHostToDevice,
-                             ctx->copy_stream));
+    DNV_CUDA(cudaMemcpyAsync(ctx->d_stage_counts[k], (const unsigned char*)counts + off * bps, (size_t)m * bps,
+                             cudaMemcpyHostToDevice, ctx->copy_stream));
     DNV_CUDA(cudaEventRecord(ctx->ev_h2d[k], ctx->copy_stream));
     DNV_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[k], 0));
     rc = launch_trio_chunk(ctx, ctx->d_stage_counts[k], off, m, dense ? ctx->d_stage_dense[k] : nullptr,
@@ -237,6 +240,23 @@ int dnv_infer_counts(dnv_ctx* ctx, const uint16_t* counts, int64_t n, dnv_site_r
     DNV_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   return rc;
+}
+
+int dnv_infer_counts_device(dnv_ctx* ctx, const uint16_t* d_counts, int64_t n, dnv_site_result* d_dense,
+                            dnv_call* d_calls, int64_t cap, int64_t* n_calls) {
+  return infer_device_impl(ctx, d_counts, 24, n, d_dense, d_calls, cap, n_calls);
+}
+int dnv_infer_counts8_device(dnv_ctx* ctx, const uint8_t* d_counts8, int64_t n, dnv_site_result* d_dense,
+                             dnv_call* d_calls, int64_t cap, int64_t* n_calls) {
+  return infer_device_impl(ctx, d_counts8, 12, n, d_dense, d_calls, cap, n_calls);
+}
+int dnv_infer_counts(dnv_ctx* ctx, const uint16_t* counts, int64_t n, dnv_site_result* dense, dnv_call* calls,
+                     int64_t cap, int64_t* n_calls) {
+  return infer_host_impl(ctx, counts, 24, n, dense, calls, cap, n_calls);
+}
+int dnv_infer_counts8(dnv_ctx* ctx, const uint8_t* counts8, int64_t n, dnv_site_result* dense, dnv_call* calls,
+                      int64_t cap, int64_t* n_calls) {
+  return infer_host_impl(ctx, counts8, 12, n, dense, calls, cap, n_calls);
 }
 
 }  // extern "C"

@@ -58,6 +58,7 @@ struct dnv_ctx {
   unsigned long long* d_tile_status;  // decoupled look-back status per compaction block
   unsigned long long epoch;           // launch counter tagging d_tile_status entries
   int calls_slot;                     // counters[] slot holding the running call total (0 or 3)
+  int count_bytes;                    // bytes per site of the current call's counts: 24 (uint16) or 12 (uint8)
   int64_t* d_call_idx;     // global site index of every call, input order
   int64_t call_idx_cap;
   unsigned long long* d_counters;  // [0]/[3] running call total (ping-pong per chunk) [4] hard sites [6] block ticket
@@ -84,7 +85,7 @@ struct dnv_ctx {
 
 namespace dnv {
 // kernels / launchers (defined in the .cu files)
-int launch_trio_chunk(dnv_ctx* ctx, const uint16_t* d_counts, int64_t site_base, int64_t n,
+int launch_trio_chunk(dnv_ctx* ctx, const void* d_counts, int64_t site_base, int64_t n,
                       dnv_site_result* d_dense, dnv_call* d_calls, int64_t cap);
 int ensure_chunk_scratch(dnv_ctx* ctx, int64_t n);
 int ensure_scratch(dnv_ctx* ctx, size_t bytes);

@@ -22,7 +22,7 @@ constexpr int kExactThreads = 128;
 
 // ---------------------------------------------------------------- K1 (exact, all sites)
 __global__ void __launch_bounds__(kExactThreads)
-trio_direct_all_kernel(const Tables* __restrict__ tab, const uint16_t* __restrict__ counts,
+trio_direct_all_kernel(const Tables* __restrict__ tab, const void* __restrict__ counts, int bps,
                        int64_t n, uint32_t* __restrict__ bits, dnv_site_result* __restrict__ dense,
                        unsigned long long* __restrict__ counters) {
   __shared__ double s_rel[1000];
@@ -37,7 +37,7 @@ trio_direct_all_kernel(const Tables* __restrict__ tab, const uint16_t* __restric
     bool dn = false;
     if (site < n) {
       uint16_t c[12];
-      load_counts(counts, site, c);
+      load_counts(counts, bps, site, c);
       ExactOut r;
       exact_site(c, s_rel, s_isden, hm, ht, mm, method, thr, &r);
       dn = r.is_denovo;
@@ -62,7 +62,7 @@ constexpr int kCompactThreads = 256;
 static_assert(kCompactThreads == kScanThreads, "one bit-word per thread");
 
 __global__ void __launch_bounds__(kCompactThreads, 2)
-compact_details_kernel(const Tables* __restrict__ tab, const uint16_t* __restrict__ counts, int64_t site_base,
+compact_details_kernel(const Tables* __restrict__ tab, const void* __restrict__ counts, int bps, int64_t site_base,
                        const uint32_t* __restrict__ bits, int64_t n_words, unsigned long long* status,
                        unsigned long long epoch, unsigned long long* counters, int in_slot, int out_slot,
                        int64_t* __restrict__ call_idx, int64_t call_idx_cap, dnv_call* __restrict__ calls,
@@ -145,7 +145,7 @@ compact_details_kernel(const Tables* __restrict__ tab, const uint16_t* __restric
     if (p >= cap) break;
     const int64_t gsite = call_idx[p];
     uint16_t c[12];
-    load_counts(counts, gsite - site_base, c);
+    load_counts(counts, bps, gsite - site_base, c);
     int ci[12];
 #pragma unroll
     for (int q = 0; q < 12; q++) ci[q] = c[q];
@@ -213,7 +213,7 @@ static int ensure_call_idx(dnv_ctx* ctx, int64_t cap) {
 
 // One chunk (n < 2^31): two kernels.  The caller zeroes the counters and ctx->calls_slot
 // before the first chunk of a batch and reads counters[ctx->calls_slot] at the end.
-int launch_trio_chunk(dnv_ctx* ctx, const uint16_t* d_counts, int64_t site_base, int64_t n,
+int launch_trio_chunk(dnv_ctx* ctx, const void* d_counts, int64_t site_base, int64_t n,
                       dnv_site_result* d_dense, dnv_call* d_calls, int64_t cap) {
   if (n <= 0) return DNV_OK;
   int rc = ensure_chunk_scratch(ctx, n);
@@ -232,7 +232,7 @@ int launch_trio_chunk(dnv_ctx* ctx, const uint16_t* d_counts, int64_t site_base,
   if (direct) {
     const int64_t want = (n + kExactThreads - 1) / kExactThreads;
     const int grid = (int)(want < (int64_t)sms * 16 ? want : (int64_t)sms * 16);
-    trio_direct_all_kernel<<<grid, kExactThreads, 0, st>>>(ctx->d_tab, d_counts, n, ctx->d_bits, d_dense,
+    trio_direct_all_kernel<<<grid, kExactThreads, 0, st>>>(ctx->d_tab, d_counts, ctx->count_bytes, n, ctx->d_bits, d_dense,
                                                           ctx->d_counters);
   } else {
     rc = launch_trio_fast(ctx, d_counts, n, d_dense);
@@ -240,7 +240,7 @@ int launch_trio_chunk(dnv_ctx* ctx, const uint16_t* d_counts, int64_t site_base,
   }
   if (timed) DNV_CUDA(cudaEventRecord(ctx->ev_k1[ctx->n_timed++], st));
   const int in_slot = ctx->calls_slot, out_slot = in_slot == 0 ? 3 : 0;
-  compact_details_kernel<<<n_blocks, kCompactThreads, 0, st>>>(ctx->d_tab, d_counts, site_base, ctx->d_bits, n_words,
+  compact_details_kernel<<<n_blocks, kCompactThreads, 0, st>>>(ctx->d_tab, d_counts, ctx->count_bytes, site_base, ctx->d_bits, n_words,
                                                               ctx->d_tile_status, ++ctx->epoch, ctx->d_counters,
                                                               in_slot, out_slot, ctx->d_call_idx, ctx->call_idx_cap,
                                                               d_calls, cap, make_fast_consts(ctx->h_tab));

@@ -222,16 +222,26 @@ __device__ __forceinline__ void stage_map_bounds(const Tables* __restrict__ tab,
   for (int i = threadIdx.x; i < 10; i += blockDim.x) s_rmax[100 + i] = tab->rmax_d[i];
 }
 
-__device__ __forceinline__ void load_counts(const uint16_t* __restrict__ counts, int64_t site,
-                                            uint16_t* c) {
-  const uint2* p = reinterpret_cast<const uint2*>(counts + site * 12);
+// counts of one site: bps = 24 (uint16 x 12) or 12 (uint8 x 12)
+__device__ __forceinline__ void load_counts(const void* __restrict__ counts, int bps, int64_t site, uint16_t* c) {
+  if (bps == 24) {
+    const uint2* p = reinterpret_cast<const uint2*>(reinterpret_cast<const unsigned char*>(counts) + site * 24);
 #pragma unroll
-  for (int i = 0; i < 3; i++) {
-    const uint2 v = __ldg(p + i);
-    c[4 * i + 0] = (uint16_t)(v.x & 0xFFFF);
-    c[4 * i + 1] = (uint16_t)(v.x >> 16);
-    c[4 * i + 2] = (uint16_t)(v.y & 0xFFFF);
-    c[4 * i + 3] = (uint16_t)(v.y >> 16);
+    for (int i = 0; i < 3; i++) {
+      const uint2 v = __ldg(p + i);
+      c[4 * i + 0] = (uint16_t)(v.x & 0xFFFF);
+      c[4 * i + 1] = (uint16_t)(v.x >> 16);
+      c[4 * i + 2] = (uint16_t)(v.y & 0xFFFF);
+      c[4 * i + 3] = (uint16_t)(v.y >> 16);
+    }
+  } else {
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(reinterpret_cast<const unsigned char*>(counts) + site * 12);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const uint32_t v = __ldg(p + i);
+#pragma unroll
+      for (int k = 0; k < 4; k++) c[4 * i + k] = (uint16_t)((v >> (8 * k)) & 0xFF);
+    }
   }
 }
 

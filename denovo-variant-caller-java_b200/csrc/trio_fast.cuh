@@ -44,7 +44,7 @@ struct FastShared {
   uint32_t isden[32];           // exact path: isDenovoMap
   double rmax[110];             // exact MAP pruning bounds
   double warp_L[kFastWarps][32];  // exact path: per-warp read log-likelihoods
-  alignas(16) unsigned char tile[kFastWarps][2][kWarpTileBytes];
+  alignas(16) unsigned char tile[kFastWarps][2][kWarpTileBytes];  // sized for the uint16 layout
   alignas(8) unsigned long long bar[kFastWarps][2];
 };
 
@@ -212,6 +212,15 @@ __device__ __forceinline__ void linear_values(const LinOut& lo, double& p, doubl
   log_men = men0 ? -INFINITY : fma(lo.s2, ln2, log(lo.men_s));
 }
 
+__device__ __forceinline__ void unpack_counts8(const uint32_t* p, int* c) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const uint32_t v = p[i];
+#pragma unroll
+    for (int k = 0; k < 4; k++) c[4 * i + k] = (int)((v >> (8 * k)) & 0xFF);
+  }
+}
+
 __device__ __forceinline__ void unpack_counts(const uint2* p, int* c) {
 #pragma unroll
   for (int i = 0; i < 3; i++) {
@@ -227,14 +236,16 @@ __device__ __forceinline__ void unpack_counts(const uint2* p, int* c) {
 // kMap: evaluate the exact log-domain argmax (MAP decision, dense maxGenoType)
 // Each WARP walks its own tiles of 32 sites (768 B of counts per tile, TMA bulk copy into a
 // warp-private double buffer, warp-private mbarriers): no block-wide barrier in the loop.
-template <bool kLin, bool kMap, bool kDense, int kMinBlocks>
+template <bool kLin, bool kMap, bool kDense, int kMinBlocks, bool kU8>
 __global__ void __launch_bounds__(kFastThreads, kMinBlocks)
-trio_fast_kernel(const Tables* __restrict__ tab, const FastConsts k, const uint16_t* __restrict__ counts, int64_t n,
+trio_fast_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsigned char* __restrict__ counts, int64_t n,
                  uint32_t* __restrict__ bits, unsigned long long* __restrict__ counters,
                  dnv_site_result* __restrict__ dense) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FastShared& s = *reinterpret_cast<FastShared*>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kBps = kU8 ? 12 : 24;            // bytes per site
+  constexpr int kTile = 32 * kBps;               // one warp tile (a multiple of 16)
 
   const int64_t n_tiles = (n + 31) / 32;
   const bool tma_ok = (reinterpret_cast<uintptr_t>(counts) & 15) == 0;
@@ -257,8 +268,8 @@ trio_fast_kernel(const Tables* __restrict__ tab, const FastConsts k, const uint1
   // a full tile (32 sites, 768 B: a multiple of 16) is bulk-copied; the ragged last one is not
   auto issue = [&](int64_t t, int buf) {
     if (lane == 0 && tma_ok && (t + 1) * 32 <= n) {
-      mbar_expect_tx(&s.bar[warp][buf], kWarpTileBytes);
-      tma_bulk_g2s(s.tile[warp][buf], counts + t * 32 * 12, kWarpTileBytes, &s.bar[warp][buf]);
+      mbar_expect_tx(&s.bar[warp][buf], kTile);
+      tma_bulk_g2s(s.tile[warp][buf], counts + t * kTile, kTile, &s.bar[warp][buf]);
     }
   };
   const int64_t warps_total = (int64_t)gridDim.x * kFastWarps;
@@ -272,9 +283,11 @@ trio_fast_kernel(const Tables* __restrict__ tab, const FastConsts k, const uint1
     if (tma_ok && (t + 1) * 32 <= n) {
       if (buf == 0) { mbar_wait(&s.bar[warp][0], phase0); phase0 ^= 1; }
       else { mbar_wait(&s.bar[warp][1], phase1); phase1 ^= 1; }
-      unpack_counts(reinterpret_cast<const uint2*>(s.tile[warp][buf] + lane * 24), c);
+      if (kU8) unpack_counts8(reinterpret_cast<const uint32_t*>(s.tile[warp][buf] + lane * 12), c);
+      else unpack_counts(reinterpret_cast<const uint2*>(s.tile[warp][buf] + lane * 24), c);
     } else if (site < n) {
-      unpack_counts(reinterpret_cast<const uint2*>(counts + site * 12), c);
+      if (kU8) unpack_counts8(reinterpret_cast<const uint32_t*>(counts + site * 12), c);
+      else unpack_counts(reinterpret_cast<const uint2*>(counts + site * 24), c);
     } else {
 #pragma unroll
       for (int q = 0; q < 12; q++) c[q] = 0;
@@ -344,12 +357,12 @@ trio_fast_kernel(const Tables* __restrict__ tab, const FastConsts k, const uint1
   }
 }
 
-template <bool kLin, bool kMap, bool kDense, int kMinBlocks>
-static int launch_fast_variant(dnv_ctx* ctx, const uint16_t* d_counts, int64_t n, dnv_site_result* d_dense) {
+template <bool kLin, bool kMap, bool kDense, int kMinBlocks, bool kU8>
+static int launch_fast_kernel(dnv_ctx* ctx, const void* d_counts, int64_t n, dnv_site_result* d_dense) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
   const size_t smem = sizeof(FastShared);
-  auto kern = trio_fast_kernel<kLin, kMap, kDense, kMinBlocks>;
+  auto kern = trio_fast_kernel<kLin, kMap, kDense, kMinBlocks, kU8>;
   DNV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
   DNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kFastThreads, smem));
@@ -358,19 +371,22 @@ static int launch_fast_variant(dnv_ctx* ctx, const uint16_t* d_counts, int64_t n
   const int64_t persistent = (int64_t)sms * per_sm;  // one resident wave; every warp walks its tiles
   const int grid = (int)(want < persistent ? want : persistent);
   const FastConsts k = make_fast_consts(ctx->h_tab);
-  kern<<<grid, kFastThreads, smem, ctx->stream>>>(ctx->d_tab, k, d_counts, n, ctx->d_bits, ctx->d_counters, d_dense);
+  kern<<<grid, kFastThreads, smem, ctx->stream>>>(ctx->d_tab, k, (const unsigned char*)d_counts, n, ctx->d_bits,
+                                                  ctx->d_counters, d_dense);
   DNV_CUDA(cudaGetLastError());
   return DNV_OK;
 }
 
-inline int launch_trio_fast(dnv_ctx* ctx, const uint16_t* d_counts, int64_t n, dnv_site_result* d_dense) {
+template <bool kLin, bool kMap, bool kDense, int kMinBlocks>
+static int launch_fast_variant(dnv_ctx* ctx, const void* d_counts, int64_t n, dnv_site_result* d_dense) {
+  if (ctx->count_bytes == 12) return launch_fast_kernel<kLin, kMap, kDense, kMinBlocks, true>(ctx, d_counts, n, d_dense);
+  return launch_fast_kernel<kLin, kMap, kDense, kMinBlocks, false>(ctx, d_counts, n, d_dense);
+}
+
+inline int launch_trio_fast(dnv_ctx* ctx, const void* d_counts, int64_t n, dnv_site_result* d_dense) {
   const bool map = ctx->prm.method == DNV_METHOD_MAP;
   if (d_dense) return launch_fast_variant<true, true, true, 2>(ctx, d_counts, n, d_dense);
   if (map) return launch_fast_variant<false, true, false, 4>(ctx, d_counts, n, nullptr);
-  static const int tune = getenv("DNV_FAST_MINBLOCKS") ? atoi(getenv("DNV_FAST_MINBLOCKS")) : 3;  // tuning knob
-  if (tune == 2) return launch_fast_variant<true, false, false, 2>(ctx, d_counts, n, nullptr);
-  if (tune == 4) return launch_fast_variant<true, false, false, 4>(ctx, d_counts, n, nullptr);
-  if (tune == 5) return launch_fast_variant<true, false, false, 5>(ctx, d_counts, n, nullptr);
   return launch_fast_variant<true, false, false, 3>(ctx, d_counts, n, nullptr);
 }
 

@@ -84,29 +84,32 @@ class TrioEngine:
 
     # ---- READ mode
     def infer(self, counts, dense=False, cap=None):
-        """counts: host uint16 [n,3,4] (DAD,MOM,CHILD x A,C,G,T).
-        Returns (calls CALL_DT[], dense SITE_DT[] or None)."""
-        counts = np.ascontiguousarray(counts, np.uint16).reshape(-1, 12)
+        """counts: host uint16 [n,3,4] (DAD,MOM,CHILD x A,C,G,T); a uint8 array selects the compact
+        12-byte-per-site entry point.  Returns (calls CALL_DT[], dense SITE_DT[] or None)."""
+        u8 = isinstance(counts, np.ndarray) and counts.dtype == np.uint8
+        counts = np.ascontiguousarray(counts, np.uint8 if u8 else np.uint16).reshape(-1, 12)
         n = counts.shape[0]
         cap = n if cap is None else cap
         calls = np.zeros(max(cap, 1), L.CALL_DT)
         d = np.zeros(n, L.SITE_DT) if dense else None
         nc = C.c_int64(0)
-        L.check(self.lib.dnv_infer_counts(self._h, L.ptr(counts), n, L.ptr(d) if dense else None,
-                                          L.ptr(calls) if cap > 0 else None, cap, C.byref(nc)))
+        fn = self.lib.dnv_infer_counts8 if u8 else self.lib.dnv_infer_counts
+        L.check(fn(self._h, L.ptr(counts), n, L.ptr(d) if dense else None,
+                   L.ptr(calls) if cap > 0 else None, cap, C.byref(nc)))
         return calls[:nc.value], d
 
-    def infer_host_into(self, counts_ptr, n, calls_ptr, cap):
+    def infer_host_into(self, counts_ptr, n, calls_ptr, cap, u8=False):
         """Zero-allocation host call (pinned buffers owned by the caller); returns n_calls."""
         nc = C.c_int64(0)
-        L.check(self.lib.dnv_infer_counts(self._h, L.ptr(counts_ptr), n, None, L.ptr(calls_ptr), cap, C.byref(nc)))
+        fn = self.lib.dnv_infer_counts8 if u8 else self.lib.dnv_infer_counts
+        L.check(fn(self._h, L.ptr(counts_ptr), n, None, L.ptr(calls_ptr), cap, C.byref(nc)))
         return nc.value
 
-    def infer_device(self, d_counts, n, d_calls, cap, d_dense=None):
+    def infer_device(self, d_counts, n, d_calls, cap, d_dense=None, u8=False):
         """Device-resident buffers (torch CUDA tensors or raw pointers); returns n_calls."""
         nc = C.c_int64(0)
-        L.check(self.lib.dnv_infer_counts_device(self._h, L.ptr(d_counts), n, L.ptr(d_dense), L.ptr(d_calls), cap,
-                                                 C.byref(nc)))
+        fn = self.lib.dnv_infer_counts8_device if u8 else self.lib.dnv_infer_counts_device
+        L.check(fn(self._h, L.ptr(d_counts), n, L.ptr(d_dense), L.ptr(d_calls), cap, C.byref(nc)))
         return nc.value
 
     def pileup(self, read_start, base_off, bases, person, site_pos):

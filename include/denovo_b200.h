@@ -177,6 +177,15 @@ int dnv_infer_counts_device(dnv_ctx *ctx, const uint16_t *d_counts, int64_t n,
                             dnv_site_result *d_dense, dnv_call *d_calls,
                             int64_t cap, int64_t *n_calls);
 
+/* Compact input variants: counts as uint8 [n][3][4] (12 bytes per site) for pileups whose
+ * per-allele depth is below 256 — halves the host->device traffic that bounds the host path.
+ * Same outputs (dnv_call.counts stays uint16). */
+int dnv_infer_counts8(dnv_ctx *ctx, const uint8_t *counts8, int64_t n, dnv_site_result *dense,
+                      dnv_call *calls, int64_t cap, int64_t *n_calls);
+int dnv_infer_counts8_device(dnv_ctx *ctx, const uint8_t *d_counts8, int64_t n,
+                             dnv_site_result *d_dense, dnv_call *d_calls, int64_t cap,
+                             int64_t *n_calls);
+
 /* ---- READ mode: reads -> pileup counts ---------------------------------- */
 /* Batched `new ReadSummary(reads, position)` x3 (M/ReadSummary.java:45-59,
  * M/ReadCaller.java:138-146).  Reads are sorted by (person, start); person in

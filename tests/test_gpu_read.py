@@ -199,3 +199,18 @@ def test_host_path_chunking_matches_single_chunk():
     assert np.array_equal(calls["site"] % 5000, np.tile(small["site"], 1000))
     assert np.all(np.diff(calls["site"]) > 0)
     assert np.array_equal(calls["p"], np.tile(small["p"], 1000))
+
+
+def test_uint8_compact_input_matches_uint16():
+    """dnv_infer_counts8 (12 B/site) must give byte-identical results to the uint16 entry point."""
+    counts = O.synth_counts(0x5EED0003, 0, 300_000)
+    assert counts.max() < 256
+    for method in ("BAYES", "MAP"):
+        with D.TrioEngine(method=method) as eng:
+            a, da = eng.infer(counts, dense=True)
+            b, db = eng.infer(counts.astype(np.uint8), dense=True)
+        assert a.tobytes() == b.tobytes() and da.tobytes() == db.tobytes() and len(a) > 100
+    with D.TrioEngine(force_direct=True) as eng:
+        c, _ = eng.infer(counts[:20000].astype(np.uint8))
+        d, _ = eng.infer(counts[:20000])
+    assert c.tobytes() == d.tobytes()
