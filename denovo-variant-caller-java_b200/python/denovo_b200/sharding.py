@@ -72,3 +72,50 @@ def globalize_sites(records_np, site_offset):
     out = records_np.copy()
     out["site"] += np.int64(site_offset)
     return out
+
+
+class PeerGather:
+    """Gather of call records to `dst` WITHOUT a data collective: every rank's compaction kernel
+    stores its dnv_call records straight into rank dst's HBM over NVLink (peer stores through a
+    torch symmetric-memory mapping), then publishes its count and joins a signal-pad barrier.
+    Layout of the destination buffer: world slots of [64-byte header (int64 count) | cap records].
+    Rank order = genomic order, so the slots read in order are the gathered result.
+    Falls back to `gather_records` (NCCL) when symmetric memory is unavailable."""
+
+    HEADER = 64
+
+    def __init__(self, dist, cap_records, itemsize=80, dst=0):
+        import torch
+        import torch.distributed._symmetric_memory as symm_mem
+        self.torch, self.dist, self.dst = torch, dist, dst
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.cap, self.itemsize = int(cap_records), int(itemsize)
+        self.slot = (self.HEADER + self.cap * self.itemsize + 255) // 256 * 256
+        self.buf = symm_mem.empty((self.world * self.slot,), dtype=torch.uint8, device="cuda")
+        self.hdl = symm_mem.rendezvous(self.buf, dist.group.WORLD)
+        self.dst_view = self.hdl.get_buffer(dst, (self.world * self.slot,), torch.uint8)  # rank dst's buffer
+        lo = self.rank * self.slot
+        self.my_header = self.dst_view[lo:lo + 8].view(torch.int64)
+        self.my_records_ptr = int(self.hdl.buffer_ptrs[dst]) + lo + self.HEADER
+
+    def records_ptr(self):
+        """Device pointer (in rank dst's memory) where this rank's kernels write their dnv_call records."""
+        return self.my_records_ptr
+
+    def publish(self, n_calls):
+        """Call after the producing kernels were enqueued on the current stream."""
+        self.my_header.fill_(int(n_calls))
+        self.hdl.barrier()
+
+    def counts(self):
+        """On dst (after publish): per-rank record counts."""
+        heads = self.buf.view(self.world, self.slot)[:, :8].contiguous().view(self.torch.int64)
+        return heads.view(-1).tolist()
+
+    def records(self, counts=None):
+        """On dst: the gathered records as one contiguous uint8 [total, itemsize] tensor."""
+        counts = self.counts() if counts is None else counts
+        rows = self.buf.view(self.world, self.slot)[:, self.HEADER:self.HEADER + self.cap * self.itemsize]
+        rows = rows.reshape(self.world, self.cap, self.itemsize)
+        return self.torch.cat([rows[r, :counts[r]] for r in range(self.world)], dim=0)
+

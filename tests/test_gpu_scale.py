@@ -61,3 +61,18 @@ def test_10m_sites_properties(method):
         ref = O.infer(O.params(), sub)
         want = ref["denovo_bayes" if method == "BAYES" else "denovo_map"].astype(bool)
         assert np.array_equal(np.isin(idx, c_all["site"]), want)
+
+
+def test_two_gpu_sharded_gather_equals_single_gpu():
+    """Needs >= 2 GPUs (skipped on a 1-GPU box): torchrun tests/multi_gpu_check.py."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", "tests/multi_gpu_check.py"],
+                       cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("multi_gpu_check OK") == 2
