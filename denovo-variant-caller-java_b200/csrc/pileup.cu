@@ -280,7 +280,8 @@ __device__ __forceinline__ void pile_person(PileTileShared& sh, int64_t c_first,
       const int rel = (int)(__ldg(read_start + c0 + i) - P0);
       const int len = (int)(__ldg(base_off + c0 + i + 1) - b0);
       // the fast path reads two aligned words: keep it 8 bytes away from the end of the buffer
-      const int fast_len = (b0 + len + 8 <= n_bases) ? len : 0;
+      // ... and off the first word, so the aligned-down address never precedes the buffer
+      const int fast_len = (b0 >= 4 && b0 + len + 8 <= n_bases) ? len : 0;
       sh.rl[i] = make_int2(rel, fast_len);
       sh.len[i] = len;
       sh.ptr[i] = bases_addr + (unsigned long long)b0 - (unsigned long long)(long long)rel;

@@ -104,3 +104,57 @@ def test_mendel_filter_edges():
         with pytest.raises(D.DenovoError) as ei:
             eng.mendel_filter(bad)
         assert ei.value.code == D.DNV_E_BADBASE
+
+
+def test_mendel_filter_full_size_tiling_property():
+    """BASELINE config 2 scale (~6M records): a stream made of shifted copies of one block must give
+    the shifted copies of that block's PositionCalls (blocks do not interact), and the block itself
+    is bit-exact against the streaming oracle."""
+    import torch
+    block = S.make_callset(31, 200_000)
+    span = int(block["end"].max()) + 100
+    reps = 30
+    parts = []
+    for r in range(reps):
+        b = block.copy()
+        b["start"] += r * span
+        b["end"] += r * span
+        b["variant_id"] += r * 200_000
+        parts.append(b)
+    calls = np.concatenate(parts)
+    n_ref, want = O.mendel_stream(block)
+    with D.TrioEngine() as eng:
+        d_calls = torch.from_numpy(calls.view(np.uint8).reshape(len(calls), 32)).cuda()
+        d_out = torch.zeros((len(calls) // 3, 24), dtype=torch.uint8, device="cuda")
+        n = eng.mendel_filter_device(d_calls, len(calls), d_out, d_out.shape[0])
+        got = d_out[:n].cpu().numpy().view(D.PCALL_DT).reshape(-1)
+    assert n == reps * n_ref and len(calls) > 5_000_000
+    for r in (0, 1, reps - 1):
+        g = got[r * n_ref:(r + 1) * n_ref]
+        assert np.array_equal(g["position"], want["position"] + r * span)
+        assert np.array_equal(g["child_index"], want["child_index"] + r * len(block))
+        for f in ("child", "mom", "dad", "is_denovo"):
+            assert np.array_equal(g[f], want[f])
+    assert np.all(np.diff(got["child_index"]) > 0)
+
+
+def test_pileup_million_sites_window_parity():
+    """1M consecutive sites at 30x (the dense layout of configs 3-4): every non-gap base is counted
+    exactly once and a 20k-site window in the middle is bit-exact against the oracle."""
+    n_sites = 1_000_000
+    rs, bo, ba, pe = S.make_reads(41, 1, n_sites, depth=30)
+    pos = np.arange(1, n_sites + 1, dtype=np.int64)
+    with D.TrioEngine() as eng:
+        got = eng.pileup(rs, bo, ba, pe, pos)
+    lens = np.diff(bo)
+    posn = np.repeat(rs, lens) + (np.arange(bo[-1]) - np.repeat(bo[:-1], lens))
+    on_site = (posn >= 1) & (posn <= n_sites) & (ba != ord("-"))
+    assert int(got.astype(np.int64).sum()) == int(on_site.sum())
+    sel = slice(n_sites // 2, n_sites // 2 + 20000)
+    keep = (rs >= pos[sel][0] - 200) & (rs <= pos[sel][-1])
+    idx = np.nonzero(keep)[0]
+    bo2 = np.zeros(len(idx) + 1, np.int64)
+    np.cumsum(lens[idx], out=bo2[1:])
+    ba2 = np.concatenate([ba[bo[i]:bo[i + 1]] for i in idx])
+    rc, want = O.pileup(rs[idx], bo2, ba2, pe[idx], pos[sel])
+    assert rc == 0 and np.array_equal(got[sel], want)
