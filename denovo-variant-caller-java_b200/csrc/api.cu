@@ -92,6 +92,7 @@ int dnv_create(const dnv_params* p, dnv_ctx** out) {
     for (int i = 0; i < 64; i++) {
       DNV_CUDA(cudaEventCreate(&ctx->ev_k0[i]));
       DNV_CUDA(cudaEventCreate(&ctx->ev_k1[i]));
+      DNV_CUDA(cudaEventCreate(&ctx->ev_s1[i]));
     }
   DNV_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   for (int i = 0; i < 2; i++) {
@@ -111,14 +112,14 @@ int dnv_destroy(dnv_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->copy_stream);
-  cudaFree(ctx->d_tab); cudaFree(ctx->d_bits); cudaFree(ctx->d_tile_status);
+  cudaFree(ctx->d_tab); cudaFree(ctx->d_bits); cudaFree(ctx->d_tile_status); cudaFree(ctx->d_list);
   cudaFree(ctx->d_call_idx); cudaFree(ctx->d_counters); cudaFree(ctx->d_stage_calls); cudaFree(ctx->d_scratch);
   for (int i = 0; i < 2; i++) {
     cudaFree(ctx->d_stage_counts[i]); cudaFree(ctx->d_stage_dense[i]);
     cudaEventDestroy(ctx->ev_h2d[i]); cudaEventDestroy(ctx->ev_done[i]);
   }
   if (ctx->prm.flags & DNV_F_TIME_KERNELS)
-    for (int i = 0; i < 64; i++) { cudaEventDestroy(ctx->ev_k0[i]); cudaEventDestroy(ctx->ev_k1[i]); }
+    for (int i = 0; i < 64; i++) { cudaEventDestroy(ctx->ev_k0[i]); cudaEventDestroy(ctx->ev_k1[i]); cudaEventDestroy(ctx->ev_s1[i]); }
   cudaStreamDestroy(ctx->own_stream);
   cudaStreamDestroy(ctx->copy_stream);
   delete ctx;
@@ -161,10 +162,14 @@ static int finish_batch(dnv_ctx* ctx, int64_t n, int64_t cap, int64_t* n_calls) 
   DNV_CUDA(cudaMemcpyAsync(h, ctx->d_counters, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
   DNV_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->stats.fused_kernel_ms = 0;
+  ctx->stats.screen_kernel_ms = 0;
   for (int i = 0; i < ctx->n_timed; i++) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, ctx->ev_k0[i], ctx->ev_k1[i]) == cudaSuccess) ctx->stats.fused_kernel_ms += ms;
+    if (ctx->screened && cudaEventElapsedTime(&ms, ctx->ev_k0[i], ctx->ev_s1[i]) == cudaSuccess)
+      ctx->stats.screen_kernel_ms += ms;
   }
+  ctx->stats.n_screened_out = ctx->screened ? n - (int64_t)h[1] : 0;
   ctx->stats.n_sites = n;
   const unsigned long long total = h[ctx->calls_slot];
   ctx->stats.n_calls = (int64_t)total;
@@ -187,6 +192,7 @@ static int infer_device_impl(dnv_ctx* ctx, const void* d_counts, int bps, int64_
   ctx->stats = dnv_stats();
   ctx->n_timed = 0;
   ctx->calls_slot = 0;
+  ctx->screened = false;
   ctx->count_bytes = bps;
   DNV_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
   for (int64_t off = 0; off < n; off += kDeviceChunk) {
@@ -208,6 +214,7 @@ static int infer_host_impl(dnv_ctx* ctx, const void* counts, int bps, int64_t n,
   ctx->stats = dnv_stats();
   ctx->n_timed = 0;
   ctx->calls_slot = 0;
+  ctx->screened = false;
   ctx->count_bytes = bps;
   const int64_t chunk = std::min<int64_t>(kHostChunk, std::max<int64_t>(n, 1));
   const int64_t dev_cap = std::min(cap, n);

@@ -26,7 +26,8 @@ struct Tables {
   double pw_m[2][kPowTable];   // mantissa in [1,2) of r_j^k
   int32_t pw_e[2][kPowTable];  // binary exponent of r_j^k
   int32_t fast_ok;             // both ratios > 1 (always, unless eps is absurdly large)
-  int32_t pad_;
+  int32_t early_ok;            // the integer screen (trio_screen.cuh) is valid for these parameters
+  uint32_t c_hom_fx, c_het_fx; // log2(r_j) in 16.16 fixed point
   double mm2;                  // log2(eps/3)
   double k_men;                // ((1-mu)/4)/64
   double k_den[4];             // (mu/256)/nDen for nDen = 9,8,7,6
@@ -46,7 +47,7 @@ struct dnv_ctx {
   int device;
   cudaStream_t stream;       // compute (own_stream unless dnv_set_stream)
   cudaStream_t own_stream;
-  cudaEvent_t ev_k0[64], ev_k1[64];  // fused-kernel brackets (DNV_F_TIME_KERNELS)
+  cudaEvent_t ev_k0[64], ev_k1[64], ev_s1[64];  // kernel brackets (DNV_F_TIME_KERNELS): start, end, end of the screen
   int n_timed;
   cudaStream_t copy_stream;  // H2D / D2H of the host API
   cudaEvent_t ev_h2d[2], ev_done[2];
@@ -55,6 +56,8 @@ struct dnv_ctx {
   // per-chunk scratch (sized for chunk_cap sites)
   int64_t chunk_cap;
   uint32_t* d_bits;        // decision bit per site
+  uint32_t* d_list;        // sites the integer screen could not decide (chunk-relative)
+  bool screened;           // the last call used the screen
   unsigned long long* d_tile_status;  // decoupled look-back status per compaction block
   unsigned long long epoch;           // launch counter tagging d_tile_status entries
   int calls_slot;                     // counters[] slot holding the running call total (0 or 3)

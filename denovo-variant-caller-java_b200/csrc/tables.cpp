@@ -96,6 +96,14 @@ void build_tables(const dnv_params& p, Tables* t) {
       t->pw_inv[j][k] = (double)exp2l(-log2r[j] * (long double)k);
     }
   t->fast_ok = (log2r[0] > 0.0L && log2r[1] > 0.0L) ? 1 : 0;
+  // integer screen (trio_screen.cuh): Lden / Lmen <= 5334 mu / (1 - mu) for a Mendelian-consistent
+  // most-likely triple; valid when that bound is below the decision threshold and k*log2(r) fits 32 bits
+  const double thr_eff = p.method == DNV_METHOD_LRT ? p.lrt_threshold : 1.0;
+  const bool fits = log2r[0] < 60.0L && log2r[1] < 60.0L;
+  t->c_hom_fx = fits ? (uint32_t)llroundl(log2r[0] * 65536.0L) : 0;
+  t->c_het_fx = fits ? (uint32_t)llroundl(log2r[1] * 65536.0L) : 0;
+  t->early_ok = (t->fast_ok && fits && p.method != DNV_METHOD_MAP && thr_eff > 0.0 && std::isfinite(thr_eff) &&
+                 5334.0 * mu / (1.0 - mu) < 0.999 * thr_eff) ? 1 : 0;
   t->mm2 = (double)((logl(le) - logl(3.0L)) * l2e);
   t->k_men = (1.0 - mu) / 4 / 64;
   const int nd[4] = {9, 8, 7, 6};

@@ -12,9 +12,12 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "scan_util.cuh"
 #include "trio_exact.cuh"
 #include "trio_fast.cuh"
+#include "trio_screen.cuh"
 
 namespace dnv {
 
@@ -189,13 +192,14 @@ compact_details_kernel(const Tables* __restrict__ tab, const void* __restrict__ 
 // ---------------------------------------------------------------- launcher
 int ensure_chunk_scratch(dnv_ctx* ctx, int64_t n) {
   if (n <= ctx->chunk_cap) return DNV_OK;
-  cudaFree(ctx->d_bits); cudaFree(ctx->d_tile_status);
-  ctx->d_bits = nullptr; ctx->d_tile_status = nullptr;
+  cudaFree(ctx->d_bits); cudaFree(ctx->d_tile_status); cudaFree(ctx->d_list);
+  ctx->d_bits = nullptr; ctx->d_tile_status = nullptr; ctx->d_list = nullptr;
   ctx->chunk_cap = 0;
   const int64_t n_words = (n + 31) / 32;
   const int64_t n_blocks = (n_words + kCompactThreads - 1) / kCompactThreads;
   DNV_CUDA(cudaMalloc(&ctx->d_bits, (size_t)(n_words + 1) * 4));
   DNV_CUDA(cudaMalloc(&ctx->d_tile_status, (size_t)(n_blocks + 1) * 8));
+  DNV_CUDA(cudaMalloc(&ctx->d_list, (size_t)n * 4));
   DNV_CUDA(cudaMemsetAsync(ctx->d_tile_status, 0, (size_t)(n_blocks + 1) * 8, ctx->stream));
   ctx->chunk_cap = n;
   return DNV_OK;
@@ -234,6 +238,32 @@ int launch_trio_chunk(dnv_ctx* ctx, const void* d_counts, int64_t site_base, int
     const int grid = (int)(want < (int64_t)sms * 16 ? want : (int64_t)sms * 16);
     trio_direct_all_kernel<<<grid, kExactThreads, 0, st>>>(ctx->d_tab, d_counts, ctx->count_bytes, n, ctx->d_bits, d_dense,
                                                           ctx->d_counters);
+  } else if (ctx->h_tab.early_ok && !d_dense && !(ctx->prm.flags & DNV_F_NO_SCREEN)) {
+    // BAYES / LRT, calls only: exact integer screen at HBM speed, then the fused FP64 kernel on
+    // the sites it could not decide
+    DNV_CUDA(cudaMemsetAsync(ctx->d_bits, 0, (size_t)n_words * 4, st));
+    DNV_CUDA(cudaMemsetAsync(ctx->d_counters + 1, 0, sizeof(unsigned long long), st));
+    ScreenConsts sk;
+    sk.c_hom = ctx->h_tab.c_hom_fx;
+    sk.c_het = ctx->h_tab.c_het_fx;
+    const int64_t want = (n + kScreenThreads - 1) / kScreenThreads;
+    int per_sm = 1;
+    if (ctx->count_bytes == 12) {
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trio_screen_kernel<true>, kScreenThreads, 0);
+      const int grid = (int)std::min<int64_t>(want, (int64_t)sms * std::max(per_sm, 1));
+      trio_screen_kernel<true><<<grid, kScreenThreads, 0, st>>>((const unsigned char*)d_counts, n, sk, ctx->d_list,
+                                                               ctx->d_counters);
+    } else {
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trio_screen_kernel<false>, kScreenThreads, 0);
+      const int grid = (int)std::min<int64_t>(want, (int64_t)sms * std::max(per_sm, 1));
+      trio_screen_kernel<false><<<grid, kScreenThreads, 0, st>>>((const unsigned char*)d_counts, n, sk, ctx->d_list,
+                                                                ctx->d_counters);
+    }
+    if (timed) DNV_CUDA(cudaEventRecord(ctx->ev_s1[ctx->n_timed], st));
+    rc = launch_trio_fast(ctx, d_counts, n, nullptr, ctx->d_list);
+    if (rc) return rc;
+    ctx->stats.n_launches += 1;
+    ctx->screened = true;
   } else {
     rc = launch_trio_fast(ctx, d_counts, n, d_dense);
     if (rc) return rc;

@@ -18,6 +18,7 @@ DNV_OK, DNV_E_INVALID, DNV_E_CUDA, DNV_E_CAPACITY, DNV_E_BADBASE, DNV_E_UNSORTED
 METHODS = {"MAP": 0, "BAYES": 1, "LRT": 2}
 F_FORCE_DIRECT = 1
 F_TIME_KERNELS = 2
+F_NO_SCREEN = 4
 
 EXPORTS = ["dnv_create", "dnv_destroy", "dnv_last_error", "dnv_abi_version", "dnv_get_tables", "dnv_get_stats",
            "dnv_set_stream",
@@ -33,7 +34,7 @@ class Params(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("n_sites", C.c_int64), ("n_calls", C.c_int64), ("n_hard", C.c_int64), ("n_launches", C.c_int64),
-                ("fused_kernel_ms", C.c_double)]
+                ("fused_kernel_ms", C.c_double), ("screen_kernel_ms", C.c_double), ("n_screened_out", C.c_int64)]
 
 
 CALL_DT = np.dtype([("site", "<i8"), ("counts", "<u2", (12,)), ("dad", "u1"), ("mom", "u1"), ("child", "u1"),

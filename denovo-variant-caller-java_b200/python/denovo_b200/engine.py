@@ -42,11 +42,12 @@ class TrioEngine:
     """One CUDA device, one set of (seq_err_rate, denovo_mut_rate, lrt_threshold, method)."""
 
     def __init__(self, seq_err_rate=1e-2, denovo_mut_rate=1e-8, lrt_threshold=1.0, method="BAYES", device=0,
-                 force_direct=False, time_kernels=False):
+                 force_direct=False, time_kernels=False, no_screen=False):
         self.lib = L.load()
         m = L.METHODS[method.upper()] if isinstance(method, str) else int(method)
         self.params = L.Params(seq_err_rate, denovo_mut_rate, lrt_threshold, m, device,
-                               (L.F_FORCE_DIRECT if force_direct else 0) | (L.F_TIME_KERNELS if time_kernels else 0), 0)
+                               (L.F_FORCE_DIRECT if force_direct else 0) | (L.F_TIME_KERNELS if time_kernels else 0)
+                               | (L.F_NO_SCREEN if no_screen else 0), 0)
         self.method = m
         self.device = device
         h = C.c_void_p()
@@ -76,7 +77,8 @@ class TrioEngine:
         s = L.Stats()
         L.check(self.lib.dnv_get_stats(self._h, C.byref(s)))
         return {"n_sites": s.n_sites, "n_calls": s.n_calls, "n_hard": s.n_hard, "n_launches": s.n_launches,
-                "fused_kernel_ms": s.fused_kernel_ms}
+                "fused_kernel_ms": s.fused_kernel_ms, "screen_kernel_ms": s.screen_kernel_ms,
+                "n_screened_out": s.n_screened_out}
 
     def set_stream(self, cuda_stream):
         """Run on the caller's CUDA stream (int handle, e.g. torch.cuda.Stream().cuda_stream); None restores."""

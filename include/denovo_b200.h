@@ -67,8 +67,10 @@ enum {
   DNV_F_FORCE_DIRECT = 1u << 0, /* evaluate EVERY site with the exact direct-form
                                    kernel (1000 exp, reference operation order);
                                    validation only, ~30x slower */
-  DNV_F_TIME_KERNELS = 1u << 1 /* bracket the fused kernel with CUDA events on the
-                                  launching stream; read dnv_stats.fused_kernel_ms */
+  DNV_F_TIME_KERNELS = 1u << 1, /* bracket the kernels with CUDA events on the launching
+                                   stream; read dnv_stats.fused_kernel_ms / screen_kernel_ms */
+  DNV_F_NO_SCREEN = 1u << 2     /* BAYES/LRT: skip the exact integer screen and evaluate
+                                   every site with the fused FP64 kernel (A/B measurements) */
 };
 
 /* DenovoShared getters that reach the engine (M/DenovoShared.java:76-204). */
@@ -109,9 +111,11 @@ typedef struct {
   int64_t n_hard;      /* sites re-evaluated by the exact direct kernel
                           (threshold-ambiguous or in the underflow gray zone) */
   int64_t n_launches;  /* kernels launched by the last call */
-  double fused_kernel_ms; /* CUDA-event duration of the fused likelihood+posterior
-                             kernel(s) of the last call, summed over chunks
-                             (only when DNV_F_TIME_KERNELS is set, else 0) */
+  double fused_kernel_ms; /* CUDA-event duration of the decision kernels (integer screen +
+                             fused likelihood/posterior) of the last call, summed over
+                             chunks (only when DNV_F_TIME_KERNELS is set, else 0) */
+  double screen_kernel_ms; /* the integer screen's share of fused_kernel_ms */
+  int64_t n_screened_out;  /* sites the integer screen proved non-de-novo (no FP64 work) */
 } dnv_stats;
 
 /* One (Variant, VariantCall) pair of the VARIANT-mode stream, flattened to the

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_sizes_match_header():
     assert C.sizeof(L.Params) == 40
-    assert C.sizeof(L.Stats) == 40
+    assert C.sizeof(L.Stats) == 56
     assert D.CALL_DT.itemsize == 80 and D.SITE_DT.itemsize == 48
     assert D.VCALL_DT.itemsize == 32 and D.PCALL_DT.itemsize == 24
 
