@@ -24,10 +24,14 @@ METRIC = "trio candidate sites/sec (READ-mode BAYES, 30x)"
 SITES_PER_GPU = 10_000_000
 SEED = 0x5EED0003
 DEPTH, EPS, MU, LRT = 30, 1e-2, 1e-8, 1.0
-# ALGORITHMIC work per site of the form the fused kernel executes:
-#   bytes: 24 B of counts in + 1 decision bit out; flops: sparse factored form, FMA = 2
+# ALGORITHMIC work per site:
+#   integer screen (dominant kernel, HBM-bound): 24 B of counts in + 1 decision bit out
+#   fused FP64 kernel (only the sites the screen cannot decide): sparse factored form, FMA = 2
 BYTES_PER_SITE = 24.125
 FLOP_PER_SITE = 451.0
+# DRAM traffic of one screen launch over 10M sites from the ncu --set full capture committed as
+# profiles/r01_trio_screen_ncu.md (dram__bytes_read.sum + dram__bytes_write.sum), per site
+NCU_TRAFFIC_BYTES_PER_SITE = 24.46
 
 
 def load_peaks():
@@ -149,6 +153,7 @@ def main():
     ap.add_argument("--sites", type=int, default=SITES_PER_GPU)
     ap.add_argument("--method", default="BAYES")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-screen", action="store_true", help="evaluate every site with the fused FP64 kernel")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -172,7 +177,7 @@ def main():
     n = args.sites
     K, W = args.steps, max(args.warmup, 3)
 
-    eng = D.TrioEngine(EPS, MU, LRT, args.method, device=local, time_kernels=True)
+    eng = D.TrioEngine(EPS, MU, LRT, args.method, device=local, time_kernels=True, no_screen=args.no_screen)
     stream = torch.cuda.Stream(device=local)
     eng.set_stream(stream.cuda_stream)
 
@@ -222,12 +227,14 @@ def main():
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    fused_ms, launches = 0.0, 0
+    fused_ms, screen_ms, launches, screened_out = 0.0, 0.0, 0, 0
     e0.record(stream)
     for _ in range(K):
         total_calls = step()
         st = eng.stats()
         fused_ms += st["fused_kernel_ms"]
+        screen_ms += st["screen_kernel_ms"]
+        screened_out = st["n_screened_out"]
         launches += st["n_launches"]
     if peer and rank == 0:
         with torch.cuda.stream(stream):
@@ -273,19 +280,35 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant (fused likelihood + posterior) kernel
+    # ---- roofline of the dominant kernel
     fp64_peak, _ = eng.measure_fp64_peak()
     hbm_peak, peak_src = load_peaks()
-    k_ms = fused_ms / K
-    ach_tf = FLOP_PER_SITE * n / (k_ms * 1e-3) / 1e12
-    ach_gbs = BYTES_PER_SITE * n / (k_ms * 1e-3) / 1e9
-    roofline = {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": ach_tf / fp64_peak if fp64_peak else None, "traffic": None,
-                "kernel": "trio_fast_kernel", "kernel_ms": k_ms, "kernel_share_of_step": k_ms / (ms_max / K),
-                "flop_per_site": FLOP_PER_SITE,
-                "peak_source": "measured in this run (dependent-free DFMA chains, all SMs; MEASURED_PEAKS.json has no FP64 figure)",
-                "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                        "bytes_per_site": BYTES_PER_SITE, "peak_source": peak_src}}
+    k_ms = fused_ms / K          # decision kernels: integer screen + fused FP64 kernel on the undecided sites
+    s_ms = screen_ms / K         # the screen alone
+    if s_ms > 0:
+        # BAYES/LRT: the integer screen streams every site's counts and is the dominant kernel (HBM-bound)
+        n_fp64 = n - screened_out
+        ach_gbs = BYTES_PER_SITE * n / (s_ms * 1e-3) / 1e9
+        f_ms = max(k_ms - s_ms, 1e-9)
+        ach_tf = FLOP_PER_SITE * n_fp64 / (f_ms * 1e-3) / 1e12
+        roofline = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                    "traffic": NCU_TRAFFIC_BYTES_PER_SITE * n, "kernel": "trio_screen_kernel", "kernel_ms": s_ms,
+                    "kernel_share_of_step": s_ms / (ms_max / K), "bytes_per_site": BYTES_PER_SITE,
+                    "peak_source": peak_src,
+                    "sites_decided_by_screen": int(screened_out), "sites_to_fp64_kernel": int(n_fp64),
+                    "fp64_kernel": {"kernel": "trio_fast_kernel (list mode)", "kernel_ms": f_ms, "sites": int(n_fp64),
+                                    "flop_per_site": FLOP_PER_SITE, "achieved_tflops": ach_tf,
+                                    "fp64_peak_tflops": fp64_peak,
+                                    "peak_source": "dependent-free DFMA chains on all SMs, measured in this run"}}
+    else:
+        # MAP (or screen disabled): the fused FP64 kernel sees every site (FP64-pipe-bound)
+        ach_tf = FLOP_PER_SITE * n / (k_ms * 1e-3) / 1e12
+        roofline = {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                    "frac": ach_tf / fp64_peak if fp64_peak else None, "traffic": None,
+                    "kernel": "trio_fast_kernel", "kernel_ms": k_ms, "kernel_share_of_step": k_ms / (ms_max / K),
+                    "flop_per_site": FLOP_PER_SITE,
+                    "peak_source": "dependent-free DFMA chains on all SMs, measured in this run "
+                                   "(MEASURED_PEAKS.json has no FP64 figure)"}
 
     cpu = None
     if not args.no_cpu_baseline:

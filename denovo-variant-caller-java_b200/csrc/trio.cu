@@ -3,8 +3,11 @@
 //   K1  trio_fast_kernel (or trio_direct_all_kernel under DNV_F_FORCE_DIRECT):
 //         counts -> decision bit per site (+ dense record); hard sites are re-evaluated
 //         inside the kernel by the whole warp with the exact direct form
-//   K2  compact_details_kernel: single-pass order-preserving compaction of the called
-//         sites (decoupled look-back) fused with the exact per-call records -> dnv_call
+//   K0  trio_screen_kernel (BAYES/LRT, calls only): exact integer screen at HBM speed; K1 then
+//         only sees the ~1 % of sites it could not decide
+//   K2  compact_calls_kernel: single-pass order-preserving compaction of the called sites
+//         (decoupled look-back)
+//   K3  call_details_kernel: one thread per called site -> dnv_call
 //
 // Replaces the per-site task of ReadCaller.runBayesDenovoInference
 // (M/ReadCaller.java:111-130) -> BayesInfer.infer (M/BayesInfer.java:50-69).
@@ -54,25 +57,18 @@ trio_direct_all_kernel(const Tables* __restrict__ tab, const void* __restrict__ 
   }
 }
 
-// ---------------------------------------------------------------- K2 compaction + call records
-// ONE kernel: order-preserving compaction of the decision bits (single pass, decoupled
-// look-back over blocks of 8192 sites) fused with the call records: as soon as a block knows
-// the output offset of its calls it evaluates them (one warp per called site, exact direct
-// form) and writes dnv_call records in INPUT order.
+// ---------------------------------------------------------------- K2 compaction
+// Single-pass, order-preserving compaction of the decision bits (decoupled look-back over
+// blocks of 8192 sites): the global site index of every called site, in INPUT order.
 // status word: [63:34] epoch of this launch, [33:32] 1 = block aggregate, 2 = inclusive prefix, [31:0] value.
 // counters: [in_slot] calls before this chunk, [out_slot] <- calls after it, [6] block ticket.
 constexpr int kCompactThreads = 256;
 static_assert(kCompactThreads == kScanThreads, "one bit-word per thread");
 
-__global__ void __launch_bounds__(kCompactThreads, 2)
-compact_details_kernel(const Tables* __restrict__ tab, const void* __restrict__ counts, int bps, int64_t site_base,
-                       const uint32_t* __restrict__ bits, int64_t n_words, unsigned long long* status,
-                       unsigned long long epoch, unsigned long long* counters, int in_slot, int out_slot,
-                       int64_t* __restrict__ call_idx, int64_t call_idx_cap, dnv_call* __restrict__ calls,
-                       int64_t cap, const FastConsts k) {
-  __shared__ double s_rel[1000];
-  __shared__ uint32_t s_isden[32];
-  __shared__ double s_rmax[110];
+__global__ void __launch_bounds__(kCompactThreads)
+compact_calls_kernel(int64_t site_base, const uint32_t* __restrict__ bits, int64_t n_words,
+                     unsigned long long* status, unsigned long long epoch, unsigned long long* counters,
+                     int in_slot, int out_slot, int64_t* __restrict__ call_idx, int64_t call_idx_cap) {
   __shared__ int s_warp_sum[kCompactThreads / 32];
   __shared__ unsigned int s_bid;
   __shared__ unsigned long long s_excl;
@@ -127,42 +123,57 @@ compact_details_kernel(const Tables* __restrict__ tab, const void* __restrict__ 
     }
   }
   if (total == 0) return;  // block-uniform
-  stage_exact_tables(tab, s_rel, s_isden);
-  stage_map_bounds(tab, s_rmax);
   __syncthreads();
-  const int64_t pos0 = (int64_t)counters[in_slot] + (int64_t)s_excl;
-  int64_t pos = pos0 + warp_off + x - cnt;
+  int64_t pos = (int64_t)counters[in_slot] + (int64_t)s_excl + warp_off + x - cnt;
   while (word) {
     const int bit = __ffs(word) - 1;
     word &= word - 1;
     if (pos < call_idx_cap) call_idx[pos] = site_base + w * 32 + bit;
     pos++;
   }
-  __syncthreads();  // this block's call_idx entries are visible to its own warps
-  // One THREAD per called site.  Values: the factored form (power tables read through L1)
-  // unless the site is hard, then the exact direct form in the reference's own order.
-  // maxGenoType / max_ll: always the exact (pruned) log-domain argmax.
+}
+
+// ---------------------------------------------------------------- K3 call records
+// One THREAD per called site (calls [counters[in_slot], counters[out_slot]) of this chunk).
+// Values: the factored form (power tables read through L1) unless the site is hard, then the
+// exact direct form in the reference's own order.  maxGenoType / max_ll: always the exact
+// (pruned) log-domain argmax.
+constexpr int kDetailThreads = 64;
+
+__global__ void __launch_bounds__(kDetailThreads)
+call_details_kernel(const Tables* __restrict__ tab, const void* __restrict__ counts, int bps, int64_t site_base,
+                    const int64_t* __restrict__ call_idx, const unsigned long long* __restrict__ counters,
+                    int in_slot, int out_slot, dnv_call* __restrict__ calls, int64_t cap, const FastConsts k) {
+  const unsigned long long lo = counters[in_slot];
+  unsigned long long hi = counters[out_slot];
+  if (hi > (unsigned long long)cap) hi = (unsigned long long)cap;
+  if (lo + (unsigned long long)blockIdx.x * kDetailThreads >= hi) return;
+  __shared__ double s_rel[1000];
+  __shared__ uint32_t s_isden[32];
+  __shared__ double s_rmax[110];
+  stage_exact_tables(tab, s_rel, s_isden);
+  stage_map_bounds(tab, s_rmax);
+  __syncthreads();
   const GmemPow pw{tab};
-  for (int i = threadIdx.x; i < total; i += kCompactThreads) {
-    const int64_t p = pos0 + i;
-    if (p >= cap) break;
+  for (unsigned long long p = lo + (unsigned long long)blockIdx.x * kDetailThreads + threadIdx.x; p < hi;
+       p += (unsigned long long)gridDim.x * kDetailThreads) {
     const int64_t gsite = call_idx[p];
     uint16_t c[12];
     load_counts(counts, bps, gsite - site_base, c);
     int ci[12];
 #pragma unroll
     for (int q = 0; q < 12; q++) ci[q] = c[q];
-    LinOut lo;
+    LinOut lo_;
     if (k.lin_ok && k.method != DNV_METHOD_MAP) {
-      linear_site(pw, ci, k.k_men, k.kd9, k.kd8, k.kd7, k.kd6, k.thr, k.mm2, k.method, k.lrt_threshold, lo);
+      linear_site(pw, ci, k.k_men, k.kd9, k.kd8, k.kd7, k.kd6, k.thr, k.mm2, k.method, k.lrt_threshold, lo_);
     } else if (k.lin_ok) {  // MAP: the decision never needed the sums; the values still come from them
-      linear_site(pw, ci, k.k_men, k.kd9, k.kd8, k.kd7, k.kd6, 1.0, k.mm2, DNV_METHOD_BAYES, 1.0, lo);
-      lo.hard = lo.zd == 2 || lo.zm == 2;
+      linear_site(pw, ci, k.k_men, k.kd9, k.kd8, k.kd7, k.kd6, 1.0, k.mm2, DNV_METHOD_BAYES, 1.0, lo_);
+      lo_.hard = lo_.zd == 2 || lo_.zm == 2;
     } else {
-      lo.hard = true;
+      lo_.hard = true;
     }
     dnv_call o;
-    if (lo.hard) {
+    if (lo_.hard) {
       ExactOut r;
       exact_site(c, s_rel, s_isden, k.hm, k.ht, k.mm, k.method, k.lrt_threshold, &r);
       o.dad = (uint8_t)r.dad; o.mom = (uint8_t)r.mom; o.child = (uint8_t)r.child;
@@ -178,7 +189,7 @@ compact_details_kernel(const Tables* __restrict__ tab, const void* __restrict__ 
       exact_map_pruned(Ld, Lm, Lc, s_rel, s_rmax, &best, &max_ll);
       o.dad = (uint8_t)(best / 100); o.mom = (uint8_t)((best / 10) % 10); o.child = (uint8_t)(best % 10);
       o.max_ll = max_ll;
-      linear_values(lo, o.p, o.lr, o.log_men, o.log_den);
+      linear_values(lo_, o.p, o.lr, o.log_men, o.log_den);
       o.flags = 0;
     }
     o.site = gsite;
@@ -246,19 +257,8 @@ int launch_trio_chunk(dnv_ctx* ctx, const void* d_counts, int64_t site_base, int
     ScreenConsts sk;
     sk.c_hom = ctx->h_tab.c_hom_fx;
     sk.c_het = ctx->h_tab.c_het_fx;
-    const int64_t want = (n + kScreenThreads - 1) / kScreenThreads;
-    int per_sm = 1;
-    if (ctx->count_bytes == 12) {
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trio_screen_kernel<true>, kScreenThreads, 0);
-      const int grid = (int)std::min<int64_t>(want, (int64_t)sms * std::max(per_sm, 1));
-      trio_screen_kernel<true><<<grid, kScreenThreads, 0, st>>>((const unsigned char*)d_counts, n, sk, ctx->d_list,
-                                                               ctx->d_counters);
-    } else {
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trio_screen_kernel<false>, kScreenThreads, 0);
-      const int grid = (int)std::min<int64_t>(want, (int64_t)sms * std::max(per_sm, 1));
-      trio_screen_kernel<false><<<grid, kScreenThreads, 0, st>>>((const unsigned char*)d_counts, n, sk, ctx->d_list,
-                                                                ctx->d_counters);
-    }
+    rc = ctx->count_bytes == 12 ? launch_screen<true>(ctx, d_counts, n, sk) : launch_screen<false>(ctx, d_counts, n, sk);
+    if (rc) return rc;
     if (timed) DNV_CUDA(cudaEventRecord(ctx->ev_s1[ctx->n_timed], st));
     rc = launch_trio_fast(ctx, d_counts, n, nullptr, ctx->d_list);
     if (rc) return rc;
@@ -270,12 +270,14 @@ int launch_trio_chunk(dnv_ctx* ctx, const void* d_counts, int64_t site_base, int
   }
   if (timed) DNV_CUDA(cudaEventRecord(ctx->ev_k1[ctx->n_timed++], st));
   const int in_slot = ctx->calls_slot, out_slot = in_slot == 0 ? 3 : 0;
-  compact_details_kernel<<<n_blocks, kCompactThreads, 0, st>>>(ctx->d_tab, d_counts, ctx->count_bytes, site_base, ctx->d_bits, n_words,
-                                                              ctx->d_tile_status, ++ctx->epoch, ctx->d_counters,
-                                                              in_slot, out_slot, ctx->d_call_idx, ctx->call_idx_cap,
-                                                              d_calls, cap, make_fast_consts(ctx->h_tab));
+  compact_calls_kernel<<<n_blocks, kCompactThreads, 0, st>>>(site_base, ctx->d_bits, n_words, ctx->d_tile_status,
+                                                            ++ctx->epoch, ctx->d_counters, in_slot, out_slot,
+                                                            ctx->d_call_idx, ctx->call_idx_cap);
+  call_details_kernel<<<sms * 4, kDetailThreads, 0, st>>>(ctx->d_tab, d_counts, ctx->count_bytes, site_base,
+                                                         ctx->d_call_idx, ctx->d_counters, in_slot, out_slot, d_calls,
+                                                         cap, make_fast_consts(ctx->h_tab));
   ctx->calls_slot = out_slot;
-  ctx->stats.n_launches += 2;
+  ctx->stats.n_launches += 3;
   DNV_CUDA(cudaGetLastError());
   return DNV_OK;
 }

@@ -19,6 +19,8 @@
 // the kernel streams the counts at HBM speed and appends the remaining sites to a list that the
 // fused FP64 kernel (trio_fast.cuh) evaluates.
 #pragma once
+#include <algorithm>
+
 #include "dnv_internal.cuh"
 #include "trio_fast.cuh"
 
@@ -32,62 +34,77 @@ struct ScreenConsts {
   uint32_t c_hom, c_het;  // log2(r_hom), log2(r_het) in 16.16 fixed point
 };
 
-struct ScreenShared {
-  alignas(16) unsigned char tile[kScreenWarps][kScreenBufs][kWarpTileBytes];
-  alignas(8) unsigned long long bar[kScreenWarps][kScreenBufs];
-};
-
-// most frequent allele (index) and its count; ties -> lowest index (any maximiser is fine)
-__device__ __forceinline__ void argmax4(int n0, int n1, int n2, int n3, int& x, int& v) {
-  const int x01 = n1 > n0 ? 1 : 0, m01 = max(n0, n1);
-  const int x23 = n3 > n2 ? 3 : 2, m23 = max(n2, n3);
-  x = m23 > m01 ? x23 : x01;
-  v = max(m01, m23);
+// One person: keys are (count << 2) | allele, so integer max/min order counts and carry the
+// allele along (equal counts -> any maximiser is fine).  Returns the allele mask of the most
+// likely genotype in bits 0-3 and its two alleles in bits 4-5 / 6-7; bit 8 set = too deep.
+__device__ __forceinline__ int screen_person(int k0, int k1, int k2, int k3, const ScreenConsts& k) {
+  const int m01 = max(k0, k1), l01 = min(k0, k1), m23 = max(k2, k3), l23 = min(k2, k3);
+  const int top = max(m01, m23);                          // most frequent allele
+  const int sec = max(min(m01, m23), max(l01, l23));      // second most frequent
+  const int k_hom = top >> 2, k_het = k_hom + (sec >> 2);
+  const int x = top & 3, y = sec & 3;
+  const bool het = (uint32_t)k_het * k.c_het > (uint32_t)k_hom * k.c_hom;  // r_het^k_het > r_hom^k_hom
+  const int y2 = het ? y : x;
+  return ((1 << x) | (1 << y2)) | (x << 4) | (y2 << 6) | (k_het >= kPowTable ? 256 : 0);
 }
 
-// true = provably not de novo (see the header of this file)
-__device__ __forceinline__ bool screen_site(const int* c, const ScreenConsts& k) {
-  int a1[3], a2[3], mask[3];
-  bool ok = true;
+// true = provably not de novo (see the header of this file); w = the site's three uint2 words
+template <bool kU8>
+__device__ __forceinline__ bool screen_site(const uint32_t* w, const ScreenConsts& k) {
+  int g[3];
 #pragma unroll
   for (int p = 0; p < 3; p++) {
-    const int* n = c + 4 * p;
-    int x, k_hom, y, second;
-    argmax4(n[0], n[1], n[2], n[3], x, k_hom);
-    argmax4(x == 0 ? -1 : n[0], x == 1 ? -1 : n[1], x == 2 ? -1 : n[2], x == 3 ? -1 : n[3], y, second);
-    const int k_het = k_hom + second;
-    ok &= k_het < kPowTable;  // deeper than the tables: the fused kernel hands it to the exact path
-    const bool het = (uint32_t)k_het * k.c_het > (uint32_t)k_hom * k.c_hom;
-    a1[p] = x;
-    a2[p] = het ? y : x;
-    mask[p] = (1 << x) | (het ? (1 << y) : 0);
+    int k0, k1, k2, k3;
+    if (kU8) {
+      const uint32_t v = w[p];
+      k0 = (int)((v & 0xFFu) << 2);
+      k1 = (int)(((v >> 6) & 0x3FCu) | 1u);
+      k2 = (int)(((v >> 14) & 0x3FCu) | 2u);
+      k3 = (int)(((v >> 22) & 0x3FCu) | 3u);
+    } else {
+      const uint32_t lo = w[2 * p], hi = w[2 * p + 1];
+      k0 = (int)((lo & 0xFFFFu) << 2);
+      k1 = (int)(((lo >> 14) & 0x3FFFCu) | 1u);
+      k2 = (int)(((hi & 0xFFFFu) << 2) | 2u);
+      k3 = (int)(((hi >> 14) & 0x3FFFCu) | 3u);
+    }
+    g[p] = screen_person(k0, k1, k2, k3, k);
   }
   // isDenovoMap, M/DenovoUtil.java:41-50, on the chosen triple (0 dad, 1 mom, 2 child)
-  const int c1 = a1[2], c2 = a2[2];
-  const int mendel = ((mask[1] >> c1) & (mask[0] >> c2) & 1) | ((mask[1] >> c2) & (mask[0] >> c1) & 1);
-  return ok && mendel;
+  const int c1 = (g[2] >> 4) & 3, c2 = (g[2] >> 6) & 3;
+  const int mendel = ((g[1] >> c1) & (g[0] >> c2) & 1) | ((g[1] >> c2) & (g[0] >> c1) & 1);
+  return mendel && !((g[0] | g[1] | g[2]) & 256);
 }
+
+// Each warp walks tiles of 64 sites (two per lane, 1536 / 768 bytes), four tiles in flight per
+// warp (TMA bulk copies into warp-private buffers), so ~0.9 MB per SM is always on its way in.
+constexpr int kScreenSites = 64;
 
 template <bool kU8>
 __global__ void __launch_bounds__(kScreenThreads)
 trio_screen_kernel(const unsigned char* __restrict__ counts, int64_t n, const ScreenConsts k,
                    uint32_t* __restrict__ list, unsigned long long* __restrict__ counters) {
-  __shared__ ScreenShared s;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int kBps = kU8 ? 12 : 24;
-  constexpr int kTile = 32 * kBps;
-  const int64_t n_tiles = (n + 31) / 32;
+  constexpr int kTile = kScreenSites * kBps;
+  constexpr int kWords = kBps / 4;  // 32-bit words per site
+  unsigned char* tiles = smem_raw;  // [kScreenWarps][kScreenBufs][kTile]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + kScreenWarps * kScreenBufs * kTile);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char* my_tiles = tiles + (size_t)warp * kScreenBufs * kTile;
+  unsigned long long* my_bars = bars + warp * kScreenBufs;
+  const int64_t n_tiles = (n + kScreenSites - 1) / kScreenSites;
   const bool tma_ok = (reinterpret_cast<uintptr_t>(counts) & 15) == 0;
   if (lane == 0) {
 #pragma unroll
-    for (int b = 0; b < kScreenBufs; b++) mbar_init(&s.bar[warp][b], 1);
+    for (int b = 0; b < kScreenBufs; b++) mbar_init(&my_bars[b], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
   auto issue = [&](int64_t t, int buf) {
-    if (lane == 0 && tma_ok && t < n_tiles && (t + 1) * 32 <= n) {
-      mbar_expect_tx(&s.bar[warp][buf], kTile);
-      tma_bulk_g2s(s.tile[warp][buf], counts + t * kTile, kTile, &s.bar[warp][buf]);
+    if (lane == 0 && tma_ok && t < n_tiles && (t + 1) * kScreenSites <= n) {
+      mbar_expect_tx(&my_bars[buf], kTile);
+      tma_bulk_g2s(my_tiles + buf * kTile, counts + t * kTile, kTile, &my_bars[buf]);
     }
   };
   const int64_t warps_total = (int64_t)gridDim.x * kScreenWarps;
@@ -97,31 +114,57 @@ trio_screen_kernel(const unsigned char* __restrict__ counts, int64_t n, const Sc
   uint32_t phases = 0;
   int buf = 0;
   for (int64_t t = t0; t < n_tiles; t += warps_total, buf = (buf + 1) % kScreenBufs) {
-    const int64_t site = t * 32 + lane;
-    int c[12];
-    if (tma_ok && (t + 1) * 32 <= n) {
-      mbar_wait(&s.bar[warp][buf], (phases >> buf) & 1u);
+    uint32_t w[2][kWords];
+    const int64_t site0 = t * kScreenSites + lane;
+    if (tma_ok && (t + 1) * kScreenSites <= n) {
+      mbar_wait(&my_bars[buf], (phases >> buf) & 1u);
       phases ^= 1u << buf;
-      if (kU8) unpack_counts8(reinterpret_cast<const uint32_t*>(s.tile[warp][buf] + lane * 12), c);
-      else unpack_counts(reinterpret_cast<const uint2*>(s.tile[warp][buf] + lane * 24), c);
-    } else if (site < n) {
-      if (kU8) unpack_counts8(reinterpret_cast<const uint32_t*>(counts + site * 12), c);
-      else unpack_counts(reinterpret_cast<const uint2*>(counts + site * 24), c);
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(my_tiles + buf * kTile);
+#pragma unroll
+      for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int q = 0; q < kWords; q++) w[h][q] = src[(h * 32 + lane) * kWords + q];
     } else {
 #pragma unroll
-      for (int q = 0; q < 12; q++) c[q] = 0;
+      for (int h = 0; h < 2; h++) {
+        const int64_t site = site0 + h * 32;
+#pragma unroll
+        for (int q = 0; q < kWords; q++)
+          w[h][q] = site < n ? __ldg(reinterpret_cast<const uint32_t*>(counts + site * kBps) + q) : 0u;
+      }
     }
     __syncwarp();  // the buffer consumed in the previous trip may now be refilled
     issue(t + (kScreenBufs - 1) * warps_total, (buf + kScreenBufs - 1) % kScreenBufs);
-    const bool fail = site < n && !screen_site(c, k);
-    const uint32_t fw = __ballot_sync(0xffffffffu, fail);
-    if (fw) {
-      unsigned long long base = 0;
-      if (lane == 0) base = atomicAdd(&counters[1], (unsigned long long)__popc(fw));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (fail) list[base + __popc(fw & ((1u << lane) - 1))] = (uint32_t)site;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int64_t site = site0 + h * 32;
+      const bool fail = site < n && !screen_site<kU8>(w[h], k);
+      const uint32_t fw = __ballot_sync(0xffffffffu, fail);
+      if (fw) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&counters[1], (unsigned long long)__popc(fw));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (fail) list[base + __popc(fw & ((1u << lane) - 1))] = (uint32_t)site;
+      }
     }
   }
+}
+
+template <bool kU8>
+static int launch_screen(dnv_ctx* ctx, const void* d_counts, int64_t n, const ScreenConsts& sk) {
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  constexpr int kTile = kScreenSites * (kU8 ? 12 : 24);
+  const size_t smem = (size_t)kScreenWarps * kScreenBufs * kTile + kScreenWarps * kScreenBufs * 8;
+  auto kern = trio_screen_kernel<kU8>;
+  DNV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  DNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kScreenThreads, smem));
+  const int64_t want = ((n + kScreenSites - 1) / kScreenSites + kScreenWarps - 1) / kScreenWarps;
+  const int grid = (int)std::min<int64_t>(std::max<int64_t>(want, 1), (int64_t)sms * std::max(per_sm, 1));
+  kern<<<grid, kScreenThreads, smem, ctx->stream>>>((const unsigned char*)d_counts, n, sk, ctx->d_list, ctx->d_counters);
+  DNV_CUDA(cudaGetLastError());
+  return DNV_OK;
 }
 
 }  // namespace dnv
