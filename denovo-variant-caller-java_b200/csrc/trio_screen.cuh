@@ -15,9 +15,17 @@
 // a person follows from integer counts alone: the best homozygote is the most frequent allele
 // (k_hom reads), the best heterozygote the two most frequent ones (k_het reads), and
 // r_hom^k_hom vs r_het^k_het is compared as k * log2(r) in 16.16 fixed point.
-// So ~99 % of sites are decided with ~100 integer instructions and no floating point at all;
-// the kernel streams the counts at HBM speed and appends the remaining sites to a list that the
+// So ~99 % of sites are decided with integer instructions and no floating point at all; the
+// kernel streams the counts at HBM speed and appends the remaining sites to a list that the
 // fused FP64 kernel (trio_fast.cuh) evaluates.
+//
+// Two levels, so the common case costs ~40 instructions:
+//   level 1  the same allele X dominates all three pileups so strongly that XX beats every
+//            heterozygote:  n_X * log2(r_hom) >= N * log2(r_het)  (N = depth; implies n_X > N/2,
+//            so XX is each person's most likely genotype) -> the triple (XX, XX, XX) is Mendelian.
+//   level 2  the general test above (top two alleles per person).  Sites failing level 1 are
+//            parked in a warp-private shared-memory queue and level 2 runs on 32 of them at a
+//            time, so the ~10 % that need it do not make whole warps diverge.
 #pragma once
 #include <algorithm>
 
@@ -28,7 +36,7 @@ namespace dnv {
 
 constexpr int kScreenThreads = 256;
 constexpr int kScreenWarps = kScreenThreads / 32;
-constexpr int kScreenBufs = 4;  // tiles in flight per warp: 3 ahead of the one being consumed
+constexpr int kScreenBufs = 3;  // tile buffers per warp: 2 tiles in flight ahead of the one being consumed
 
 struct ScreenConsts {
   uint32_t c_hom, c_het;  // log2(r_hom), log2(r_het) in 16.16 fixed point
@@ -76,9 +84,45 @@ __device__ __forceinline__ bool screen_site(const uint32_t* w, const ScreenConst
   return mendel && !((g[0] | g[1] | g[2]) & 256);
 }
 
-// Each warp walks tiles of 64 sites (two per lane, 1536 / 768 bytes), four tiles in flight per
-// warp (TMA bulk copies into warp-private buffers), so ~0.9 MB per SM is always on its way in.
+// level 1 (see the header): w = the site's packed count words
+template <bool kU8>
+__device__ __forceinline__ bool screen_level1(const uint32_t* w, const ScreenConsts& k) {
+  // candidate X = dad's most frequent allele
+  int k0, k1, k2, k3;
+  if (kU8) {
+    const uint32_t v = w[0];
+    k0 = (int)((v & 0xFFu) << 2);
+    k1 = (int)(((v >> 6) & 0x3FCu) | 1u);
+    k2 = (int)(((v >> 14) & 0x3FCu) | 2u);
+    k3 = (int)(((v >> 22) & 0x3FCu) | 3u);
+  } else {
+    const uint32_t lo = w[0], hi = w[1];
+    k0 = (int)((lo & 0xFFFFu) << 2);
+    k1 = (int)(((lo >> 14) & 0x3FFFCu) | 1u);
+    k2 = (int)(((hi & 0xFFFFu) << 2) | 2u);
+    k3 = (int)(((hi >> 14) & 0x3FFFCu) | 3u);
+  }
+  const int x = max(max(k0, k1), max(k2, k3)) & 3;
+  bool ok = true;
+#pragma unroll
+  for (int p = 0; p < 3; p++) {
+    uint32_t nx, depth;
+    if (kU8) {
+      nx = (w[p] >> (8 * x)) & 0xFFu;
+      depth = __dp4a(w[p], 0x01010101u, 0u);
+    } else {
+      nx = ((x & 2 ? w[2 * p + 1] : w[2 * p]) >> (16 * (x & 1))) & 0xFFFFu;
+      depth = __dp2a_lo(w[2 * p], 0x0101u, __dp2a_lo(w[2 * p + 1], 0x0101u, 0u));
+    }
+    ok &= depth < (uint32_t)kPowTable && nx * k.c_hom >= depth * k.c_het;
+  }
+  return ok;
+}
+
+// Each warp walks tiles of 64 sites (two per lane, 1536 / 768 bytes), three tiles in flight per
+// warp (TMA bulk copies into warp-private buffers).
 constexpr int kScreenSites = 64;
+constexpr int kScreenQueue = 64;  // level-2 queue entries per warp (at most 31 + 32 are ever parked)
 
 template <bool kU8>
 __global__ void __launch_bounds__(kScreenThreads)
@@ -88,11 +132,14 @@ trio_screen_kernel(const unsigned char* __restrict__ counts, int64_t n, const Sc
   constexpr int kBps = kU8 ? 12 : 24;
   constexpr int kTile = kScreenSites * kBps;
   constexpr int kWords = kBps / 4;  // 32-bit words per site
+  constexpr int kEntry = kWords + 1;  // queue entry: the site's words + its index
   unsigned char* tiles = smem_raw;  // [kScreenWarps][kScreenBufs][kTile]
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + kScreenWarps * kScreenBufs * kTile);
+  uint32_t* queues = reinterpret_cast<uint32_t*>(bars + kScreenWarps * kScreenBufs);  // [kScreenWarps][kScreenQueue][kEntry]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char* my_tiles = tiles + (size_t)warp * kScreenBufs * kTile;
   unsigned long long* my_bars = bars + warp * kScreenBufs;
+  uint32_t* my_queue = queues + (size_t)warp * kScreenQueue * kEntry;
   const int64_t n_tiles = (n + kScreenSites - 1) / kScreenSites;
   const bool tma_ok = (reinterpret_cast<uintptr_t>(counts) & 15) == 0;
   if (lane == 0) {
@@ -106,6 +153,30 @@ trio_screen_kernel(const unsigned char* __restrict__ counts, int64_t n, const Sc
       mbar_expect_tx(&my_bars[buf], kTile);
       tma_bulk_g2s(my_tiles + buf * kTile, counts + t * kTile, kTile, &my_bars[buf]);
     }
+  };
+  // level 2 on up to 32 parked sites; what it cannot decide goes to the FP64 kernel's list
+  int qcount = 0;
+  auto drain = [&](int take) {
+    __syncwarp();
+    const int e = qcount - take + lane;
+    bool fail = false;
+    uint32_t site = 0;
+    if (lane < take) {
+      uint32_t w[kWords];
+#pragma unroll
+      for (int q = 0; q < kWords; q++) w[q] = my_queue[e * kEntry + q];
+      site = my_queue[e * kEntry + kWords];
+      fail = !screen_site<kU8>(w, k);
+    }
+    const uint32_t fw = __ballot_sync(0xffffffffu, fail);
+    if (fw) {
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(&counters[1], (unsigned long long)__popc(fw));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (fail) list[base + __popc(fw & ((1u << lane) - 1))] = site;
+    }
+    qcount -= take;
+    __syncwarp();
   };
   const int64_t warps_total = (int64_t)gridDim.x * kScreenWarps;
   const int64_t t0 = (int64_t)blockIdx.x * kScreenWarps + warp;
@@ -138,16 +209,21 @@ trio_screen_kernel(const unsigned char* __restrict__ counts, int64_t n, const Sc
 #pragma unroll
     for (int h = 0; h < 2; h++) {
       const int64_t site = site0 + h * 32;
-      const bool fail = site < n && !screen_site<kU8>(w[h], k);
-      const uint32_t fw = __ballot_sync(0xffffffffu, fail);
-      if (fw) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(&counters[1], (unsigned long long)__popc(fw));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (fail) list[base + __popc(fw & ((1u << lane) - 1))] = (uint32_t)site;
+      const bool park = site < n && !screen_level1<kU8>(w[h], k);
+      const uint32_t pw = __ballot_sync(0xffffffffu, park);
+      if (pw) {
+        if (park) {
+          const int e = qcount + __popc(pw & ((1u << lane) - 1));
+#pragma unroll
+          for (int q = 0; q < kWords; q++) my_queue[e * kEntry + q] = w[h][q];
+          my_queue[e * kEntry + kWords] = (uint32_t)site;
+        }
+        qcount += __popc(pw);
+        if (qcount >= 32) drain(32);
       }
     }
   }
+  if (qcount > 0) drain(qcount);
 }
 
 template <bool kU8>
@@ -155,7 +231,8 @@ static int launch_screen(dnv_ctx* ctx, const void* d_counts, int64_t n, const Sc
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
   constexpr int kTile = kScreenSites * (kU8 ? 12 : 24);
-  const size_t smem = (size_t)kScreenWarps * kScreenBufs * kTile + kScreenWarps * kScreenBufs * 8;
+  const size_t smem = (size_t)kScreenWarps * kScreenBufs * kTile + kScreenWarps * kScreenBufs * 8 +
+                      (size_t)kScreenWarps * kScreenQueue * ((kU8 ? 3 : 6) + 1) * 4;
   auto kern = trio_screen_kernel<kU8>;
   DNV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
