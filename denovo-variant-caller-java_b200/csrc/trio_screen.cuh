@@ -119,10 +119,11 @@ __device__ __forceinline__ bool screen_level1(const uint32_t* w, const ScreenCon
   return ok;
 }
 
-// Each warp walks tiles of 64 sites (two per lane, 1536 / 768 bytes), three tiles in flight per
-// warp (TMA bulk copies into warp-private buffers).
-constexpr int kScreenSites = 64;
-constexpr int kScreenQueue = 64;  // level-2 queue entries per warp (at most 31 + 32 are ever parked)
+// Each warp walks tiles of 128 sites (four per lane, 3072 / 1536 bytes); TMA bulk copies keep two
+// tiles in flight ahead of the one being consumed, in warp-private buffers.
+constexpr int kScreenSites = 128;
+constexpr int kScreenPerLane = kScreenSites / 32;
+constexpr int kScreenQueue = 64;  // level-2 queue entries (site indices) per warp: at most 31 + 32 parked
 
 template <bool kU8>
 __global__ void __launch_bounds__(kScreenThreads)
@@ -132,14 +133,13 @@ trio_screen_kernel(const unsigned char* __restrict__ counts, int64_t n, const Sc
   constexpr int kBps = kU8 ? 12 : 24;
   constexpr int kTile = kScreenSites * kBps;
   constexpr int kWords = kBps / 4;  // 32-bit words per site
-  constexpr int kEntry = kWords + 1;  // queue entry: the site's words + its index
   unsigned char* tiles = smem_raw;  // [kScreenWarps][kScreenBufs][kTile]
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + kScreenWarps * kScreenBufs * kTile);
-  uint32_t* queues = reinterpret_cast<uint32_t*>(bars + kScreenWarps * kScreenBufs);  // [kScreenWarps][kScreenQueue][kEntry]
+  uint32_t* queues = reinterpret_cast<uint32_t*>(bars + kScreenWarps * kScreenBufs);  // [kScreenWarps][kScreenQueue]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char* my_tiles = tiles + (size_t)warp * kScreenBufs * kTile;
   unsigned long long* my_bars = bars + warp * kScreenBufs;
-  uint32_t* my_queue = queues + (size_t)warp * kScreenQueue * kEntry;
+  uint32_t* my_queue = queues + warp * kScreenQueue;
   const int64_t n_tiles = (n + kScreenSites - 1) / kScreenSites;
   const bool tma_ok = (reinterpret_cast<uintptr_t>(counts) & 15) == 0;
   if (lane == 0) {
@@ -154,18 +154,19 @@ trio_screen_kernel(const unsigned char* __restrict__ counts, int64_t n, const Sc
       tma_bulk_g2s(my_tiles + buf * kTile, counts + t * kTile, kTile, &my_bars[buf]);
     }
   };
-  // level 2 on up to 32 parked sites; what it cannot decide goes to the FP64 kernel's list
+  // level 2 on up to 32 parked sites (their counts are re-read through L2, where the tile that
+  // just streamed in still sits); what it cannot decide goes to the FP64 kernel's list
   int qcount = 0;
   auto drain = [&](int take) {
     __syncwarp();
-    const int e = qcount - take + lane;
     bool fail = false;
     uint32_t site = 0;
     if (lane < take) {
+      site = my_queue[qcount - take + lane];
       uint32_t w[kWords];
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(counts + (size_t)site * kBps);
 #pragma unroll
-      for (int q = 0; q < kWords; q++) w[q] = my_queue[e * kEntry + q];
-      site = my_queue[e * kEntry + kWords];
+      for (int q = 0; q < kWords; q++) w[q] = __ldg(src + q);
       fail = !screen_site<kU8>(w, k);
     }
     const uint32_t fw = __ballot_sync(0xffffffffu, fail);
@@ -185,19 +186,19 @@ trio_screen_kernel(const unsigned char* __restrict__ counts, int64_t n, const Sc
   uint32_t phases = 0;
   int buf = 0;
   for (int64_t t = t0; t < n_tiles; t += warps_total, buf = (buf + 1) % kScreenBufs) {
-    uint32_t w[2][kWords];
+    uint32_t w[kScreenPerLane][kWords];
     const int64_t site0 = t * kScreenSites + lane;
     if (tma_ok && (t + 1) * kScreenSites <= n) {
       mbar_wait(&my_bars[buf], (phases >> buf) & 1u);
       phases ^= 1u << buf;
       const uint32_t* src = reinterpret_cast<const uint32_t*>(my_tiles + buf * kTile);
 #pragma unroll
-      for (int h = 0; h < 2; h++)
+      for (int h = 0; h < kScreenPerLane; h++)
 #pragma unroll
         for (int q = 0; q < kWords; q++) w[h][q] = src[(h * 32 + lane) * kWords + q];
     } else {
 #pragma unroll
-      for (int h = 0; h < 2; h++) {
+      for (int h = 0; h < kScreenPerLane; h++) {
         const int64_t site = site0 + h * 32;
 #pragma unroll
         for (int q = 0; q < kWords; q++)
@@ -207,17 +208,12 @@ trio_screen_kernel(const unsigned char* __restrict__ counts, int64_t n, const Sc
     __syncwarp();  // the buffer consumed in the previous trip may now be refilled
     issue(t + (kScreenBufs - 1) * warps_total, (buf + kScreenBufs - 1) % kScreenBufs);
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
+    for (int h = 0; h < kScreenPerLane; h++) {
       const int64_t site = site0 + h * 32;
       const bool park = site < n && !screen_level1<kU8>(w[h], k);
       const uint32_t pw = __ballot_sync(0xffffffffu, park);
       if (pw) {
-        if (park) {
-          const int e = qcount + __popc(pw & ((1u << lane) - 1));
-#pragma unroll
-          for (int q = 0; q < kWords; q++) my_queue[e * kEntry + q] = w[h][q];
-          my_queue[e * kEntry + kWords] = (uint32_t)site;
-        }
+        if (park) my_queue[qcount + __popc(pw & ((1u << lane) - 1))] = (uint32_t)site;
         qcount += __popc(pw);
         if (qcount >= 32) drain(32);
       }
@@ -232,7 +228,7 @@ static int launch_screen(dnv_ctx* ctx, const void* d_counts, int64_t n, const Sc
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
   constexpr int kTile = kScreenSites * (kU8 ? 12 : 24);
   const size_t smem = (size_t)kScreenWarps * kScreenBufs * kTile + kScreenWarps * kScreenBufs * 8 +
-                      (size_t)kScreenWarps * kScreenQueue * ((kU8 ? 3 : 6) + 1) * 4;
+                      (size_t)kScreenWarps * kScreenQueue * 4;
   auto kern = trio_screen_kernel<kU8>;
   DNV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
