@@ -30,8 +30,8 @@ DEPTH, EPS, MU, LRT = 30, 1e-2, 1e-8, 1.0
 BYTES_PER_SITE = 24.125
 FLOP_PER_SITE = 451.0
 # DRAM traffic of one screen launch over 10M sites from the ncu --set full capture committed as
-# profiles/r01_trio_screen_ncu.md (dram__bytes_read.sum + dram__bytes_write.sum), per site
-NCU_TRAFFIC_BYTES_PER_SITE = 24.46
+# profiles/r01_read_pipeline_ncu.md (dram__bytes_read.sum + dram__bytes_write.sum), per site
+NCU_TRAFFIC_BYTES_PER_SITE = 24.66
 
 
 def load_peaks():

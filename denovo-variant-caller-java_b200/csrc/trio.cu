@@ -243,17 +243,20 @@ int launch_trio_chunk(dnv_ctx* ctx, const void* d_counts, int64_t site_base, int
 
   const bool direct = (ctx->prm.flags & DNV_F_FORCE_DIRECT) != 0;
   const bool timed = (ctx->prm.flags & DNV_F_TIME_KERNELS) != 0 && ctx->n_timed < 64;
+  const bool screen = !direct && ctx->h_tab.early_ok && !d_dense && !(ctx->prm.flags & DNV_F_NO_SCREEN);
+  if (screen) {  // list-mode decision bits start from zero; the undecided-site counter too
+    DNV_CUDA(cudaMemsetAsync(ctx->d_bits, 0, (size_t)n_words * 4, st));
+    DNV_CUDA(cudaMemsetAsync(ctx->d_counters + 1, 0, sizeof(unsigned long long), st));
+  }
   if (timed) DNV_CUDA(cudaEventRecord(ctx->ev_k0[ctx->n_timed], st));
   if (direct) {
     const int64_t want = (n + kExactThreads - 1) / kExactThreads;
     const int grid = (int)(want < (int64_t)sms * 16 ? want : (int64_t)sms * 16);
     trio_direct_all_kernel<<<grid, kExactThreads, 0, st>>>(ctx->d_tab, d_counts, ctx->count_bytes, n, ctx->d_bits, d_dense,
                                                           ctx->d_counters);
-  } else if (ctx->h_tab.early_ok && !d_dense && !(ctx->prm.flags & DNV_F_NO_SCREEN)) {
+  } else if (screen) {
     // BAYES / LRT, calls only: exact integer screen at HBM speed, then the fused FP64 kernel on
     // the sites it could not decide
-    DNV_CUDA(cudaMemsetAsync(ctx->d_bits, 0, (size_t)n_words * 4, st));
-    DNV_CUDA(cudaMemsetAsync(ctx->d_counters + 1, 0, sizeof(unsigned long long), st));
     ScreenConsts sk;
     sk.c_hom = ctx->h_tab.c_hom_fx;
     sk.c_het = ctx->h_tab.c_het_fx;
