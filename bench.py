@@ -199,20 +199,39 @@ def main():
             print("symmetric memory unavailable (%r): falling back to the NCCL gather" % (e,), file=sys.stderr)
     calls_out = peer.records_ptr() if peer else d_calls
 
-    def gather_calls(n_calls):
-        """Call records + counts to rank 0 (the reference's shared PrintWriter, DenovoCaller.java:56-59)."""
-        if world == 1:
-            return n_calls
-        if peer:
-            peer.publish(n_calls)  # records + count now sit in rank 0's HBM; the host reads the counts once, after the loop
-            return n_calls
-        _, counts = sharding.gather_records(d_calls[:n_calls], dist)
-        return sum(counts)
+    # One step = one batch through the asynchronous device entry point (dnv_infer_counts_device_async):
+    # the whole pipeline is enqueued on `stream`, the batch's call count lands in a pinned host slot
+    # (N=1) or straight in rank 0's HBM next to the records (N>1), and the host only waits at the end
+    # (dnv_sync) — how a genome is walked chunk by chunk.  N>1 adds one signal-pad barrier per step.
+    torch.cuda.set_stream(stream)
+    h_nc = torch.zeros(64, dtype=torch.int64).pin_memory()
+    counts_ptr, calls_ptr = d_counts.data_ptr(), (calls_out if isinstance(calls_out, int) else calls_out.data_ptr())
+    nc_ptrs = [h_nc.data_ptr() + 8 * i for i in range(64)]
+    peer_nc = peer.count_ptr() if peer else None
 
-    def step():
-        with torch.cuda.stream(stream):
-            nc = eng.infer_device(d_counts, n, calls_out, cap)
-            return gather_calls(nc)
+    def run_steps(k_steps):
+        """k_steps pipelined steps; returns summed library stats."""
+        acc = {"fused_kernel_ms": 0.0, "screen_kernel_ms": 0.0, "n_launches": 0, "n_screened_out": 0, "n_hard": 0,
+               "n_calls": 0, "n_sites": 0}
+        done = 0
+        while done < k_steps:
+            m = min(32, k_steps - done)
+            if world > 1 and not peer:  # no symmetric memory: NCCL gather, needs the count on the host every step
+                m = 1
+                eng.infer_device_async(counts_ptr, n, calls_ptr, cap, nc_ptrs[0])
+                eng.sync()
+                sharding.gather_records(d_calls[:int(h_nc[0])], dist)
+            else:
+                for i in range(m):
+                    eng.infer_device_async(counts_ptr, n, calls_ptr, cap, peer_nc if peer else nc_ptrs[i])
+                    if peer:
+                        peer.barrier()  # records + count of every rank now sit in rank 0's HBM
+                eng.sync()
+            st = eng.stats()
+            for key in acc:
+                acc[key] += st[key]
+            done += m
+        return acc
 
     def barrier():
         torch.cuda.synchronize()
@@ -220,35 +239,41 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(W):
-        total_calls = step()
+    run_steps(W)
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    fused_ms, screen_ms, launches, screened_out = 0.0, 0.0, 0, 0
     e0.record(stream)
-    for _ in range(K):
-        total_calls = step()
-        st = eng.stats()
-        fused_ms += st["fused_kernel_ms"]
-        screen_ms += st["screen_kernel_ms"]
-        screened_out = st["n_screened_out"]
-        launches += st["n_launches"]
-    if peer and rank == 0:
-        with torch.cuda.stream(stream):
-            total_calls = sum(peer.counts())  # gathered counts of the last step, read on rank 0
+    acc = run_steps(K)
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
+    fused_ms, screen_ms, launches = acc["fused_kernel_ms"], acc["screen_kernel_ms"], acc["n_launches"]
+    screened_out = acc["n_screened_out"] // K
+    n_hard = acc["n_hard"] // K
+    if peer:
+        total_calls = sum(peer.counts()) if rank == 0 else 0
+    else:
+        total_calls = acc["n_calls"] // K
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     value = world * n * K / (ms_max * 1e-3)
-    n_hard = eng.stats()["n_hard"]
+
+    # the same step through the synchronous entry point (the host reads n_calls after every batch)
+    sync_ms = None
+    if world == 1:
+        for _ in range(3):
+            eng.infer_device(counts_ptr, n, calls_ptr, cap)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            eng.infer_device(counts_ptr, n, calls_ptr, cap)
+        sync_ms = (time.perf_counter() - t0) * 1e3 / K
 
     # ---- end to end through the host API: pinned host counts -> calls in pinned host memory
     # the host packs counts as uint8 (12 B/site) when every per-allele depth is below 256, else uint16
@@ -329,7 +354,9 @@ def main():
                                    % (args.method, n, "by peer stores over NVLink from the compaction kernel + one signal-pad "
                                       "barrier (no data collective)" if peer else ("with NCCL" if world > 1 else "(single GPU)")),
                        "sites_per_gpu": n, "l2": "input 240 MB per pass > 126 MB L2 (no flush needed)",
-                       "calls_per_step": int(total_calls), "hard_sites_last_step": int(n_hard)},
+                       "calls_per_step": int(total_calls), "hard_sites_per_step": int(n_hard),
+                       "step": "asynchronous batches (dnv_infer_counts_device_async), one dnv_sync per 32 steps",
+                       "ms_per_step_synchronous_api": sync_ms},
             "e2e": {"value": e2e_value, "unit": "sites/s", "h2d_bytes_per_step": n * (12 if u8 else 24),
                     "input_format": "uint8 counts, 12 B/site (dnv_infer_counts8)" if u8 else "uint16 counts, 24 B/site",
                     "d2h_bytes_per_step": int(e2e_calls) * D.CALL_DT.itemsize + 64, "steps": Ke,

@@ -103,6 +103,7 @@ int dnv_create(const dnv_params* p, dnv_ctx** out) {
   DNV_CUDA(cudaMemcpy(ctx->d_tab, &ctx->h_tab, sizeof(Tables), cudaMemcpyHostToDevice));
   DNV_CUDA(cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)));
   DNV_CUDA(cudaMemset(ctx->d_counters, 0, 8 * sizeof(unsigned long long)));
+  DNV_CUDA(cudaHostAlloc((void**)&ctx->h_ring, 64 * 8 * sizeof(unsigned long long), cudaHostAllocDefault));
   *out = ctx;
   return DNV_OK;
 }
@@ -122,6 +123,7 @@ int dnv_destroy(dnv_ctx* ctx) {
     for (int i = 0; i < 64; i++) { cudaEventDestroy(ctx->ev_k0[i]); cudaEventDestroy(ctx->ev_k1[i]); cudaEventDestroy(ctx->ev_s1[i]); }
   cudaStreamDestroy(ctx->own_stream);
   cudaStreamDestroy(ctx->copy_stream);
+  cudaFreeHost(ctx->h_ring);
   delete ctx;
   return DNV_OK;
 }
@@ -157,10 +159,7 @@ int dnv_get_stats(dnv_ctx* ctx, dnv_stats* out) {
   return DNV_OK;
 }
 
-static int finish_batch(dnv_ctx* ctx, int64_t n, int64_t cap, int64_t* n_calls) {
-  unsigned long long h[8];
-  DNV_CUDA(cudaMemcpyAsync(h, ctx->d_counters, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-  DNV_CUDA(cudaStreamSynchronize(ctx->stream));
+static void collect_kernel_times(dnv_ctx* ctx) {
   ctx->stats.fused_kernel_ms = 0;
   ctx->stats.screen_kernel_ms = 0;
   for (int i = 0; i < ctx->n_timed; i++) {
@@ -169,6 +168,13 @@ static int finish_batch(dnv_ctx* ctx, int64_t n, int64_t cap, int64_t* n_calls) 
     if (ctx->screened && cudaEventElapsedTime(&ms, ctx->ev_k0[i], ctx->ev_s1[i]) == cudaSuccess)
       ctx->stats.screen_kernel_ms += ms;
   }
+}
+
+static int finish_batch(dnv_ctx* ctx, int64_t n, int64_t cap, int64_t* n_calls) {
+  unsigned long long h[8];
+  DNV_CUDA(cudaMemcpyAsync(h, ctx->d_counters, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  DNV_CUDA(cudaStreamSynchronize(ctx->stream));
+  collect_kernel_times(ctx);
   ctx->stats.n_screened_out = ctx->screened ? n - (int64_t)h[1] : 0;
   ctx->stats.n_sites = n;
   const unsigned long long total = h[ctx->calls_slot];
@@ -182,6 +188,64 @@ static int finish_batch(dnv_ctx* ctx, int64_t n, int64_t cap, int64_t* n_calls) 
   return DNV_OK;
 }
 
+// batches enqueued by the async entry points must be collected before a synchronous call reuses the ctx
+static int drain_async(dnv_ctx* ctx) {
+  if (ctx->n_async == 0) return DNV_OK;
+  DNV_CUDA(cudaStreamSynchronize(ctx->stream));
+  collect_kernel_times(ctx);
+  int64_t calls = 0, hard = 0, undecided = 0;
+  for (int i = 0; i < ctx->n_async; i++) {
+    const unsigned long long* h = ctx->h_ring + i * 8;
+    calls += (int64_t)h[ctx->ring_slot[i]];
+    hard += (int64_t)h[4];
+    undecided += (int64_t)h[1];
+  }
+  ctx->stats.n_sites = ctx->async_sites;
+  ctx->stats.n_calls = calls;
+  ctx->stats.n_hard = hard;
+  ctx->stats.n_screened_out = ctx->screened ? ctx->async_sites - undecided : 0;
+  ctx->n_async = 0;
+  ctx->async_sites = 0;
+  return DNV_OK;
+}
+
+static int infer_device_async_impl(dnv_ctx* ctx, const void* d_counts, int bps, int64_t n, dnv_call* d_calls,
+                                   int64_t cap, int64_t* h_n_calls) {
+  if (!ctx || !h_n_calls || n < 0 || cap < 0 || (n > 0 && !d_counts) || (cap > 0 && !d_calls)) {
+    set_error("dnv_infer_counts_device_async: invalid argument");
+    return DNV_E_INVALID;
+  }
+  if (ctx->n_async >= 64) {
+    set_error("dnv_infer_counts_device_async: 64 batches in flight, call dnv_sync first");
+    return DNV_E_INVALID;
+  }
+  DNV_CUDA(cudaSetDevice(ctx->device));
+  if (ctx->n_async == 0) {
+    ctx->stats = dnv_stats();
+    ctx->n_timed = 0;
+    ctx->screened = false;
+    ctx->async_sites = 0;
+  }
+  ctx->calls_slot = 0;
+  ctx->count_bytes = bps;
+  DNV_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+  ctx->count_out = h_n_calls;
+  for (int64_t off = 0; off < n; off += kDeviceChunk) {
+    const int64_t m = std::min(kDeviceChunk, n - off);
+    int rc = launch_trio_chunk(ctx, (const unsigned char*)d_counts + off * bps, off, m, nullptr, d_calls, cap);
+    if (rc) { ctx->count_out = nullptr; return rc; }
+  }
+  ctx->count_out = nullptr;
+  if (n == 0)  // no kernel ran: the (zeroed) total still has to reach the caller's slot
+    DNV_CUDA(cudaMemcpyAsync(h_n_calls, ctx->d_counters, sizeof(int64_t), cudaMemcpyDefault, ctx->stream));
+  unsigned long long* ring = ctx->h_ring + ctx->n_async * 8;
+  DNV_CUDA(cudaMemcpyAsync(ring, ctx->d_counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->ring_slot[ctx->n_async] = ctx->calls_slot;
+  ctx->n_async++;
+  ctx->async_sites += n;
+  return DNV_OK;
+}
+
 static int infer_device_impl(dnv_ctx* ctx, const void* d_counts, int bps, int64_t n, dnv_site_result* d_dense,
                              dnv_call* d_calls, int64_t cap, int64_t* n_calls) {
   if (!ctx || !n_calls || n < 0 || cap < 0 || (n > 0 && !d_counts) || (cap > 0 && !d_calls)) {
@@ -189,6 +253,7 @@ static int infer_device_impl(dnv_ctx* ctx, const void* d_counts, int bps, int64_
     return DNV_E_INVALID;
   }
   DNV_CUDA(cudaSetDevice(ctx->device));
+  { int rc = drain_async(ctx); if (rc) return rc; }
   ctx->stats = dnv_stats();
   ctx->n_timed = 0;
   ctx->calls_slot = 0;
@@ -211,6 +276,7 @@ static int infer_host_impl(dnv_ctx* ctx, const void* counts, int bps, int64_t n,
     return DNV_E_INVALID;
   }
   DNV_CUDA(cudaSetDevice(ctx->device));
+  { int rc = drain_async(ctx); if (rc) return rc; }
   ctx->stats = dnv_stats();
   ctx->n_timed = 0;
   ctx->calls_slot = 0;
@@ -256,6 +322,20 @@ int dnv_infer_counts_device(dnv_ctx* ctx, const uint16_t* d_counts, int64_t n, d
 int dnv_infer_counts8_device(dnv_ctx* ctx, const uint8_t* d_counts8, int64_t n, dnv_site_result* d_dense,
                              dnv_call* d_calls, int64_t cap, int64_t* n_calls) {
   return infer_device_impl(ctx, d_counts8, 12, n, d_dense, d_calls, cap, n_calls);
+}
+int dnv_infer_counts_device_async(dnv_ctx* ctx, const uint16_t* d_counts, int64_t n, dnv_call* d_calls, int64_t cap,
+                                  int64_t* h_n_calls) {
+  return infer_device_async_impl(ctx, d_counts, 24, n, d_calls, cap, h_n_calls);
+}
+int dnv_infer_counts8_device_async(dnv_ctx* ctx, const uint8_t* d_counts8, int64_t n, dnv_call* d_calls, int64_t cap,
+                                   int64_t* h_n_calls) {
+  return infer_device_async_impl(ctx, d_counts8, 12, n, d_calls, cap, h_n_calls);
+}
+int dnv_sync(dnv_ctx* ctx) {
+  if (!ctx) { set_error("dnv_sync: null ctx"); return DNV_E_INVALID; }
+  DNV_CUDA(cudaSetDevice(ctx->device));
+  if (ctx->n_async == 0) { DNV_CUDA(cudaStreamSynchronize(ctx->stream)); return DNV_OK; }
+  return drain_async(ctx);
 }
 int dnv_infer_counts(dnv_ctx* ctx, const uint16_t* counts, int64_t n, dnv_site_result* dense, dnv_call* calls,
                      int64_t cap, int64_t* n_calls) {

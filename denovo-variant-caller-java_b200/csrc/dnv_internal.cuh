@@ -28,6 +28,7 @@ struct Tables {
   int32_t fast_ok;             // both ratios > 1 (always, unless eps is absurdly large)
   int32_t early_ok;            // the integer screen (trio_screen.cuh) is valid for these parameters
   uint32_t c_hom_fx, c_het_fx; // log2(r_j) in 16.16 fixed point
+  uint32_t scr_w[4];           // screen level 1: signed-byte weights (A,C,G,T) when allele X is the candidate
   double mm2;                  // log2(eps/3)
   double k_men;                // ((1-mu)/4)/64
   double k_den[4];             // (mu/256)/nDen for nDen = 9,8,7,6
@@ -75,6 +76,12 @@ struct dnv_ctx {
   void* d_scratch;
   size_t scratch_bytes;
   dnv_stats stats;
+  // asynchronous batches (dnv_infer_counts*_device_async): per-batch counters land in a pinned ring
+  unsigned long long* h_ring;  // [64][8]
+  int n_async;                 // batches enqueued since the last dnv_sync
+  int ring_slot[64];           // which counter slot holds each batch's call total
+  int64_t async_sites;
+  int64_t* count_out;          // where the details kernel stores the batch's call total (async batches), else null
 };
 
 #define DNV_CUDA(call)                                                        \

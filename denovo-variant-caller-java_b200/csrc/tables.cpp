@@ -102,7 +102,21 @@ void build_tables(const dnv_params& p, Tables* t) {
   const bool fits = log2r[0] < 60.0L && log2r[1] < 60.0L;
   t->c_hom_fx = fits ? (uint32_t)llroundl(log2r[0] * 65536.0L) : 0;
   t->c_het_fx = fits ? (uint32_t)llroundl(log2r[1] * 65536.0L) : 0;
-  t->early_ok = (t->fast_ok && fits && p.method != DNV_METHOD_MAP && thr_eff > 0.0 && std::isfinite(thr_eff) &&
+  // screen level 1: n_X * a >= (N - n_X) * h  must IMPLY  n_X * log2(r_hom) >= N * log2(r_het), i.e.
+  // a / h <= (log2 r_hom - log2 r_het) / log2 r_het; h = 127, a rounded down (signed bytes for dp2a / dp4a)
+  {
+    int a = 0;
+    if (log2r[1] > 0.0L && log2r[0] > log2r[1]) {
+      long double q = 127.0L * (log2r[0] - log2r[1]) / log2r[1] * (1.0L - 1e-12L);
+      a = q > 127.0L ? 127 : (int)floorl(q);
+    }
+    for (int x = 0; x < 4; x++) {
+      uint32_t w = 0;
+      for (int b = 0; b < 4; b++) w |= (uint32_t)(uint8_t)(int8_t)(b == x ? a : -127) << (8 * b);
+      t->scr_w[x] = w;
+    }
+  }
+  t->early_ok = (t->fast_ok && fits && log2r[0] > log2r[1] && p.method != DNV_METHOD_MAP && thr_eff > 0.0 && std::isfinite(thr_eff) &&
                  5334.0 * mu / (1.0 - mu) < 0.999 * thr_eff) ? 1 : 0;
   t->mm2 = (double)((logl(le) - logl(3.0L)) * l2e);
   t->k_men = (1.0 - mu) / 4 / 64;

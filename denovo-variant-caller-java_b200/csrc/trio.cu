@@ -143,9 +143,13 @@ constexpr int kDetailThreads = 64;
 __global__ void __launch_bounds__(kDetailThreads)
 call_details_kernel(const Tables* __restrict__ tab, const void* __restrict__ counts, int bps, int64_t site_base,
                     const int64_t* __restrict__ call_idx, const unsigned long long* __restrict__ counters,
-                    int in_slot, int out_slot, dnv_call* __restrict__ calls, int64_t cap, const FastConsts k) {
+                    int in_slot, int out_slot, dnv_call* __restrict__ calls, int64_t cap, const FastConsts k,
+                    int64_t* count_out) {
   const unsigned long long lo = counters[in_slot];
   unsigned long long hi = counters[out_slot];
+  // asynchronous batches: the running call total goes where the caller wants it (pinned host memory,
+  // or a peer GPU's HBM next to the records) — a plain store, ordered by the stream like the records
+  if (count_out && blockIdx.x == 0 && threadIdx.x == 0) *count_out = (int64_t)hi;
   if (hi > (unsigned long long)cap) hi = (unsigned long long)cap;
   if (lo + (unsigned long long)blockIdx.x * kDetailThreads >= hi) return;
   __shared__ double s_rel[1000];
@@ -260,6 +264,8 @@ int launch_trio_chunk(dnv_ctx* ctx, const void* d_counts, int64_t site_base, int
     ScreenConsts sk;
     sk.c_hom = ctx->h_tab.c_hom_fx;
     sk.c_het = ctx->h_tab.c_het_fx;
+    for (int x = 0; x < 4; x++) sk.w[x] = ctx->h_tab.scr_w[x];
+    sk.shift32 = 32;
     rc = ctx->count_bytes == 12 ? launch_screen<true>(ctx, d_counts, n, sk) : launch_screen<false>(ctx, d_counts, n, sk);
     if (rc) return rc;
     if (timed) DNV_CUDA(cudaEventRecord(ctx->ev_s1[ctx->n_timed], st));
@@ -278,7 +284,7 @@ int launch_trio_chunk(dnv_ctx* ctx, const void* d_counts, int64_t site_base, int
                                                             ctx->d_call_idx, ctx->call_idx_cap);
   call_details_kernel<<<sms * 4, kDetailThreads, 0, st>>>(ctx->d_tab, d_counts, ctx->count_bytes, site_base,
                                                          ctx->d_call_idx, ctx->d_counters, in_slot, out_slot, d_calls,
-                                                         cap, make_fast_consts(ctx->h_tab));
+                                                         cap, make_fast_consts(ctx->h_tab), ctx->count_out);
   ctx->calls_slot = out_slot;
   ctx->stats.n_launches += 3;
   DNV_CUDA(cudaGetLastError());

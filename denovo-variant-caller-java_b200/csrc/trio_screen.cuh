@@ -36,10 +36,12 @@ namespace dnv {
 
 constexpr int kScreenThreads = 256;
 constexpr int kScreenWarps = kScreenThreads / 32;
-constexpr int kScreenBufs = 3;  // tile buffers per warp: 2 tiles in flight ahead of the one being consumed
+constexpr int kScreenBufs = 2;  // tile buffers per warp, refilled as soon as their tile sits in registers
 
 struct ScreenConsts {
   uint32_t c_hom, c_het;  // log2(r_hom), log2(r_het) in 16.16 fixed point
+  uint32_t w[4];          // level 1 weights per candidate allele (Tables::scr_w)
+  uint32_t shift32;       // 32 (a run-time value the assembler cannot fold: x >> 32 == 0 orders the tile refill)
 };
 
 // One person: keys are (count << 2) | allele, so integer max/min order counts and carry the
@@ -84,142 +86,189 @@ __device__ __forceinline__ bool screen_site(const uint32_t* w, const ScreenConst
   return mendel && !((g[0] | g[1] | g[2]) & 256);
 }
 
-// level 1 (see the header): w = the site's packed count words
+// signed-byte dot products with unsigned counts (PTX dp4a / dp2a, SASS IDP): counts may use all 8 / 16 bits
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ int dp2a_lo_us(uint32_t a, uint32_t b, int c) {
+  int d;
+  asm("dp2a.lo.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ int dp2a_hi_us(uint32_t a, uint32_t b, int c) {
+  int d;
+  asm("dp2a.hi.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+// sum_b n_b * wt_b for one person (wt = four signed bytes A,C,G,T)
+template <bool kU8>
+__device__ __forceinline__ int screen_dot(const uint32_t* w, int p, uint32_t wt) {
+  if (kU8) return dp4a_us(w[p], wt, 0);
+  return dp2a_lo_us(w[2 * p], wt, dp2a_hi_us(w[2 * p + 1], wt, 0));
+}
+
+// level 1 (see the header): w = the site's packed count words.  The candidate X comes from two
+// sign tests on dad's pileup (G+T > A+C, C+T > A+G), which name the dominant allele whenever there
+// is one; the test itself is  n_X * a >= (N - n_X) * h  per person with signed-byte weights chosen on
+// the host so that it implies n_X * log2(r_hom) >= N * log2(r_het) (tables.cpp) — one dot-product
+// instruction per count word, no overflow at any depth.  Any X is sound: a wrong guess only parks the site.
 template <bool kU8>
 __device__ __forceinline__ bool screen_level1(const uint32_t* w, const ScreenConsts& k) {
-  // candidate X = dad's most frequent allele
-  int k0, k1, k2, k3;
-  if (kU8) {
-    const uint32_t v = w[0];
-    k0 = (int)((v & 0xFFu) << 2);
-    k1 = (int)(((v >> 6) & 0x3FCu) | 1u);
-    k2 = (int)(((v >> 14) & 0x3FCu) | 2u);
-    k3 = (int)(((v >> 22) & 0x3FCu) | 3u);
-  } else {
-    const uint32_t lo = w[0], hi = w[1];
-    k0 = (int)((lo & 0xFFFFu) << 2);
-    k1 = (int)(((lo >> 14) & 0x3FFFCu) | 1u);
-    k2 = (int)(((hi & 0xFFFFu) << 2) | 2u);
-    k3 = (int)(((hi >> 14) & 0x3FFFCu) | 3u);
-  }
-  const int x = max(max(k0, k1), max(k2, k3)) & 3;
-  bool ok = true;
-#pragma unroll
-  for (int p = 0; p < 3; p++) {
-    uint32_t nx, depth;
-    if (kU8) {
-      nx = (w[p] >> (8 * x)) & 0xFFu;
-      depth = __dp4a(w[p], 0x01010101u, 0u);
-    } else {
-      nx = ((x & 2 ? w[2 * p + 1] : w[2 * p]) >> (16 * (x & 1))) & 0xFFFFu;
-      depth = __dp2a_lo(w[2 * p], 0x0101u, __dp2a_lo(w[2 * p + 1], 0x0101u, 0u));
-    }
-    ok &= depth < (uint32_t)kPowTable && nx * k.c_hom >= depth * k.c_het;
-  }
-  return ok;
+  const bool hi2 = screen_dot<kU8>(w, 0, 0x0101FFFFu) > 0;  // -A -C +G +T
+  const bool odd = screen_dot<kU8>(w, 0, 0x01FF01FFu) > 0;  // -A +C -G +T
+  const uint32_t wlo = odd ? k.w[1] : k.w[0], whi = odd ? k.w[3] : k.w[2];
+  const uint32_t wt = hi2 ? whi : wlo;
+  const int s = screen_dot<kU8>(w, 0, wt) | screen_dot<kU8>(w, 1, wt) | screen_dot<kU8>(w, 2, wt);
+  return s >= 0;
 }
 
 // Each warp walks tiles of 128 sites (four per lane, 3072 / 1536 bytes); TMA bulk copies keep two
-// tiles in flight ahead of the one being consumed, in warp-private buffers.
+// tiles in flight ahead of the one being consumed, in warp-private buffers.  Level 2 is software
+// pipelined: the counts of 32 parked sites are requested (through L2, where the tile that just
+// streamed in still sits) one batch ahead of their evaluation, and the sites level 2 cannot
+// decide collect in a warp-private list that reaches global memory 32 at a time (one atomic each).
 constexpr int kScreenSites = 128;
 constexpr int kScreenPerLane = kScreenSites / 32;
 constexpr int kScreenQueue = 64;  // level-2 queue entries (site indices) per warp: at most 31 + 32 parked
+constexpr int kScreenFails = 64;  // undecided sites per warp waiting for their flush: at most 31 + 32
 
 template <bool kU8>
-__global__ void __launch_bounds__(kScreenThreads)
+__global__ void __launch_bounds__(kScreenThreads, 4)
 trio_screen_kernel(const unsigned char* __restrict__ counts, int64_t n, const ScreenConsts k,
                    uint32_t* __restrict__ list, unsigned long long* __restrict__ counters) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int kBps = kU8 ? 12 : 24;
   constexpr int kTile = kScreenSites * kBps;
   constexpr int kWords = kBps / 4;  // 32-bit words per site
+  constexpr uint32_t kFull = 0xffffffffu;
   unsigned char* tiles = smem_raw;  // [kScreenWarps][kScreenBufs][kTile]
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + kScreenWarps * kScreenBufs * kTile);
-  uint32_t* queues = reinterpret_cast<uint32_t*>(bars + kScreenWarps * kScreenBufs);  // [kScreenWarps][kScreenQueue]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t* queues = reinterpret_cast<uint32_t*>(bars + kScreenWarps * kScreenBufs);  // [kScreenWarps][queue | fails]
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
   unsigned char* my_tiles = tiles + (size_t)warp * kScreenBufs * kTile;
   unsigned long long* my_bars = bars + warp * kScreenBufs;
-  uint32_t* my_queue = queues + warp * kScreenQueue;
-  const int64_t n_tiles = (n + kScreenSites - 1) / kScreenSites;
-  const bool tma_ok = (reinterpret_cast<uintptr_t>(counts) & 15) == 0;
+  uint32_t* my_queue = queues + warp * (kScreenQueue + kScreenFails);
+  uint32_t* my_fails = my_queue + kScreenQueue;
+  // a chunk holds fewer than 2^31 sites (api.cu: kDeviceChunk), so tile and site indices fit 32 bits
+  const uint32_t n_sites = (uint32_t)n;
+  const uint32_t n_tiles = (n_sites + kScreenSites - 1) / kScreenSites;
+  const uint32_t n_full = (reinterpret_cast<uintptr_t>(counts) & 15) == 0 ? n_sites / kScreenSites : 0u;  // TMA-eligible tiles
   if (lane == 0) {
 #pragma unroll
     for (int b = 0; b < kScreenBufs; b++) mbar_init(&my_bars[b], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  auto issue = [&](int64_t t, int buf) {
-    if (lane == 0 && tma_ok && t < n_tiles && (t + 1) * kScreenSites <= n) {
+  auto issue = [&](uint32_t t, int buf) {
+    if (lane == 0 && t < n_full) {
       mbar_expect_tx(&my_bars[buf], kTile);
-      tma_bulk_g2s(my_tiles + buf * kTile, counts + t * kTile, kTile, &my_bars[buf]);
+      tma_bulk_g2s(my_tiles + buf * kTile, counts + (size_t)t * kTile, kTile, &my_bars[buf]);
     }
   };
-  // level 2 on up to 32 parked sites (their counts are re-read through L2, where the tile that
-  // just streamed in still sits); what it cannot decide goes to the FP64 kernel's list
-  int qcount = 0;
-  auto drain = [&](int take) {
-    __syncwarp();
-    bool fail = false;
-    uint32_t site = 0;
-    if (lane < take) {
-      site = my_queue[qcount - take + lane];
-      uint32_t w[kWords];
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(counts + (size_t)site * kBps);
+  int qcount = 0, fcount = 0, ptake = 0;  // warp-uniform: parked sites, undecided sites, sites of the batch in flight
+  uint32_t pw[kWords], psite = 0;         // the batch in flight: one parked site per lane
 #pragma unroll
-      for (int q = 0; q < kWords; q++) w[q] = __ldg(src + q);
-      fail = !screen_site<kU8>(w, k);
-    }
-    const uint32_t fw = __ballot_sync(0xffffffffu, fail);
+  for (int q = 0; q < kWords; q++) pw[q] = 0;
+  auto flush = [&](int take) {  // the newest `take` undecided sites -> the FP64 kernel's list
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&counters[1], (unsigned long long)take);
+    base = __shfl_sync(kFull, base, 0);
+    if ((int)lane < take) list[base + lane] = my_fails[fcount - take + lane];
+    fcount -= take;
+    __syncwarp();
+  };
+  auto evaluate = [&]() {  // level 2 on the batch in flight
+    const bool fail = (int)lane < ptake && !screen_site<kU8>(pw, k);
+    const uint32_t fw = __ballot_sync(kFull, fail);
+    ptake = 0;
     if (fw) {
-      unsigned long long base = 0;
-      if (lane == 0) base = atomicAdd(&counters[1], (unsigned long long)__popc(fw));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (fail) list[base + __popc(fw & ((1u << lane) - 1))] = site;
+      if (fail) my_fails[fcount + __popc(fw & lt_mask)] = psite;
+      fcount += __popc(fw);
+      __syncwarp();
+      if (fcount >= 32) flush(32);
     }
+  };
+  auto fetch = [&](int take) {  // request the counts of the newest `take` parked sites
+    __syncwarp();
+    if ((int)lane < take) {
+      psite = my_queue[qcount - take + lane];
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(counts + (size_t)psite * kBps);
+#pragma unroll
+      for (int q = 0; q < kWords; q++) pw[q] = __ldg(src + q);
+    }
+    ptake = take;
     qcount -= take;
     __syncwarp();
   };
-  const int64_t warps_total = (int64_t)gridDim.x * kScreenWarps;
-  const int64_t t0 = (int64_t)blockIdx.x * kScreenWarps + warp;
+  const uint32_t warps_total = gridDim.x * kScreenWarps;
+  const uint32_t t0 = blockIdx.x * kScreenWarps + warp;
 #pragma unroll
-  for (int b = 0; b < kScreenBufs - 1; b++) issue(t0 + b * warps_total, b);
+  for (int b = 0; b < kScreenBufs; b++) issue(t0 + b * warps_total, b);
   uint32_t phases = 0;
   int buf = 0;
-  for (int64_t t = t0; t < n_tiles; t += warps_total, buf = (buf + 1) % kScreenBufs) {
+  for (uint32_t t = t0; t < n_tiles; t += warps_total, buf = buf == kScreenBufs - 1 ? 0 : buf + 1) {
     uint32_t w[kScreenPerLane][kWords];
-    const int64_t site0 = t * kScreenSites + lane;
-    if (tma_ok && (t + 1) * kScreenSites <= n) {
+    const uint32_t site0 = t * kScreenSites + lane;
+    if (t < n_full) {
       mbar_wait(&my_bars[buf], (phases >> buf) & 1u);
       phases ^= 1u << buf;
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(my_tiles + buf * kTile);
+      if (kU8) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(my_tiles + buf * kTile);
 #pragma unroll
-      for (int h = 0; h < kScreenPerLane; h++)
+        for (int h = 0; h < kScreenPerLane; h++)
 #pragma unroll
-        for (int q = 0; q < kWords; q++) w[h][q] = src[(h * 32 + lane) * kWords + q];
+          for (int q = 0; q < kWords; q++) w[h][q] = src[(h * 32 + lane) * kWords + q];
+      } else {  // 24-byte sites: three conflict-free 64-bit loads
+        const uint2* src = reinterpret_cast<const uint2*>(my_tiles + buf * kTile);
+#pragma unroll
+        for (int h = 0; h < kScreenPerLane; h++)
+#pragma unroll
+          for (int q = 0; q < 3; q++) {
+            const uint2 v = src[(h * 32 + lane) * 3 + q];
+            w[h][2 * q] = v.x;
+            w[h][2 * q + 1] = v.y;
+          }
+      }
     } else {
 #pragma unroll
       for (int h = 0; h < kScreenPerLane; h++) {
-        const int64_t site = site0 + h * 32;
+        const uint32_t site = site0 + h * 32;
 #pragma unroll
         for (int q = 0; q < kWords; q++)
-          w[h][q] = site < n ? __ldg(reinterpret_cast<const uint32_t*>(counts + site * kBps) + q) : 0u;
+          w[h][q] = site < n_sites ? __ldg(reinterpret_cast<const uint32_t*>(counts + (size_t)site * kBps) + q) : 0u;
       }
     }
-    __syncwarp();  // the buffer consumed in the previous trip may now be refilled
-    issue(t + (kScreenBufs - 1) * warps_total, (buf + kScreenBufs - 1) % kScreenBufs);
+    // The tile now lives in registers: refill the SAME buffer at once, so kScreenBufs tiles per warp
+    // stay in flight.  The refill is made data-dependent on the last word read (shared-memory loads
+    // of a warp complete in order), so the bulk copy cannot overtake the reads it overwrites.
+    uint32_t fence_word;
+    asm volatile("shr.b32 %0, %1, %2;" : "=r"(fence_word) : "r"(w[kScreenPerLane - 1][kWords - 1]), "r"(k.shift32));  // == 0
+    __syncwarp();
+    issue(t + kScreenBufs * warps_total + fence_word, buf);
 #pragma unroll
     for (int h = 0; h < kScreenPerLane; h++) {
-      const int64_t site = site0 + h * 32;
-      const bool park = site < n && !screen_level1<kU8>(w[h], k);
-      const uint32_t pw = __ballot_sync(0xffffffffu, park);
-      if (pw) {
-        if (park) my_queue[qcount + __popc(pw & ((1u << lane) - 1))] = (uint32_t)site;
-        qcount += __popc(pw);
-        if (qcount >= 32) drain(32);
+      const uint32_t site = site0 + h * 32;
+      const bool park = site < n_sites && !screen_level1<kU8>(w[h], k);
+      const uint32_t pm = __ballot_sync(kFull, park);
+      if (pm) {
+        if (park) my_queue[qcount + __popc(pm & lt_mask)] = site;
+        qcount += __popc(pm);
+        if (qcount >= 32) {
+          if (ptake) evaluate();
+          fetch(32);
+        }
       }
     }
   }
-  if (qcount > 0) drain(qcount);
+  if (ptake) evaluate();
+  if (qcount > 0) {
+    fetch(qcount);
+    evaluate();
+  }
+  if (fcount > 0) flush(fcount);
 }
 
 template <bool kU8>
@@ -228,7 +277,7 @@ static int launch_screen(dnv_ctx* ctx, const void* d_counts, int64_t n, const Sc
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
   constexpr int kTile = kScreenSites * (kU8 ? 12 : 24);
   const size_t smem = (size_t)kScreenWarps * kScreenBufs * kTile + kScreenWarps * kScreenBufs * 8 +
-                      (size_t)kScreenWarps * kScreenQueue * 4;
+                      (size_t)kScreenWarps * (kScreenQueue + kScreenFails) * 4;
   auto kern = trio_screen_kernel<kU8>;
   DNV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;

@@ -114,6 +114,16 @@ class TrioEngine:
         L.check(fn(self._h, L.ptr(d_counts), n, L.ptr(d_dense), L.ptr(d_calls), cap, C.byref(nc)))
         return nc.value
 
+    def infer_device_async(self, d_counts, n, d_calls, cap, h_n_calls, u8=False):
+        """Enqueue one batch without waiting; h_n_calls = pinned host int64 slot (tensor / array / address)
+        that receives the batch's call count in stream order.  Pair with sync()."""
+        fn = self.lib.dnv_infer_counts8_device_async if u8 else self.lib.dnv_infer_counts_device_async
+        L.check(fn(self._h, L.ptr(d_counts), n, L.ptr(d_calls), cap, L.ptr(h_n_calls)))
+
+    def sync(self):
+        """Wait for every enqueued batch; stats() then holds the sums over those batches."""
+        L.check(self.lib.dnv_sync(self._h))
+
     def pileup(self, read_start, base_off, bases, person, site_pos):
         read_start = np.ascontiguousarray(read_start, np.int64)
         base_off = np.ascontiguousarray(base_off, np.int64)

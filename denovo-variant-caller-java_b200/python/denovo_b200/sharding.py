@@ -102,6 +102,14 @@ class PeerGather:
         """Device pointer (in rank dst's memory) where this rank's kernels write their dnv_call records."""
         return self.my_records_ptr
 
+    def count_ptr(self):
+        """Device pointer (in rank dst's memory) of this rank's int64 record count."""
+        return int(self.hdl.buffer_ptrs[self.dst]) + self.rank * self.slot
+
+    def barrier(self):
+        """Signal-pad barrier on the current stream: after it, every rank's stores have landed in dst."""
+        self.hdl.barrier()
+
     def publish(self, n_calls):
         """Call after the producing kernels were enqueued on the current stream."""
         self.my_header.fill_(int(n_calls))

@@ -181,6 +181,24 @@ int dnv_infer_counts_device(dnv_ctx *ctx, const uint16_t *d_counts, int64_t n,
                             dnv_site_result *d_dense, dnv_call *d_calls,
                             int64_t cap, int64_t *n_calls);
 
+/* Asynchronous form for streams of batches (a genome walked chunk by chunk, a candidate
+ * file read block by block): enqueues the whole pipeline on the ctx's stream and returns
+ * without waiting.  The number of calls of this batch is STORED BY THE LAST KERNEL into
+ * *n_calls_out, which must be device-writable: pinned host memory (cudaHostAlloc /
+ * cudaHostRegister, mapped under UVA), this GPU's memory, or a peer GPU's memory mapped
+ * here (the multi-GPU gather puts it next to the records in rank 0's HBM); call
+ * dnv_sync (or synchronise the stream) before reading it or d_calls.  Records beyond cap
+ * are not written (compare *n_calls_out with cap).  Scratch inside the ctx is reused in
+ * stream order, so batches may be enqueued back to back; each batch needs its own d_calls
+ * and n_calls_out if the results are to outlive the next batch.  dnv_get_stats after
+ * dnv_sync reports the sums over the batches enqueued since the previous dnv_sync
+ * (at most 64 batches between two dnv_sync calls). */
+int dnv_infer_counts_device_async(dnv_ctx *ctx, const uint16_t *d_counts, int64_t n,
+                                  dnv_call *d_calls, int64_t cap, int64_t *n_calls_out);
+int dnv_infer_counts8_device_async(dnv_ctx *ctx, const uint8_t *d_counts8, int64_t n,
+                                   dnv_call *d_calls, int64_t cap, int64_t *n_calls_out);
+int dnv_sync(dnv_ctx *ctx);
+
 /* Compact input variants: counts as uint8 [n][3][4] (12 bytes per site) for pileups whose
  * per-allele depth is below 256 — halves the host->device traffic that bounds the host path.
  * Same outputs (dnv_call.counts stays uint16). */

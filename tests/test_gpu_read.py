@@ -214,3 +214,35 @@ def test_uint8_compact_input_matches_uint16():
         c, _ = eng.infer(counts[:20000].astype(np.uint8))
         d, _ = eng.infer(counts[:20000])
     assert c.tobytes() == d.tobytes()
+
+
+@pytest.mark.parametrize("method", ["BAYES", "MAP"])
+def test_async_batches_match_synchronous_calls(method):
+    """dnv_infer_counts_device_async: several batches in flight on one ctx, each with its own
+    outputs, must give byte-identical records and counts to the synchronous entry point."""
+    import torch
+    sizes = [70_001, 0, 5, 200_000, 33]
+    with D.TrioEngine(method=method) as eng:
+        bufs, want = [], []
+        for i, n in enumerate(sizes):
+            c = torch.empty((max(n, 1), 12), dtype=torch.int16, device="cuda")
+            if n:
+                eng.synth_counts_device(0x5EED0003, 1000 * i, n, c, depth=30)
+            bufs.append(c)
+            calls = torch.zeros((max(n, 1), D.CALL_DT.itemsize), dtype=torch.uint8, device="cuda")
+            k = eng.infer_device(c, n, calls, max(n, 1))
+            want.append(calls[:k].cpu().numpy().tobytes())
+        h_nc = torch.full((len(sizes),), -1, dtype=torch.int64).pin_memory()
+        outs = [torch.zeros((max(n, 1), D.CALL_DT.itemsize), dtype=torch.uint8, device="cuda") for n in sizes]
+        for i, n in enumerate(sizes):
+            eng.infer_device_async(bufs[i], n, outs[i], max(n, 1), h_nc.data_ptr() + 8 * i)
+        eng.sync()
+        st = eng.stats()
+        got_counts = h_nc.tolist()
+        for i, n in enumerate(sizes):
+            assert outs[i][:got_counts[i]].cpu().numpy().tobytes() == want[i], (i, n)
+        assert st["n_sites"] == sum(sizes) and st["n_calls"] == sum(got_counts) and sum(got_counts) > 100
+        # the ctx goes back to synchronous use without an explicit sync in between
+        eng.infer_device_async(bufs[3], sizes[3], outs[3], sizes[3], h_nc.data_ptr())
+        k = eng.infer_device(bufs[0], sizes[0], outs[0], sizes[0])
+        assert outs[0][:k].cpu().numpy().tobytes() == want[0]
