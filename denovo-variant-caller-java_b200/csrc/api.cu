@@ -103,6 +103,7 @@ int dnv_create(const dnv_params* p, dnv_ctx** out) {
   DNV_CUDA(cudaMemcpy(ctx->d_tab, &ctx->h_tab, sizeof(Tables), cudaMemcpyHostToDevice));
   DNV_CUDA(cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)));
   DNV_CUDA(cudaMemset(ctx->d_counters, 0, 8 * sizeof(unsigned long long)));
+  DNV_CUDA(cudaMalloc(&ctx->d_wcount, 8192 * sizeof(uint32_t)));
   DNV_CUDA(cudaHostAlloc((void**)&ctx->h_ring, 64 * 8 * sizeof(unsigned long long), cudaHostAllocDefault));
   *out = ctx;
   return DNV_OK;
@@ -114,7 +115,7 @@ int dnv_destroy(dnv_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->copy_stream);
   cudaFree(ctx->d_tab); cudaFree(ctx->d_bits); cudaFree(ctx->d_tile_status); cudaFree(ctx->d_list);
-  cudaFree(ctx->d_call_idx); cudaFree(ctx->d_counters); cudaFree(ctx->d_stage_calls); cudaFree(ctx->d_scratch);
+  cudaFree(ctx->d_call_idx); cudaFree(ctx->d_counters); cudaFree(ctx->d_wcount); cudaFree(ctx->d_stage_calls); cudaFree(ctx->d_scratch);
   for (int i = 0; i < 2; i++) {
     cudaFree(ctx->d_stage_counts[i]); cudaFree(ctx->d_stage_dense[i]);
     cudaEventDestroy(ctx->ev_h2d[i]); cudaEventDestroy(ctx->ev_done[i]);

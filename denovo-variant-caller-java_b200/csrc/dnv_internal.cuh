@@ -57,7 +57,8 @@ struct dnv_ctx {
   // per-chunk scratch (sized for chunk_cap sites)
   int64_t chunk_cap;
   uint32_t* d_bits;        // decision bit per site
-  uint32_t* d_list;        // sites the integer screen could not decide (chunk-relative)
+  uint32_t* d_list;        // sites the integer screen could not decide (chunk-relative), per-warp sorted segments
+  uint32_t* d_wcount;      // length of every screen warp's segment of d_list
   bool screened;           // the last call used the screen
   unsigned long long* d_tile_status;  // decoupled look-back status per compaction block
   unsigned long long epoch;           // launch counter tagging d_tile_status entries

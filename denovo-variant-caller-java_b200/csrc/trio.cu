@@ -20,6 +20,7 @@
 #include "scan_util.cuh"
 #include "trio_exact.cuh"
 #include "trio_fast.cuh"
+#include "trio_list.cuh"
 #include "trio_screen.cuh"
 
 namespace dnv {
@@ -211,11 +212,17 @@ int ensure_chunk_scratch(dnv_ctx* ctx, int64_t n) {
   ctx->d_bits = nullptr; ctx->d_tile_status = nullptr; ctx->d_list = nullptr;
   ctx->chunk_cap = 0;
   const int64_t n_words = (n + 31) / 32;
-  const int64_t n_blocks = (n_words + kCompactThreads - 1) / kCompactThreads;
+  // look-back status: one entry per compaction block (256 bit-words) or per list tile (128 undecided sites)
+  const int64_t n_status = std::max((n_words + kCompactThreads - 1) / kCompactThreads, (n + kListThreads - 1) / kListThreads) + 1;
   DNV_CUDA(cudaMalloc(&ctx->d_bits, (size_t)(n_words + 1) * 4));
-  DNV_CUDA(cudaMalloc(&ctx->d_tile_status, (size_t)(n_blocks + 1) * 8));
-  DNV_CUDA(cudaMalloc(&ctx->d_list, (size_t)n * 4));
-  DNV_CUDA(cudaMemsetAsync(ctx->d_tile_status, 0, (size_t)(n_blocks + 1) * 8, ctx->stream));
+#ifdef DNV_LIST_TRACE
+  const int64_t n_status_alloc = (1 << 20) + 8 * 8192;  // room for the per-CTA time stamps of trio_list_kernel
+#else
+  const int64_t n_status_alloc = n_status;
+#endif
+  DNV_CUDA(cudaMalloc(&ctx->d_tile_status, (size_t)n_status_alloc * 8));
+  DNV_CUDA(cudaMalloc(&ctx->d_list, ((size_t)n + kScreenSites) * 4));
+  DNV_CUDA(cudaMemsetAsync(ctx->d_tile_status, 0, (size_t)n_status * 8, ctx->stream));
   ctx->chunk_cap = n;
   return DNV_OK;
 }
@@ -248,10 +255,6 @@ int launch_trio_chunk(dnv_ctx* ctx, const void* d_counts, int64_t site_base, int
   const bool direct = (ctx->prm.flags & DNV_F_FORCE_DIRECT) != 0;
   const bool timed = (ctx->prm.flags & DNV_F_TIME_KERNELS) != 0 && ctx->n_timed < 64;
   const bool screen = !direct && ctx->h_tab.early_ok && !d_dense && !(ctx->prm.flags & DNV_F_NO_SCREEN);
-  if (screen) {  // list-mode decision bits start from zero; the undecided-site counter too
-    DNV_CUDA(cudaMemsetAsync(ctx->d_bits, 0, (size_t)n_words * 4, st));
-    DNV_CUDA(cudaMemsetAsync(ctx->d_counters + 1, 0, sizeof(unsigned long long), st));
-  }
   if (timed) DNV_CUDA(cudaEventRecord(ctx->ev_k0[ctx->n_timed], st));
   if (direct) {
     const int64_t want = (n + kExactThreads - 1) / kExactThreads;
@@ -259,20 +262,27 @@ int launch_trio_chunk(dnv_ctx* ctx, const void* d_counts, int64_t site_base, int
     trio_direct_all_kernel<<<grid, kExactThreads, 0, st>>>(ctx->d_tab, d_counts, ctx->count_bytes, n, ctx->d_bits, d_dense,
                                                           ctx->d_counters);
   } else if (screen) {
-    // BAYES / LRT, calls only: exact integer screen at HBM speed, then the fused FP64 kernel on
-    // the sites it could not decide
+    // BAYES / LRT, calls only: exact integer screen at HBM speed, then ONE kernel for the sites it could
+    // not decide (fused FP64 posterior, ordered compaction, call records)
     ScreenConsts sk;
     sk.c_hom = ctx->h_tab.c_hom_fx;
     sk.c_het = ctx->h_tab.c_het_fx;
     for (int x = 0; x < 4; x++) sk.w[x] = ctx->h_tab.scr_w[x];
     sk.shift32 = 32;
-    rc = ctx->count_bytes == 12 ? launch_screen<true>(ctx, d_counts, n, sk) : launch_screen<false>(ctx, d_counts, n, sk);
+    const bool u8 = ctx->count_bytes == 12;
+    int sgrid = 0;
+    rc = u8 ? launch_screen<true>(ctx, d_counts, n, sk, &sgrid) : launch_screen<false>(ctx, d_counts, n, sk, &sgrid);
     if (rc) return rc;
     if (timed) DNV_CUDA(cudaEventRecord(ctx->ev_s1[ctx->n_timed], st));
-    rc = launch_trio_fast(ctx, d_counts, n, nullptr, ctx->d_list);
+    const int in_slot = ctx->calls_slot, out_slot = in_slot == 0 ? 3 : 0;
+    rc = u8 ? launch_trio_list<true>(ctx, d_counts, n, site_base, sgrid, in_slot, out_slot, d_calls, cap)
+            : launch_trio_list<false>(ctx, d_counts, n, site_base, sgrid, in_slot, out_slot, d_calls, cap);
     if (rc) return rc;
-    ctx->stats.n_launches += 1;
+    if (timed) DNV_CUDA(cudaEventRecord(ctx->ev_k1[ctx->n_timed++], st));
+    ctx->calls_slot = out_slot;
+    ctx->stats.n_launches += 2;
     ctx->screened = true;
+    return DNV_OK;
   } else {
     rc = launch_trio_fast(ctx, d_counts, n, d_dense);
     if (rc) return rc;
@@ -292,3 +302,9 @@ int launch_trio_chunk(dnv_ctx* ctx, const void* d_counts, int64_t site_base, int
 }
 
 }  // namespace dnv
+
+#ifdef DNV_LIST_TRACE
+extern "C" int dnv_debug_list_trace(dnv_ctx* ctx, unsigned long long* out, int n_ctas) {
+  return cudaMemcpy(out, ctx->d_tile_status + (1 << 20), (size_t)n_ctas * 64, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+}
+#endif

@@ -1,0 +1,349 @@
+// trio_list.cuh — the tail of the screened READ pipeline in ONE kernel.
+//
+// Input: the sites the integer screen (trio_screen.cuh) could not decide, as per-warp sorted
+// segments of `list` plus their lengths wcount[] — concatenated in warp order they are the
+// undecided sites in ascending order (about 1 % of all sites).  For every such site:
+//   1. the fused likelihood + posterior in the factored linear form (trio_fast.cuh:
+//      linear_site; power tables read through L1 — with ~2 sites per thread, staging them in
+//      shared memory would cost more than it saves); hard sites (threshold-ambiguous,
+//      underflow gray zone, deeper than the tables) are re-evaluated by the whole warp with
+//      the exact direct form (trio_exact.cuh: exact_site_warp);
+//   2. an order-preserving compaction of the called sites across the grid (tiles of 128 list
+//      items handed out by ticket, decoupled look-back over the tile totals), so that the
+//      thread that decided a site writes its dnv_call record straight to its final,
+//      input-ordered position: site, counts, p / LR / log-likelihoods from the linear form
+//      (everything, from the exact evaluation, for hard sites);
+//   3. after a grid-wide barrier (cooperative launch: every CTA is resident), ONE THREAD PER
+//      CALL completes the record with the exact pruned log-domain sweep (MAP triple, max_ll).
+//      Called sites are ~1 in 5 of the list, so doing this densely instead of inside the
+//      divergent decision loop takes the sweep off every warp's critical path.
+// No decision bitmap, no separate compaction or record kernels, no sort.
+//
+// Replaces, for the ~1 % of sites that need it, BayesInfer.infer -> performInference ->
+// isDenovo (M/BayesInfer.java:50-69, M/DenovoBayesNet.java:247-289, M/DenovoUtil.java:261-288)
+// and the `if (result.isDenovo()) writeCalls(...)` of M/ReadCaller.java:122-129.
+#pragma once
+#include "dnv_internal.cuh"
+#include "trio_exact.cuh"
+#include "trio_fast.cuh"
+#include "trio_screen.cuh"
+
+namespace dnv {
+
+constexpr int kListThreads = 128;
+constexpr int kListWarps = kListThreads / 32;
+
+struct ListShared {
+  double rel[1000];               // exact path: getRelationshipLogLikelihood
+  double rmax[110];               // exact MAP pruning bounds
+  double warp_L[kListWarps][32];  // exact path: per-warp read log-likelihoods
+  uint32_t isden[32];             // exact path: isDenovoMap
+  uint32_t woff[kScreenMaxWarps + 1];  // exclusive scan of wcount[]
+  uint32_t part[kListWarps];
+  int warp_sum[kListWarps];
+  unsigned long long excl;
+};
+
+// counters: [in_slot] calls before this chunk, [out_slot] <- calls after it, [1] <- undecided sites,
+//           [4] += hard sites, [7] barrier arrivals, [5] CTAs gone (the last CTA to leave resets
+//           both for the next launch).
+// status word: [63:34] epoch of this launch, [33:32] 1 = tile aggregate, 2 = inclusive prefix, [31:0] value.
+template <bool kU8>
+__global__ void __launch_bounds__(kListThreads, 3)
+trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsigned char* __restrict__ counts,
+                 int64_t n, int64_t site_base, const uint32_t* __restrict__ list, const uint32_t* __restrict__ wcount,
+                 uint32_t n_warps, uint32_t range_base, uint32_t range_rem, unsigned long long* status,
+                 unsigned long long epoch, unsigned long long* counters, int in_slot, int out_slot,
+                 dnv_call* __restrict__ calls, int64_t cap, int64_t* count_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ListShared& s = *reinterpret_cast<ListShared*>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kBps = kU8 ? 12 : 24;
+#ifdef DNV_LIST_TRACE
+  unsigned long long* trace = status + (1 << 20) + blockIdx.x * 8;
+  auto stamp = [&](int i) { if (threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace[i] = t; } };
+#else
+  auto stamp = [&](int) {};
+#endif
+  stamp(0);
+
+  // Prologue: every global load is issued before the first one is consumed (one round trip, not a
+  // dependent chain): wcount[] (coalesced, kScreenMaxWarps / kListThreads words per thread) and this
+  // thread's slice of the exact tables; then the block-wide scan of wcount[] in shared memory.
+  constexpr int kWLoads = kScreenMaxWarps / kListThreads;
+  uint32_t wv[kWLoads];
+#pragma unroll
+  for (int i = 0; i < kWLoads; i++) {
+    const uint32_t j = i * kListThreads + threadIdx.x;
+    wv[i] = j < n_warps ? __ldg(wcount + j) : 0u;
+  }
+  double2 relv[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int j = threadIdx.x + i * kListThreads;  // 500 double2 = rel[1000]
+    relv[i] = j < 500 ? __ldg(reinterpret_cast<const double2*>(tab->rel) + j) : make_double2(0.0, 0.0);
+  }
+  const double rmaxv = threadIdx.x < 110 ? (threadIdx.x < 100 ? tab->rmax_dm[threadIdx.x] : tab->rmax_d[threadIdx.x - 100]) : 0.0;
+  const uint32_t isdenv = threadIdx.x < 32 ? tab->isden[threadIdx.x] : 0u;
+#pragma unroll
+  for (int i = 0; i < kWLoads; i++) {
+    const uint32_t j = i * kListThreads + threadIdx.x;
+    if (j < n_warps) s.woff[j] = wv[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int j = threadIdx.x + i * kListThreads;
+    if (j < 500) reinterpret_cast<double2*>(s.rel)[j] = relv[i];
+  }
+  if (threadIdx.x < 110) s.rmax[threadIdx.x] = rmaxv;
+  if (threadIdx.x < 32) s.isden[threadIdx.x] = isdenv;
+  __syncthreads();
+  // one contiguous run of `per` entries per thread (odd or not, scalar accesses at stride `per` words
+  // spread over the banks well enough), block-wide exclusive scan of the run sums by shuffles
+  const uint32_t per = (n_warps + kListThreads - 1) / kListThreads;
+  const uint32_t lo = min(threadIdx.x * per, n_warps), hi = min(lo + per, n_warps);
+  uint32_t sum = 0;
+  for (uint32_t i = lo; i < hi; i++) sum += s.woff[i];
+  uint32_t incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  if (lane == 31) s.part[warp] = incl;
+  __syncthreads();
+  uint32_t before = incl - sum, total_items = 0;
+#pragma unroll
+  for (int i = 0; i < kListWarps; i++) {
+    const uint32_t v = s.part[i];
+    if (i < warp) before += v;
+    total_items += v;
+  }
+  for (uint32_t i = lo; i < hi; i++) {
+    const uint32_t v = s.woff[i];
+    s.woff[i] = before;
+    before += v;
+  }
+  if (threadIdx.x == 0) s.woff[n_warps] = total_items;
+  __syncthreads();
+
+  const uint32_t n_tiles = (total_items + kListThreads - 1) / kListThreads;
+  const unsigned long long calls_before = counters[in_slot];
+  const unsigned long long tag = epoch << 34;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    counters[1] = total_items;
+    if (n_tiles == 0) {  // nothing undecided: the call total carries over
+      counters[out_slot] = calls_before;
+      if (count_out) *count_out = (int64_t)calls_before;
+    }
+  }
+  const GmemPow pw{tab};
+  stamp(1);
+
+  // Tiles are dealt statically (tile = blockIdx.x + trip * gridDim.x): every CTA is resident (cooperative
+  // launch), so the look-back below always finds its predecessors running.  The inputs of the next
+  // trip (list entry -> site -> packed counts, two dependent global loads) are requested before this
+  // trip's arithmetic starts.
+  auto fetch_site = [&](uint32_t tile) -> uint32_t {
+    const uint32_t item = tile * kListThreads + threadIdx.x;
+    if (tile >= n_tiles || item >= total_items) return 0u;  // dead lanes read site 0 (harmless) and are masked by `live`
+    uint32_t a = 0, b = n_warps;  // largest g with woff[g] <= item
+    while (b - a > 1) {
+      const uint32_t mid = (a + b) >> 1;
+      if (s.woff[mid] <= item) a = mid; else b = mid;
+    }
+    return __ldg(list + (size_t)screen_range_lo(a, range_base, range_rem) * kScreenSites + (item - s.woff[a]));
+  };
+  auto fetch_counts = [&](uint32_t site, uint32_t* words) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(counts + (size_t)site * kBps);
+#pragma unroll
+    for (int q = 0; q < kBps / 4; q++) words[q] = __ldg(src + q);
+  };
+  // two-deep software pipeline: list entries are requested two trips ahead, packed counts one trip ahead
+  uint32_t site_cur = fetch_site(blockIdx.x), site_nxt = fetch_site(blockIdx.x + gridDim.x);
+  uint32_t words_cur[kBps / 4];
+  fetch_counts(site_cur, words_cur);
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t item = tile * kListThreads + threadIdx.x;
+    const bool live = item < total_items;
+    const uint32_t site = site_cur;
+    int c[12];
+    if (kU8) unpack_counts8(words_cur, c);
+    else unpack_counts(reinterpret_cast<const uint2*>(words_cur), c);
+    site_cur = site_nxt;
+    site_nxt = fetch_site(tile + 2 * gridDim.x);
+    fetch_counts(site_cur, words_cur);
+    LinOut lo_;
+    lo_.hard = false; lo_.dn = false; lo_.zd = lo_.zm = 2; lo_.den_s = lo_.men_s = lo_.s2 = 0.0;
+    if (live) {
+      if (k.lin_ok) linear_site(pw, c, k.k_men, k.kd9, k.kd8, k.kd7, k.kd6, k.thr, k.mm2, k.method, k.lrt_threshold, lo_);
+      else lo_.hard = true;  // eps so large that r <= 1: the table scheme does not apply
+    }
+    bool dn = lo_.dn;
+    // hard sites: the whole warp evaluates them one at a time with the exact direct form
+    ExactOut ex;
+    ex.is_denovo = false;
+    uint32_t hword = __ballot_sync(0xffffffffu, lo_.hard);
+    if (hword) {
+      if (lane == 0) atomicAdd(&counters[4], (unsigned long long)__popc(hword));
+      while (hword) {
+        const int h = __ffs(hword) - 1;
+        hword &= hword - 1;
+        uint16_t cu[12];
+#pragma unroll
+        for (int q = 0; q < 12; q++) cu[q] = (uint16_t)__shfl_sync(0xffffffffu, c[q], h);
+        ExactOut r;
+        exact_site_warp(cu, s.rel, s.isden, s.warp_L[warp], k.hm, k.ht, k.mm, k.method, k.lrt_threshold, &r);
+        if (lane == h) { ex = r; dn = r.is_denovo; }
+      }
+    }
+    if (tile == blockIdx.x) stamp(2);
+    // order-preserving rank of the called sites inside the tile
+    const uint32_t dw = __ballot_sync(0xffffffffu, dn);
+    __syncthreads();  // s.warp_sum / s.excl of the previous trip are no longer read
+    if (lane == 0) s.warp_sum[warp] = __popc(dw);
+    __syncthreads();
+    int warp_off = 0, total = 0;
+#pragma unroll
+    for (int i = 0; i < kListWarps; i++) {
+      if (i < warp) warp_off += s.warp_sum[i];
+      total += s.warp_sum[i];
+    }
+    if (warp == 0) {  // warp-parallel decoupled look-back: 32 predecessor tiles per probe
+      unsigned long long excl = 0;
+      if (tile > 0) {
+        if (lane == 0) atomicExch(&status[tile], tag | (1ull << 32) | (unsigned long long)total);
+        int hi_t = (int)tile - 1;
+        for (;;) {
+          const int p = hi_t - lane;
+          unsigned long long v = tag | (2ull << 32);  // lanes before tile 0 act as an empty inclusive prefix
+          if (p >= 0) {
+            do { v = *(volatile unsigned long long*)&status[p]; } while ((v >> 34) != epoch);
+          }
+          const uint32_t is_prefix = __ballot_sync(0xffffffffu, ((v >> 32) & 3ull) == 2ull);
+          const int stop = is_prefix ? __ffs(is_prefix) - 1 : 31;  // nearest inclusive prefix in this window
+          unsigned long long val = lane <= stop ? (v & 0xffffffffull) : 0ull;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+          excl += val;
+          if (is_prefix) break;
+          hi_t -= 32;
+        }
+      }
+      if (lane == 0) {
+        atomicExch(&status[tile], tag | (2ull << 32) | (excl + (unsigned long long)total));
+        s.excl = excl;
+        if (tile == n_tiles - 1) {
+          const unsigned long long all = calls_before + excl + (unsigned long long)total;
+          counters[out_slot] = all;
+          if (count_out) *count_out = (int64_t)all;
+        }
+      }
+    }
+    if (total == 0) continue;  // block-uniform
+    __syncthreads();
+    if (dn) {
+      const unsigned long long pos = calls_before + s.excl + (unsigned long long)(warp_off + __popc(dw & ((1u << lane) - 1u)));
+      if (pos < (unsigned long long)cap) {
+        dnv_call o;
+        if (lo_.hard) {
+          o.dad = (uint8_t)ex.dad; o.mom = (uint8_t)ex.mom; o.child = (uint8_t)ex.child;
+          o.max_ll = ex.max_ll; o.p = ex.p; o.lr = ex.lr; o.log_men = ex.log_men; o.log_den = ex.log_den;
+          o.flags = 1;
+        } else {  // phase 2 fills in the MAP triple and max_ll
+          o.dad = o.mom = o.child = 0;
+          o.max_ll = 0.0;
+          linear_values(lo_, o.p, o.lr, o.log_men, o.log_den);
+          o.flags = 0;
+        }
+        o.site = site_base + (int64_t)site;
+#pragma unroll
+        for (int q = 0; q < 12; q++) o.counts[q] = (uint16_t)c[q];
+        o.is_denovo = 1;
+        calls[pos] = o;
+      }
+    }
+  }
+
+  // ---- grid-wide barrier: every record of phase 1 and the call total are now in global memory
+  __syncthreads();
+  stamp(3);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(&counters[7], 1ull);
+    while (*(volatile unsigned long long*)&counters[7] < (unsigned long long)gridDim.x) {}
+    __threadfence();
+  }
+  __syncthreads();
+
+  stamp(4);
+  // ---- phase 2: one thread per call, exact pruned MAP sweep (bit-identical to the reference's argmax)
+  {
+    unsigned long long all = *(volatile unsigned long long*)&counters[out_slot];
+    if (all > (unsigned long long)cap) all = (unsigned long long)cap;
+    // call j goes to CTA j % gridDim.x: every SM gets the same share of the sweep
+    for (unsigned long long pos = calls_before + (unsigned long long)threadIdx.x * gridDim.x + blockIdx.x; pos < all;
+         pos += (unsigned long long)gridDim.x * kListThreads) {
+      dnv_call* rec = calls + pos;
+      if (__ldcg(&rec->flags) & 1u) continue;  // hard site: complete already
+      const uint2* cw = reinterpret_cast<const uint2*>(rec->counts);
+      uint16_t cu[12];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        const uint2 v = __ldcg(cw + i);
+        cu[4 * i + 0] = (uint16_t)(v.x & 0xFFFF); cu[4 * i + 1] = (uint16_t)(v.x >> 16);
+        cu[4 * i + 2] = (uint16_t)(v.y & 0xFFFF); cu[4 * i + 3] = (uint16_t)(v.y >> 16);
+      }
+      double Ld[10], Lm[10], Lc[10];
+      exact_read_loglik(cu + 0, k.hm, k.ht, k.mm, Ld);
+      exact_read_loglik(cu + 4, k.hm, k.ht, k.mm, Lm);
+      exact_read_loglik(cu + 8, k.hm, k.ht, k.mm, Lc);
+      int best;
+      double max_ll;
+      exact_map_pruned(Ld, Lm, Lc, s.rel, s.rmax, &best, &max_ll);
+      rec->dad = (uint8_t)(best / 100); rec->mom = (uint8_t)((best / 10) % 10); rec->child = (uint8_t)(best % 10);
+      rec->max_ll = max_ll;
+    }
+  }
+  __syncthreads();
+  stamp(5);
+  // the last CTA to leave resets the barrier for the next launch
+  if (threadIdx.x == 0) {
+    if (atomicAdd(&counters[5], 1ull) == (unsigned long long)gridDim.x - 1ull) {
+      counters[5] = 0;
+      counters[7] = 0;
+    }
+  }
+}
+
+template <bool kU8>
+static int launch_trio_list(dnv_ctx* ctx, const void* d_counts, int64_t n, int64_t site_base, int screen_grid_size,
+                            int in_slot, int out_slot, dnv_call* d_calls, int64_t cap) {
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  const size_t smem = sizeof(ListShared);
+  auto kern = trio_list_kernel<kU8>;
+  DNV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;
+  DNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kListThreads, smem));
+  if (per_sm < 1) per_sm = 1;
+  const int64_t want = (n + kListThreads - 1) / kListThreads;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sms * per_sm));
+  const uint32_t n_tiles = (uint32_t)((n + kScreenSites - 1) / kScreenSites);
+  const uint32_t n_warps = (uint32_t)screen_grid_size * kScreenWarps;
+  // cooperative launch: the in-kernel barrier needs every CTA resident (grid <= sms * per_sm by construction)
+  const Tables* a_tab = ctx->d_tab;
+  FastConsts a_k = make_fast_consts(ctx->h_tab);
+  const unsigned char* a_counts = (const unsigned char*)d_counts;
+  const uint32_t* a_list = ctx->d_list;
+  const uint32_t* a_wcount = ctx->d_wcount;
+  uint32_t a_base = n_tiles / n_warps, a_rem = n_tiles % n_warps, a_warps = n_warps;
+  unsigned long long a_epoch = ++ctx->epoch;
+  void* args[] = {&a_tab, &a_k, &a_counts, &n, &site_base, &a_list, &a_wcount, &a_warps, &a_base, &a_rem,
+                  &ctx->d_tile_status, &a_epoch, &ctx->d_counters, &in_slot, &out_slot, &d_calls, &cap, &ctx->count_out};
+  DNV_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(kListThreads), args, smem, ctx->stream));
+  DNV_CUDA(cudaGetLastError());
+  return DNV_OK;
+}
+
+}  // namespace dnv

@@ -16,8 +16,8 @@
 // (k_hom reads), the best heterozygote the two most frequent ones (k_het reads), and
 // r_hom^k_hom vs r_het^k_het is compared as k * log2(r) in 16.16 fixed point.
 // So ~99 % of sites are decided with integer instructions and no floating point at all; the
-// kernel streams the counts at HBM speed and appends the remaining sites to a list that the
-// fused FP64 kernel (trio_fast.cuh) evaluates.
+// kernel streams the counts at HBM speed and hands the remaining sites, in ascending order, to
+// the fused FP64 list kernel (trio_list.cuh).
 //
 // Two levels, so the common case costs ~40 instructions:
 //   level 1  the same allele X dominates all three pileups so strongly that XX beats every
@@ -124,20 +124,28 @@ __device__ __forceinline__ bool screen_level1(const uint32_t* w, const ScreenCon
   return s >= 0;
 }
 
-// Each warp walks tiles of 128 sites (four per lane, 3072 / 1536 bytes); TMA bulk copies keep two
-// tiles in flight ahead of the one being consumed, in warp-private buffers.  Level 2 is software
-// pipelined: the counts of 32 parked sites are requested (through L2, where the tile that just
-// streamed in still sits) one batch ahead of their evaluation, and the sites level 2 cannot
-// decide collect in a warp-private list that reaches global memory 32 at a time (one atomic each).
+// Each warp walks a CONTIGUOUS range of 128-site tiles (four sites per lane, 3072 / 1536 bytes per
+// tile); TMA bulk copies keep kScreenBufs tiles in flight in warp-private buffers.  Level 2 is
+// software pipelined: the counts of 32 parked sites are requested (through L2, where the tile that
+// just streamed in still sits) one batch ahead of their evaluation.  Parked and undecided sites
+// move through warp-private FIFO rings, so every warp emits its undecided sites in ascending order
+// into its own segment of `list` (the segment starts at the warp's first site index, so it cannot
+// overflow) and records how many it wrote in wcount[warp]: the concatenation of the segments in
+// warp order is the sorted list of undecided sites — no atomics, no sort (trio_list.cuh consumes it).
 constexpr int kScreenSites = 128;
 constexpr int kScreenPerLane = kScreenSites / 32;
-constexpr int kScreenQueue = 64;  // level-2 queue entries (site indices) per warp: at most 31 + 32 parked
-constexpr int kScreenFails = 64;  // undecided sites per warp waiting for their flush: at most 31 + 32
+constexpr int kScreenRing = 64;       // ring entries (site indices): at most 31 + 32 waiting
+constexpr int kScreenMaxWarps = 8192; // upper bound of gridDim.x * kScreenWarps (sizes wcount and its scan)
+
+// tiles [lo, hi) of warp g when n_tiles tiles are dealt to W warps in contiguous, balanced ranges
+__host__ __device__ __forceinline__ uint32_t screen_range_lo(uint32_t g, uint32_t base, uint32_t rem) {
+  return g * base + (g < rem ? g : rem);
+}
 
 template <bool kU8>
 __global__ void __launch_bounds__(kScreenThreads, 4)
 trio_screen_kernel(const unsigned char* __restrict__ counts, int64_t n, const ScreenConsts k,
-                   uint32_t* __restrict__ list, unsigned long long* __restrict__ counters) {
+                   uint32_t* __restrict__ list, uint32_t* __restrict__ wcount) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int kBps = kU8 ? 12 : 24;
   constexpr int kTile = kScreenSites * kBps;
@@ -145,17 +153,21 @@ trio_screen_kernel(const unsigned char* __restrict__ counts, int64_t n, const Sc
   constexpr uint32_t kFull = 0xffffffffu;
   unsigned char* tiles = smem_raw;  // [kScreenWarps][kScreenBufs][kTile]
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + kScreenWarps * kScreenBufs * kTile);
-  uint32_t* queues = reinterpret_cast<uint32_t*>(bars + kScreenWarps * kScreenBufs);  // [kScreenWarps][queue | fails]
+  uint32_t* rings = reinterpret_cast<uint32_t*>(bars + kScreenWarps * kScreenBufs);  // [kScreenWarps][parked | undecided]
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
   unsigned char* my_tiles = tiles + (size_t)warp * kScreenBufs * kTile;
   unsigned long long* my_bars = bars + warp * kScreenBufs;
-  uint32_t* my_queue = queues + warp * (kScreenQueue + kScreenFails);
-  uint32_t* my_fails = my_queue + kScreenQueue;
+  uint32_t* my_queue = rings + warp * (2 * kScreenRing);
+  uint32_t* my_fails = my_queue + kScreenRing;
   // a chunk holds fewer than 2^31 sites (api.cu: kDeviceChunk), so tile and site indices fit 32 bits
   const uint32_t n_sites = (uint32_t)n;
   const uint32_t n_tiles = (n_sites + kScreenSites - 1) / kScreenSites;
   const uint32_t n_full = (reinterpret_cast<uintptr_t>(counts) & 15) == 0 ? n_sites / kScreenSites : 0u;  // TMA-eligible tiles
+  const uint32_t warps_total = gridDim.x * kScreenWarps, g = blockIdx.x * kScreenWarps + warp;
+  const uint32_t base = n_tiles / warps_total, rem = n_tiles % warps_total;
+  const uint32_t t_lo = screen_range_lo(g, base, rem), t_hi = screen_range_lo(g + 1, base, rem);
+  uint32_t* my_list = list + (size_t)t_lo * kScreenSites;
   if (lane == 0) {
 #pragma unroll
     for (int b = 0; b < kScreenBufs; b++) mbar_init(&my_bars[b], 1);
@@ -163,53 +175,52 @@ trio_screen_kernel(const unsigned char* __restrict__ counts, int64_t n, const Sc
   }
   __syncwarp();
   auto issue = [&](uint32_t t, int buf) {
-    if (lane == 0 && t < n_full) {
+    if (lane == 0 && t < t_hi && t < n_full) {
       mbar_expect_tx(&my_bars[buf], kTile);
       tma_bulk_g2s(my_tiles + buf * kTile, counts + (size_t)t * kTile, kTile, &my_bars[buf]);
     }
   };
-  int qcount = 0, fcount = 0, ptake = 0;  // warp-uniform: parked sites, undecided sites, sites of the batch in flight
-  uint32_t pw[kWords], psite = 0;         // the batch in flight: one parked site per lane
+  // warp-uniform ring state: parked sites, undecided sites, the batch in flight, sites already written out
+  uint32_t qhead = 0, qcount = 0, fhead = 0, fcount = 0, ptake = 0, written = 0;
+  uint32_t pw[kWords], psite = 0;  // the batch in flight: one parked site per lane
 #pragma unroll
   for (int q = 0; q < kWords; q++) pw[q] = 0;
-  auto flush = [&](int take) {  // the newest `take` undecided sites -> the FP64 kernel's list
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(&counters[1], (unsigned long long)take);
-    base = __shfl_sync(kFull, base, 0);
-    if ((int)lane < take) list[base + lane] = my_fails[fcount - take + lane];
+  auto flush = [&](uint32_t take) {  // the oldest `take` undecided sites -> this warp's segment of the list
+    if (lane < take) my_list[written + lane] = my_fails[(fhead + lane) & (kScreenRing - 1)];
+    written += take;
+    fhead += take;
     fcount -= take;
     __syncwarp();
   };
   auto evaluate = [&]() {  // level 2 on the batch in flight
-    const bool fail = (int)lane < ptake && !screen_site<kU8>(pw, k);
+    const bool fail = lane < ptake && !screen_site<kU8>(pw, k);
     const uint32_t fw = __ballot_sync(kFull, fail);
     ptake = 0;
     if (fw) {
-      if (fail) my_fails[fcount + __popc(fw & lt_mask)] = psite;
+      if (fail) my_fails[(fhead + fcount + __popc(fw & lt_mask)) & (kScreenRing - 1)] = psite;
       fcount += __popc(fw);
       __syncwarp();
       if (fcount >= 32) flush(32);
     }
   };
-  auto fetch = [&](int take) {  // request the counts of the newest `take` parked sites
+  auto fetch = [&](uint32_t take) {  // request the counts of the oldest `take` parked sites
     __syncwarp();
-    if ((int)lane < take) {
-      psite = my_queue[qcount - take + lane];
+    if (lane < take) {
+      psite = my_queue[(qhead + lane) & (kScreenRing - 1)];
       const uint32_t* src = reinterpret_cast<const uint32_t*>(counts + (size_t)psite * kBps);
 #pragma unroll
       for (int q = 0; q < kWords; q++) pw[q] = __ldg(src + q);
     }
     ptake = take;
+    qhead += take;
     qcount -= take;
     __syncwarp();
   };
-  const uint32_t warps_total = gridDim.x * kScreenWarps;
-  const uint32_t t0 = blockIdx.x * kScreenWarps + warp;
 #pragma unroll
-  for (int b = 0; b < kScreenBufs; b++) issue(t0 + b * warps_total, b);
+  for (int b = 0; b < kScreenBufs; b++) issue(t_lo + b, b);
   uint32_t phases = 0;
   int buf = 0;
-  for (uint32_t t = t0; t < n_tiles; t += warps_total, buf = buf == kScreenBufs - 1 ? 0 : buf + 1) {
+  for (uint32_t t = t_lo; t < t_hi; t++, buf = buf == kScreenBufs - 1 ? 0 : buf + 1) {
     uint32_t w[kScreenPerLane][kWords];
     const uint32_t site0 = t * kScreenSites + lane;
     if (t < n_full) {
@@ -247,14 +258,14 @@ trio_screen_kernel(const unsigned char* __restrict__ counts, int64_t n, const Sc
     uint32_t fence_word;
     asm volatile("shr.b32 %0, %1, %2;" : "=r"(fence_word) : "r"(w[kScreenPerLane - 1][kWords - 1]), "r"(k.shift32));  // == 0
     __syncwarp();
-    issue(t + kScreenBufs * warps_total + fence_word, buf);
+    issue(t + kScreenBufs + fence_word, buf);
 #pragma unroll
     for (int h = 0; h < kScreenPerLane; h++) {
       const uint32_t site = site0 + h * 32;
       const bool park = site < n_sites && !screen_level1<kU8>(w[h], k);
       const uint32_t pm = __ballot_sync(kFull, park);
       if (pm) {
-        if (park) my_queue[qcount + __popc(pm & lt_mask)] = site;
+        if (park) my_queue[(qhead + qcount + __popc(pm & lt_mask)) & (kScreenRing - 1)] = site;
         qcount += __popc(pm);
         if (qcount >= 32) {
           if (ptake) evaluate();
@@ -269,23 +280,37 @@ trio_screen_kernel(const unsigned char* __restrict__ counts, int64_t n, const Sc
     evaluate();
   }
   if (fcount > 0) flush(fcount);
+  if (lane == 0) wcount[g] = written;
 }
 
+// grid of the screen (and so the warp -> tile-range map the list kernel has to reproduce)
 template <bool kU8>
-static int launch_screen(dnv_ctx* ctx, const void* d_counts, int64_t n, const ScreenConsts& sk) {
+static int screen_grid(dnv_ctx* ctx, int64_t n, size_t* smem_out) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
   constexpr int kTile = kScreenSites * (kU8 ? 12 : 24);
   const size_t smem = (size_t)kScreenWarps * kScreenBufs * kTile + kScreenWarps * kScreenBufs * 8 +
-                      (size_t)kScreenWarps * (kScreenQueue + kScreenFails) * 4;
+                      (size_t)kScreenWarps * 2 * kScreenRing * 4;
   auto kern = trio_screen_kernel<kU8>;
-  DNV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
   int per_sm = 1;
-  DNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kScreenThreads, smem));
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kScreenThreads, smem) != cudaSuccess) return -1;
   const int64_t want = ((n + kScreenSites - 1) / kScreenSites + kScreenWarps - 1) / kScreenWarps;
-  const int grid = (int)std::min<int64_t>(std::max<int64_t>(want, 1), (int64_t)sms * std::max(per_sm, 1));
-  kern<<<grid, kScreenThreads, smem, ctx->stream>>>((const unsigned char*)d_counts, n, sk, ctx->d_list, ctx->d_counters);
+  int64_t grid = std::min<int64_t>(std::max<int64_t>(want, 1), (int64_t)sms * std::max(per_sm, 1));
+  grid = std::min<int64_t>(grid, kScreenMaxWarps / kScreenWarps);
+  *smem_out = smem;
+  return (int)grid;
+}
+
+template <bool kU8>
+static int launch_screen(dnv_ctx* ctx, const void* d_counts, int64_t n, const ScreenConsts& sk, int* grid_out) {
+  size_t smem = 0;
+  const int grid = screen_grid<kU8>(ctx, n, &smem);
+  if (grid < 1) { set_error("trio_screen_kernel: launch configuration failed"); return DNV_E_CUDA; }
+  trio_screen_kernel<kU8><<<grid, kScreenThreads, smem, ctx->stream>>>((const unsigned char*)d_counts, n, sk, ctx->d_list,
+                                                                      ctx->d_wcount);
   DNV_CUDA(cudaGetLastError());
+  *grid_out = grid;
   return DNV_OK;
 }
 

@@ -12,7 +12,7 @@ import numpy as np
 
 PKG_ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 CSRC = os.path.join(PKG_ROOT, "csrc")
-LIB_PATH = os.path.join(PKG_ROOT, "lib", "libdenovo_b200.so")
+LIB_PATH = os.environ.get("DNV_B200_LIB") or os.path.join(PKG_ROOT, "lib", "libdenovo_b200.so")
 
 DNV_OK, DNV_E_INVALID, DNV_E_CUDA, DNV_E_CAPACITY, DNV_E_BADBASE, DNV_E_UNSORTED, DNV_E_NOMEM = 0, -1, -2, -3, -4, -5, -6
 METHODS = {"MAP": 0, "BAYES": 1, "LRT": 2}
