@@ -24,6 +24,7 @@ METRIC = "trio candidate sites/sec (READ-mode BAYES, 30x)"
 SITES_PER_GPU = 10_000_000
 SEED = 0x5EED0003
 DEPTH, EPS, MU, LRT = 30, 1e-2, 1e-8, 1.0
+GROUP = 32  # asynchronous steps per host synchronisation (and per inter-GPU barrier)
 # ALGORITHMIC work per site:
 #   integer screen (dominant kernel, HBM-bound): 24 B of counts in + 1 decision bit out
 #   fused FP64 kernel (only the sites the screen cannot decide): sparse factored form, FMA = 2
@@ -147,7 +148,7 @@ def reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--sites", type=int, default=SITES_PER_GPU)
@@ -184,20 +185,20 @@ def main():
     # ---- synthetic shard of this rank (interval sharding: rank r owns sites [r*n, (r+1)*n))
     d_counts = torch.empty((n, 12), dtype=torch.int16, device="cuda")
     eng.synth_counts_device(SEED, rank * n, n, d_counts, depth=DEPTH)
-    cap = max(n // 50, 1024)
+    cap = max(n // 100, 1024)
     d_calls = torch.zeros((cap, D.CALL_DT.itemsize), dtype=torch.uint8, device="cuda")
 
     from denovo_b200 import sharding
 
-    # N>1: the compaction kernel of every rank writes its call records straight into rank 0's HBM
-    # over NVLink (symmetric memory); no data collective, one signal-pad barrier per step.
+    # N>1: the list kernel of every rank writes its call records and their count straight into rank 0's
+    # HBM over NVLink (symmetric memory, one generation of slots per step of a group); no data
+    # collective, one signal-pad barrier per group of GROUP steps.
     peer = None
     if world > 1:
         try:
-            peer = sharding.PeerGather(dist, cap, D.CALL_DT.itemsize)
+            peer = sharding.PeerGather(dist, cap, D.CALL_DT.itemsize, slots=GROUP)
         except Exception as e:  # noqa: BLE001
             print("symmetric memory unavailable (%r): falling back to the NCCL gather" % (e,), file=sys.stderr)
-    calls_out = peer.records_ptr() if peer else d_calls
 
     # One step = one batch through the asynchronous device entry point (dnv_infer_counts_device_async):
     # the whole pipeline is enqueued on `stream`, the batch's call count lands in a pinned host slot
@@ -205,9 +206,8 @@ def main():
     # (dnv_sync) — how a genome is walked chunk by chunk.  N>1 adds one signal-pad barrier per step.
     torch.cuda.set_stream(stream)
     h_nc = torch.zeros(64, dtype=torch.int64).pin_memory()
-    counts_ptr, calls_ptr = d_counts.data_ptr(), (calls_out if isinstance(calls_out, int) else calls_out.data_ptr())
+    counts_ptr, calls_ptr = d_counts.data_ptr(), d_calls.data_ptr()
     nc_ptrs = [h_nc.data_ptr() + 8 * i for i in range(64)]
-    peer_nc = peer.count_ptr() if peer else None
 
     def run_steps(k_steps):
         """k_steps pipelined steps; returns summed library stats."""
@@ -215,7 +215,7 @@ def main():
                "n_calls": 0, "n_sites": 0}
         done = 0
         while done < k_steps:
-            m = min(32, k_steps - done)
+            m = min(GROUP, k_steps - done)
             if world > 1 and not peer:  # no symmetric memory: NCCL gather, needs the count on the host every step
                 m = 1
                 eng.infer_device_async(counts_ptr, n, calls_ptr, cap, nc_ptrs[0])
@@ -223,9 +223,12 @@ def main():
                 sharding.gather_records(d_calls[:int(h_nc[0])], dist)
             else:
                 for i in range(m):
-                    eng.infer_device_async(counts_ptr, n, calls_ptr, cap, peer_nc if peer else nc_ptrs[i])
                     if peer:
-                        peer.barrier()  # records + count of every rank now sit in rank 0's HBM
+                        eng.infer_device_async(counts_ptr, n, peer.records_ptr(i), cap, peer.count_ptr(i))
+                    else:
+                        eng.infer_device_async(counts_ptr, n, calls_ptr, cap, nc_ptrs[i])
+                if peer:
+                    peer.barrier()  # records + counts of every rank and step of the group now sit in rank 0's HBM
                 eng.sync()
             st = eng.stats()
             for key in acc:
@@ -245,6 +248,8 @@ def main():
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if peer:
+        peer.barrier()  # device-side line-up: every rank's timed region starts when all ranks are ready
     e0.record(stream)
     acc = run_steps(K)
     e1.record(stream)
@@ -255,7 +260,7 @@ def main():
     screened_out = acc["n_screened_out"] // K
     n_hard = acc["n_hard"] // K
     if peer:
-        total_calls = sum(peer.counts()) if rank == 0 else 0
+        total_calls = sum(peer.counts(gen=(K - 1) % GROUP)) if rank == 0 else 0
     else:
         total_calls = acc["n_calls"] // K
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -351,11 +356,11 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "READ-mode %s inference, %d synthetic trio candidate sites per GPU at 30x, eps 1e-2, "
                                    "mu 1e-8 (BASELINE configs[2]); interval-sharded; calls gathered to rank 0 %s"
-                                   % (args.method, n, "by peer stores over NVLink from the compaction kernel + one signal-pad "
-                                      "barrier (no data collective)" if peer else ("with NCCL" if world > 1 else "(single GPU)")),
+                                   % (args.method, n, "by peer stores over NVLink from the list kernel + one signal-pad "
+                                      "barrier per group of steps (no data collective)" if peer else ("with NCCL" if world > 1 else "(single GPU)")),
                        "sites_per_gpu": n, "l2": "input 240 MB per pass > 126 MB L2 (no flush needed)",
                        "calls_per_step": int(total_calls), "hard_sites_per_step": int(n_hard),
-                       "step": "asynchronous batches (dnv_infer_counts_device_async), one dnv_sync per 32 steps",
+                       "step": "asynchronous batches (dnv_infer_counts_device_async), one dnv_sync per %d steps" % GROUP,
                        "ms_per_step_synchronous_api": sync_ms},
             "e2e": {"value": e2e_value, "unit": "sites/s", "h2d_bytes_per_step": n * (12 if u8 else 24),
                     "input_format": "uint8 counts, 12 B/site (dnv_infer_counts8)" if u8 else "uint16 counts, 24 B/site",

@@ -115,7 +115,7 @@ int dnv_destroy(dnv_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->copy_stream);
   cudaFree(ctx->d_tab); cudaFree(ctx->d_bits); cudaFree(ctx->d_tile_status); cudaFree(ctx->d_list);
-  cudaFree(ctx->d_call_idx); cudaFree(ctx->d_counters); cudaFree(ctx->d_wcount); cudaFree(ctx->d_stage_calls); cudaFree(ctx->d_scratch);
+  cudaFree(ctx->d_call_idx); cudaFree(ctx->d_counters); cudaFree(ctx->d_wcount); cudaFree(ctx->d_list_stage); cudaFree(ctx->d_stage_calls); cudaFree(ctx->d_scratch);
   for (int i = 0; i < 2; i++) {
     cudaFree(ctx->d_stage_counts[i]); cudaFree(ctx->d_stage_dense[i]);
     cudaEventDestroy(ctx->ev_h2d[i]); cudaEventDestroy(ctx->ev_done[i]);

@@ -59,6 +59,8 @@ struct dnv_ctx {
   uint32_t* d_bits;        // decision bit per site
   uint32_t* d_list;        // sites the integer screen could not decide (chunk-relative), per-warp sorted segments
   uint32_t* d_wcount;      // length of every screen warp's segment of d_list
+  dnv_call* d_list_stage;  // list kernel: records between its two phases (local HBM)
+  int64_t list_stage_cap;
   bool screened;           // the last call used the screen
   unsigned long long* d_tile_status;  // decoupled look-back status per compaction block
   unsigned long long epoch;           // launch counter tagging d_tile_status entries

@@ -54,7 +54,7 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
                  int64_t n, int64_t site_base, const uint32_t* __restrict__ list, const uint32_t* __restrict__ wcount,
                  uint32_t n_warps, uint32_t range_base, uint32_t range_rem, unsigned long long* status,
                  unsigned long long epoch, unsigned long long* counters, int in_slot, int out_slot,
-                 dnv_call* __restrict__ calls, int64_t cap, int64_t* count_out) {
+                 dnv_call* __restrict__ calls, int64_t cap, int64_t* count_out, dnv_call* __restrict__ stage) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ListShared& s = *reinterpret_cast<ListShared*>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -260,7 +260,7 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
 #pragma unroll
         for (int q = 0; q < 12; q++) o.counts[q] = (uint16_t)c[q];
         o.is_denovo = 1;
-        calls[pos] = o;
+        stage[pos - calls_before] = o;  // local scratch; phase 2 completes it and writes the caller's buffer once
       }
     }
   }
@@ -284,25 +284,26 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
     // call j goes to CTA j % gridDim.x: every SM gets the same share of the sweep
     for (unsigned long long pos = calls_before + (unsigned long long)threadIdx.x * gridDim.x + blockIdx.x; pos < all;
          pos += (unsigned long long)gridDim.x * kListThreads) {
-      dnv_call* rec = calls + pos;
-      if (__ldcg(&rec->flags) & 1u) continue;  // hard site: complete already
-      const uint2* cw = reinterpret_cast<const uint2*>(rec->counts);
-      uint16_t cu[12];
+      // 80-byte record as five 16-byte words: read from the local scratch, written once to the caller's
+      // buffer (which may live in a peer GPU's HBM: no read-back over NVLink)
+      union { dnv_call r; uint4 v[5]; } u;
+      const uint4* src = reinterpret_cast<const uint4*>(stage + (pos - calls_before));
 #pragma unroll
-      for (int i = 0; i < 3; i++) {
-        const uint2 v = __ldcg(cw + i);
-        cu[4 * i + 0] = (uint16_t)(v.x & 0xFFFF); cu[4 * i + 1] = (uint16_t)(v.x >> 16);
-        cu[4 * i + 2] = (uint16_t)(v.y & 0xFFFF); cu[4 * i + 3] = (uint16_t)(v.y >> 16);
+      for (int i = 0; i < 5; i++) u.v[i] = __ldcg(src + i);
+      if (!(u.r.flags & 1u)) {  // hard sites are complete already
+        double Ld[10], Lm[10], Lc[10];
+        exact_read_loglik(u.r.counts + 0, k.hm, k.ht, k.mm, Ld);
+        exact_read_loglik(u.r.counts + 4, k.hm, k.ht, k.mm, Lm);
+        exact_read_loglik(u.r.counts + 8, k.hm, k.ht, k.mm, Lc);
+        int best;
+        double max_ll;
+        exact_map_pruned(Ld, Lm, Lc, s.rel, s.rmax, &best, &max_ll);
+        u.r.dad = (uint8_t)(best / 100); u.r.mom = (uint8_t)((best / 10) % 10); u.r.child = (uint8_t)(best % 10);
+        u.r.max_ll = max_ll;
       }
-      double Ld[10], Lm[10], Lc[10];
-      exact_read_loglik(cu + 0, k.hm, k.ht, k.mm, Ld);
-      exact_read_loglik(cu + 4, k.hm, k.ht, k.mm, Lm);
-      exact_read_loglik(cu + 8, k.hm, k.ht, k.mm, Lc);
-      int best;
-      double max_ll;
-      exact_map_pruned(Ld, Lm, Lc, s.rel, s.rmax, &best, &max_ll);
-      rec->dad = (uint8_t)(best / 100); rec->mom = (uint8_t)((best / 10) % 10); rec->child = (uint8_t)(best % 10);
-      rec->max_ll = max_ll;
+      uint4* dst = reinterpret_cast<uint4*>(calls + pos);
+#pragma unroll
+      for (int i = 0; i < 5; i++) dst[i] = u.v[i];
     }
   }
   __syncthreads();
@@ -331,6 +332,19 @@ static int launch_trio_list(dnv_ctx* ctx, const void* d_counts, int64_t n, int64
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sms * per_sm));
   const uint32_t n_tiles = (uint32_t)((n + kScreenSites - 1) / kScreenSites);
   const uint32_t n_warps = (uint32_t)screen_grid_size * kScreenWarps;
+  if (reinterpret_cast<uintptr_t>(d_calls) & 15) {
+    set_error("d_calls must be 16-byte aligned (records are written as 16-byte words)");
+    return DNV_E_INVALID;
+  }
+  // local scratch for the records between the two phases: at most min(cap, n) calls in this chunk
+  const int64_t need = std::max<int64_t>(1, std::min(cap, n));
+  if (need > ctx->list_stage_cap) {
+    cudaFree(ctx->d_list_stage);
+    ctx->d_list_stage = nullptr;
+    ctx->list_stage_cap = 0;
+    DNV_CUDA(cudaMalloc(&ctx->d_list_stage, (size_t)need * sizeof(dnv_call)));
+    ctx->list_stage_cap = need;
+  }
   // cooperative launch: the in-kernel barrier needs every CTA resident (grid <= sms * per_sm by construction)
   const Tables* a_tab = ctx->d_tab;
   FastConsts a_k = make_fast_consts(ctx->h_tab);
@@ -340,7 +354,7 @@ static int launch_trio_list(dnv_ctx* ctx, const void* d_counts, int64_t n, int64
   uint32_t a_base = n_tiles / n_warps, a_rem = n_tiles % n_warps, a_warps = n_warps;
   unsigned long long a_epoch = ++ctx->epoch;
   void* args[] = {&a_tab, &a_k, &a_counts, &n, &site_base, &a_list, &a_wcount, &a_warps, &a_base, &a_rem,
-                  &ctx->d_tile_status, &a_epoch, &ctx->d_counters, &in_slot, &out_slot, &d_calls, &cap, &ctx->count_out};
+                  &ctx->d_tile_status, &a_epoch, &ctx->d_counters, &in_slot, &out_slot, &d_calls, &cap, &ctx->count_out, &ctx->d_list_stage};
   DNV_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(kListThreads), args, smem, ctx->stream));
   DNV_CUDA(cudaGetLastError());
   return DNV_OK;

@@ -75,55 +75,61 @@ def globalize_sites(records_np, site_offset):
 
 
 class PeerGather:
-    """Gather of call records to `dst` WITHOUT a data collective: every rank's compaction kernel
-    stores its dnv_call records straight into rank dst's HBM over NVLink (peer stores through a
-    torch symmetric-memory mapping), then publishes its count and joins a signal-pad barrier.
-    Layout of the destination buffer: world slots of [64-byte header (int64 count) | cap records].
-    Rank order = genomic order, so the slots read in order are the gathered result.
-    Falls back to `gather_records` (NCCL) when symmetric memory is unavailable."""
+    """Gather of call records to `dst` WITHOUT a data collective: every rank's kernels store their
+    dnv_call records and the record count straight into rank dst's HBM over NVLink (peer stores
+    through a torch symmetric-memory mapping).  The destination holds `slots` generations of
+    world x [64-byte header (int64 count) | cap records]: batch k of a pipelined run writes
+    generation k % slots, so ranks never wait for each other per batch — ONE signal-pad barrier per
+    group of <= slots batches (`barrier()`) tells dst that everything has landed.
+    Rank order = genomic order, so the regions of one generation read in rank order are the
+    gathered result.  `gather_records` (NCCL) is the fallback when symmetric memory is unavailable."""
 
     HEADER = 64
 
-    def __init__(self, dist, cap_records, itemsize=80, dst=0):
+    def __init__(self, dist, cap_records, itemsize=80, dst=0, slots=1):
         import torch
         import torch.distributed._symmetric_memory as symm_mem
         self.torch, self.dist, self.dst = torch, dist, dst
         self.world, self.rank = dist.get_world_size(), dist.get_rank()
-        self.cap, self.itemsize = int(cap_records), int(itemsize)
+        self.cap, self.itemsize, self.slots = int(cap_records), int(itemsize), int(slots)
         self.slot = (self.HEADER + self.cap * self.itemsize + 255) // 256 * 256
-        self.buf = symm_mem.empty((self.world * self.slot,), dtype=torch.uint8, device="cuda")
+        self.total = self.slots * self.world * self.slot
+        self.buf = symm_mem.empty((self.total,), dtype=torch.uint8, device="cuda")
         self.hdl = symm_mem.rendezvous(self.buf, dist.group.WORLD)
-        self.dst_view = self.hdl.get_buffer(dst, (self.world * self.slot,), torch.uint8)  # rank dst's buffer
-        lo = self.rank * self.slot
-        self.my_header = self.dst_view[lo:lo + 8].view(torch.int64)
-        self.my_records_ptr = int(self.hdl.buffer_ptrs[dst]) + lo + self.HEADER
+        self.dst_view = self.hdl.get_buffer(dst, (self.total,), torch.uint8)  # rank dst's buffer
+        self.dst_base = int(self.hdl.buffer_ptrs[dst])
 
-    def records_ptr(self):
+    def _off(self, rank, gen):
+        return ((gen % self.slots) * self.world + rank) * self.slot
+
+    def records_ptr(self, gen=0):
         """Device pointer (in rank dst's memory) where this rank's kernels write their dnv_call records."""
-        return self.my_records_ptr
+        return self.dst_base + self._off(self.rank, gen) + self.HEADER
 
-    def count_ptr(self):
+    def count_ptr(self, gen=0):
         """Device pointer (in rank dst's memory) of this rank's int64 record count."""
-        return int(self.hdl.buffer_ptrs[self.dst]) + self.rank * self.slot
+        return self.dst_base + self._off(self.rank, gen)
 
     def barrier(self):
         """Signal-pad barrier on the current stream: after it, every rank's stores have landed in dst."""
         self.hdl.barrier()
 
-    def publish(self, n_calls):
-        """Call after the producing kernels were enqueued on the current stream."""
-        self.my_header.fill_(int(n_calls))
+    def publish(self, n_calls, gen=0):
+        """Host-known count: write it next to the records, then barrier (synchronous callers)."""
+        lo = self._off(self.rank, gen)
+        self.dst_view[lo:lo + 8].view(self.torch.int64).fill_(int(n_calls))
         self.hdl.barrier()
 
-    def counts(self):
-        """On dst (after publish): per-rank record counts."""
-        heads = self.buf.view(self.world, self.slot)[:, :8].contiguous().view(self.torch.int64)
-        return heads.view(-1).tolist()
+    def counts(self, gen=0):
+        """On dst (after barrier): per-rank record counts of one generation."""
+        lo = self._off(0, gen)
+        heads = self.buf[lo:lo + self.world * self.slot].view(self.world, self.slot)[:, :8].contiguous()
+        return heads.view(self.torch.int64).view(-1).tolist()
 
-    def records(self, counts=None):
-        """On dst: the gathered records as one contiguous uint8 [total, itemsize] tensor."""
-        counts = self.counts() if counts is None else counts
-        rows = self.buf.view(self.world, self.slot)[:, self.HEADER:self.HEADER + self.cap * self.itemsize]
-        rows = rows.reshape(self.world, self.cap, self.itemsize)
+    def records(self, counts=None, gen=0):
+        """On dst: the gathered records of one generation as one contiguous uint8 [total, itemsize] tensor."""
+        counts = self.counts(gen) if counts is None else counts
+        lo = self._off(0, gen)
+        rows = self.buf[lo:lo + self.world * self.slot].view(self.world, self.slot)
+        rows = rows[:, self.HEADER:self.HEADER + self.cap * self.itemsize].reshape(self.world, self.cap, self.itemsize)
         return self.torch.cat([rows[r, :counts[r]] for r in range(self.world)], dim=0)
-

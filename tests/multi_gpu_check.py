@@ -25,8 +25,26 @@ def main():
     eng = D.TrioEngine(device=local)
     counts = torch.empty((n, 12), dtype=torch.int16, device="cuda")
     eng.synth_counts_device(seed, lo, n, counts)
-    for use_peer in (True, False):
-        if use_peer:
+    for use_peer in ("async", True, False):
+        if use_peer == "async":
+            # pipelined batches: three generations in flight, the kernels store records AND counts into
+            # rank 0's HBM, one barrier for the group; every generation must hold the same gathered result
+            pg = sharding.PeerGather(dist, cap, D.CALL_DT.itemsize, slots=3)
+            torch.cuda.set_stream(torch.cuda.Stream())
+            eng.set_stream(torch.cuda.current_stream().cuda_stream)
+            for g in range(3):
+                eng.infer_device_async(counts, n, pg.records_ptr(g), cap, pg.count_ptr(g))
+            pg.barrier()
+            eng.sync()
+            torch.cuda.synchronize()
+            if rank == 0:
+                gens = [pg.records(gen=g).cpu().numpy().tobytes() for g in range(3)]
+                assert gens[0] == gens[1] == gens[2], "generations differ"
+            got = pg.records(gen=2).cpu().numpy().reshape(-1).view(D.CALL_DT) if rank == 0 else None
+            offs = np.cumsum([0] + pg.counts(gen=2))[:-1] if rank == 0 else None
+            eng.set_stream(None)
+            torch.cuda.set_stream(torch.cuda.default_stream())
+        elif use_peer:
             pg = sharding.PeerGather(dist, cap, D.CALL_DT.itemsize)
             nc = eng.infer_device(counts, n, pg.records_ptr(), cap)
             pg.publish(nc)
@@ -51,7 +69,7 @@ def main():
             nref = eng.infer_device(whole, total, ref_calls, 4 * cap)
             want = ref_calls[:nref].cpu().numpy().reshape(-1).view(D.CALL_DT)
             assert len(got) == len(want) and got.tobytes() == want.tobytes(), ("mismatch", use_peer, len(got), len(want))
-            print("multi_gpu_check OK: world %d, %s gather, %d calls" % (world, "peer-store" if use_peer else "NCCL", len(got)))
+            print("multi_gpu_check OK: world %d, %s gather, %d calls" % (world, {"async": "pipelined peer-store", True: "peer-store", False: "NCCL"}[use_peer], len(got)))
         dist.barrier()
     dist.destroy_process_group()
 
