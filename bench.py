@@ -26,13 +26,13 @@ SEED = 0x5EED0003
 DEPTH, EPS, MU, LRT = 30, 1e-2, 1e-8, 1.0
 GROUP = 32  # asynchronous steps per host synchronisation (and per inter-GPU barrier)
 # ALGORITHMIC work per site:
-#   integer screen (dominant kernel, HBM-bound): 24 B of counts in + 1 decision bit out
-#   fused FP64 kernel (only the sites the screen cannot decide): sparse factored form, FMA = 2
+#   integer screen (dominant kernel, HBM-bound): 24 B of counts in + 1 bit of decision out
+#   list kernel (only the sites the screen cannot decide): sparse factored FP64 form, FMA = 2
 BYTES_PER_SITE = 24.125
 FLOP_PER_SITE = 451.0
 # DRAM traffic of one screen launch over 10M sites from the ncu --set full capture committed as
 # profiles/r01_read_pipeline_ncu.md (dram__bytes_read.sum + dram__bytes_write.sum), per site
-NCU_TRAFFIC_BYTES_PER_SITE = 24.66
+NCU_TRAFFIC_BYTES_PER_SITE = 26.05
 
 
 def load_peaks():
@@ -313,7 +313,7 @@ def main():
     # ---- roofline of the dominant kernel
     fp64_peak, _ = eng.measure_fp64_peak()
     hbm_peak, peak_src = load_peaks()
-    k_ms = fused_ms / K          # decision kernels: integer screen + fused FP64 kernel on the undecided sites
+    k_ms = fused_ms / K          # both kernels of a step: integer screen + list kernel
     s_ms = screen_ms / K         # the screen alone
     if s_ms > 0:
         # BAYES/LRT: the integer screen streams every site's counts and is the dominant kernel (HBM-bound)
@@ -326,7 +326,7 @@ def main():
                     "kernel_share_of_step": s_ms / (ms_max / K), "bytes_per_site": BYTES_PER_SITE,
                     "peak_source": peak_src,
                     "sites_decided_by_screen": int(screened_out), "sites_to_fp64_kernel": int(n_fp64),
-                    "fp64_kernel": {"kernel": "trio_fast_kernel (list mode)", "kernel_ms": f_ms, "sites": int(n_fp64),
+                    "fp64_kernel": {"kernel": "trio_list_kernel (fused FP64 posterior + ordered compaction + call records)", "kernel_ms": f_ms, "sites": int(n_fp64),
                                     "flop_per_site": FLOP_PER_SITE, "achieved_tflops": ach_tf,
                                     "fp64_peak_tflops": fp64_peak,
                                     "peak_source": "dependent-free DFMA chains on all SMs, measured in this run"}}

@@ -1,12 +1,16 @@
-// trio.cu — READ-mode pipeline on one chunk of sites resident in HBM:
+// trio.cu — READ-mode pipeline on one chunk of sites resident in HBM.
 //
-//   K1  trio_fast_kernel (or trio_direct_all_kernel under DNV_F_FORCE_DIRECT):
-//         counts -> decision bit per site (+ dense record); hard sites are re-evaluated
-//         inside the kernel by the whole warp with the exact direct form
-//   K0  trio_screen_kernel (BAYES/LRT, calls only): exact integer screen at HBM speed; K1 then
-//         only sees the ~1 % of sites it could not decide
-//   K2  compact_calls_kernel: single-pass order-preserving compaction of the called sites
-//         (decoupled look-back)
+// BAYES / LRT, calls only (the BASELINE workload) — two kernels:
+//   S   trio_screen_kernel (trio_screen.cuh): exact integer screen of EVERY site at HBM speed; the
+//         ~1 % it cannot prove non-de-novo leave as per-warp sorted segments
+//   L   trio_list_kernel (trio_list.cuh, cooperative): fused FP64 likelihood + posterior on those
+//         sites, order-preserving compaction (decoupled look-back), dnv_call records
+//
+// MAP, dense output, DNV_F_NO_SCREEN, DNV_F_FORCE_DIRECT — three kernels:
+//   K1  trio_fast_kernel (trio_fast.cuh) or trio_direct_all_kernel: counts -> decision bit per site
+//         (+ dense record); hard sites are re-evaluated inside the kernel by the whole warp with the
+//         exact direct form
+//   K2  compact_calls_kernel: single-pass order-preserving compaction of the decision bits
 //   K3  call_details_kernel: one thread per called site -> dnv_call
 //
 // Replaces the per-site task of ReadCaller.runBayesDenovoInference

@@ -240,18 +240,15 @@ template <bool kLin, bool kMap, bool kDense, int kMinBlocks, bool kU8>
 __global__ void __launch_bounds__(kFastThreads, kMinBlocks)
 trio_fast_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsigned char* __restrict__ counts, int64_t n,
                  uint32_t* __restrict__ bits, unsigned long long* __restrict__ counters,
-                 dnv_site_result* __restrict__ dense, const uint32_t* __restrict__ list) {
+                 dnv_site_result* __restrict__ dense) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FastShared& s = *reinterpret_cast<FastShared*>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int kBps = kU8 ? 12 : 24;            // bytes per site
   constexpr int kTile = 32 * kBps;               // one warp tile (a multiple of 16)
 
-  // list mode: only the sites the integer screen could not decide (counters[1] of them), gathered
-  // by index; the decision bits were zeroed by the launcher and de novo sites are OR-ed in.
-  const int64_t n_items = list ? (int64_t)counters[1] : n;
-  const int64_t n_tiles = (n_items + 31) / 32;
-  const bool tma_ok = !list && (reinterpret_cast<uintptr_t>(counts) & 15) == 0;
+  const int64_t n_tiles = (n + 31) / 32;
+  const bool tma_ok = (reinterpret_cast<uintptr_t>(counts) & 15) == 0;
   if (lane == 0) {
     mbar_init(&s.bar[warp][0], 1);
     mbar_init(&s.bar[warp][1], 1);
@@ -281,8 +278,7 @@ trio_fast_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
   int64_t t = (int64_t)blockIdx.x * kFastWarps + warp;
   if (t < n_tiles) issue(t, 0);
   for (; t < n_tiles; t += warps_total, buf ^= 1) {
-    const int64_t item = t * 32 + lane;
-    const int64_t site = list ? (item < n_items ? (int64_t)list[item] : n) : item;
+    const int64_t site = t * 32 + lane;
     int c[12];
     if (tma_ok && (t + 1) * 32 <= n) {
       if (buf == 0) { mbar_wait(&s.bar[warp][0], phase0); phase0 ^= 1; }
@@ -356,18 +352,13 @@ trio_fast_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
         }
       }
     }
-    if (list) {
-      if (dn) atomicOr(&bits[site >> 5], 1u << (site & 31));
-    } else {
-      const uint32_t word = __ballot_sync(0xffffffffu, dn);
-      if (lane == 0) bits[t] = word;
-    }
+    const uint32_t word = __ballot_sync(0xffffffffu, dn);
+    if (lane == 0) bits[t] = word;
   }
 }
 
 template <bool kLin, bool kMap, bool kDense, int kMinBlocks, bool kU8>
-static int launch_fast_kernel(dnv_ctx* ctx, const void* d_counts, int64_t n, dnv_site_result* d_dense,
-                              const uint32_t* d_list) {
+static int launch_fast_kernel(dnv_ctx* ctx, const void* d_counts, int64_t n, dnv_site_result* d_dense) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
   const size_t smem = sizeof(FastShared);
@@ -381,24 +372,22 @@ static int launch_fast_kernel(dnv_ctx* ctx, const void* d_counts, int64_t n, dnv
   const int grid = (int)(want < persistent ? want : persistent);
   const FastConsts k = make_fast_consts(ctx->h_tab);
   kern<<<grid, kFastThreads, smem, ctx->stream>>>(ctx->d_tab, k, (const unsigned char*)d_counts, n, ctx->d_bits,
-                                                  ctx->d_counters, d_dense, d_list);
+                                                  ctx->d_counters, d_dense);
   DNV_CUDA(cudaGetLastError());
   return DNV_OK;
 }
 
 template <bool kLin, bool kMap, bool kDense, int kMinBlocks>
-static int launch_fast_variant(dnv_ctx* ctx, const void* d_counts, int64_t n, dnv_site_result* d_dense,
-                               const uint32_t* d_list = nullptr) {
-  if (ctx->count_bytes == 12) return launch_fast_kernel<kLin, kMap, kDense, kMinBlocks, true>(ctx, d_counts, n, d_dense, d_list);
-  return launch_fast_kernel<kLin, kMap, kDense, kMinBlocks, false>(ctx, d_counts, n, d_dense, d_list);
+static int launch_fast_variant(dnv_ctx* ctx, const void* d_counts, int64_t n, dnv_site_result* d_dense) {
+  if (ctx->count_bytes == 12) return launch_fast_kernel<kLin, kMap, kDense, kMinBlocks, true>(ctx, d_counts, n, d_dense);
+  return launch_fast_kernel<kLin, kMap, kDense, kMinBlocks, false>(ctx, d_counts, n, d_dense);
 }
 
-inline int launch_trio_fast(dnv_ctx* ctx, const void* d_counts, int64_t n, dnv_site_result* d_dense,
-                            const uint32_t* d_list = nullptr) {
+inline int launch_trio_fast(dnv_ctx* ctx, const void* d_counts, int64_t n, dnv_site_result* d_dense) {
   const bool map = ctx->prm.method == DNV_METHOD_MAP;
   if (d_dense) return launch_fast_variant<true, true, true, 2>(ctx, d_counts, n, d_dense);
   if (map) return launch_fast_variant<false, true, false, 4>(ctx, d_counts, n, nullptr);
-  return launch_fast_variant<true, false, false, 3>(ctx, d_counts, n, nullptr, d_list);
+  return launch_fast_variant<true, false, false, 3>(ctx, d_counts, n, nullptr);
 }
 
 }  // namespace dnv

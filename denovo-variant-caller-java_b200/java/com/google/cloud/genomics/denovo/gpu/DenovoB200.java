@@ -61,7 +61,7 @@ public final class DenovoB200 implements AutoCloseable {
   private static final Linker LINKER = Linker.nativeLinker();
   private final Arena libArena = Arena.ofShared();
   private final SymbolLookup lib;
-  private final MethodHandle create, destroy, lastError, inferCounts, pileup, mendelFilter, synthCountsAt;
+  private final MethodHandle create, destroy, lastError, inferCounts, inferCounts8, pileup, mendelFilter, synthCountsAt;
   private MemorySegment ctx = MemorySegment.NULL;
 
   private MethodHandle handle(String name, FunctionDescriptor fd) {
@@ -80,6 +80,8 @@ public final class DenovoB200 implements AutoCloseable {
     destroy = handle("dnv_destroy", FunctionDescriptor.of(JAVA_INT, ADDRESS));
     lastError = handle("dnv_last_error", FunctionDescriptor.of(ADDRESS));
     inferCounts = handle("dnv_infer_counts", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG,
+        ADDRESS, ADDRESS, JAVA_LONG, ADDRESS));
+    inferCounts8 = handle("dnv_infer_counts8", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG,
         ADDRESS, ADDRESS, JAVA_LONG, ADDRESS));
     pileup = handle("dnv_pileup", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS,
         JAVA_LONG, ADDRESS, JAVA_LONG, ADDRESS));
@@ -124,6 +126,22 @@ public final class DenovoB200 implements AutoCloseable {
     try (Arena a = Arena.ofConfined()) {
       MemorySegment nCalls = a.allocate(JAVA_LONG);
       check((int) inferCounts.invoke(ctx, counts, n, MemorySegment.NULL, calls, cap, nCalls));
+      return nCalls.get(JAVA_LONG, 0);
+    } catch (RuntimeException e) {
+      throw e;
+    } catch (Throwable t) {
+      throw new IllegalStateException(t);
+    }
+  }
+
+  /**
+   * Same with counts packed as uint8 [n][3][4] (12 bytes per site): for pileups whose per-allele depth is
+   * below 256 this halves the host-to-device traffic, which is what bounds the host path (PCIe).
+   */
+  public long inferCounts8(MemorySegment counts8, long n, MemorySegment calls, long cap) {
+    try (Arena a = Arena.ofConfined()) {
+      MemorySegment nCalls = a.allocate(JAVA_LONG);
+      check((int) inferCounts8.invoke(ctx, counts8, n, MemorySegment.NULL, calls, cap, nCalls));
       return nCalls.get(JAVA_LONG, 0);
     } catch (RuntimeException e) {
       throw e;
