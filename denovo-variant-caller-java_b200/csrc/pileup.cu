@@ -15,6 +15,7 @@
 #include <stdlib.h>
 #include <algorithm>
 #include "dnv_internal.cuh"
+#include "pileup_stage.cuh"
 
 namespace dnv {
 
@@ -467,14 +468,20 @@ int dnv_pileup_device(dnv_ctx* ctx, const int64_t* d_read_start, const int64_t* 
     pileup_prep_kernel<<<grid, 256, 0, ctx->stream>>>(d_read_start, d_base_off, d_person, n_reads, meta);
   }
   const int grid = (int)std::min<int64_t>((n_sites + 255) / 256, (int64_t)sms * 16);
-  static const int variant = getenv("DNV_PILEUP_VARIANT") ? atoi(getenv("DNV_PILEUP_VARIANT")) : 2;  // A/B knob
+  static const int variant = getenv("DNV_PILEUP_VARIANT") ? atoi(getenv("DNV_PILEUP_VARIANT")) : 3;  // A/B knob
   if (variant == 0)  // v0: one thread per site, per-lane windows
     pileup_gather_kernel<<<grid, 256, 0, ctx->stream>>>(d_read_start, d_base_off, d_bases, meta, d_site_pos, n_sites,
                                                         d_counts_out);
   else if (variant == 1)  // v1: warp-cooperative window walk
     pileup_warp_kernel<<<grid, 256, 0, ctx->stream>>>(d_read_start, d_base_off, d_bases, meta, d_site_pos, n_sites,
                                                       d_counts_out);
-  else {  // v2: 512-site tiles, 4 sites per thread, descriptors staged in shared memory
+  else if (variant == 3 || variant == 4) {  // v3 / v4: bases staged in shared memory, 8 / 16 sites per thread
+    cudaError_t e = variant == 3 ? launch_pileup_stage<8>(ctx->stream, sms, d_read_start, d_base_off, d_bases, meta, d_site_pos,
+                                                          n_sites, n_reads, d_counts_out)
+                                 : launch_pileup_stage<16>(ctx->stream, sms, d_read_start, d_base_off, d_bases, meta, d_site_pos,
+                                                           n_sites, n_reads, d_counts_out);
+    DNV_CUDA(e);
+  } else {  // v2: 512-site tiles, 4 sites per thread, descriptors staged in shared memory
     const int64_t n_tiles = (n_sites + kPT_Sites - 1) / kPT_Sites;
     const int tgrid = (int)std::min<int64_t>(n_tiles, (int64_t)sms * 16);
     pileup_tile_kernel<<<tgrid, kPT_Threads, 0, ctx->stream>>>(d_read_start, d_base_off, d_bases, meta, d_site_pos,
