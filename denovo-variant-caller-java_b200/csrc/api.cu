@@ -1,6 +1,7 @@
 // api.cu — the extern "C" boundary (include/denovo_b200.h): context lifecycle
 // and the READ-mode entry points.  Plain pointers and sizes only.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -24,7 +25,17 @@ int ensure_scratch(dnv_ctx* ctx, size_t bytes) {
 }
 
 // sites per pipeline chunk of the device path (scratch is sized for one chunk)
-constexpr int64_t kDeviceChunk = 1ll << 27;
+constexpr int64_t kDeviceChunkDefault = 1ll << 27;
+// DNV_DEVICE_CHUNK (sites, a multiple of 128 so that chunk boundaries keep the 16-byte alignment the
+// bulk copies want) shrinks the chunk so the tests can drive the multi-chunk path with small inputs
+static int64_t device_chunk() {
+  static const int64_t v = [] {
+    const char* e = getenv("DNV_DEVICE_CHUNK");
+    const long long x = e ? atoll(e) : 0;
+    return (x >= 128 && x <= kDeviceChunkDefault) ? (int64_t)(x / 128 * 128) : kDeviceChunkDefault;
+  }();
+  return v;
+}
 // sites per H2D/compute/D2H stage of the host path
 constexpr int64_t kHostChunk = 1ll << 21;
 
@@ -231,6 +242,7 @@ static int infer_device_async_impl(dnv_ctx* ctx, const void* d_counts, int bps, 
   ctx->count_bytes = bps;
   DNV_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
   ctx->count_out = h_n_calls;
+  const int64_t kDeviceChunk = device_chunk();
   for (int64_t off = 0; off < n; off += kDeviceChunk) {
     const int64_t m = std::min(kDeviceChunk, n - off);
     int rc = launch_trio_chunk(ctx, (const unsigned char*)d_counts + off * bps, off, m, nullptr, d_calls, cap);
@@ -261,6 +273,7 @@ static int infer_device_impl(dnv_ctx* ctx, const void* d_counts, int bps, int64_
   ctx->screened = false;
   ctx->count_bytes = bps;
   DNV_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->stream));
+  const int64_t kDeviceChunk = device_chunk();
   for (int64_t off = 0; off < n; off += kDeviceChunk) {
     const int64_t m = std::min(kDeviceChunk, n - off);
     int rc = launch_trio_chunk(ctx, (const unsigned char*)d_counts + off * bps, off, m,

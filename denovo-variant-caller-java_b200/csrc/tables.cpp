@@ -97,7 +97,9 @@ void build_tables(const dnv_params& p, Tables* t) {
     }
   t->fast_ok = (log2r[0] > 0.0L && log2r[1] > 0.0L) ? 1 : 0;
   // integer screen (trio_screen.cuh): Lden / Lmen <= 5334 mu / (1 - mu) for a Mendelian-consistent
-  // most-likely triple; valid when that bound is below the decision threshold and k*log2(r) fits 32 bits
+  // most-likely triple; valid when that bound is below the decision threshold and k*log2(r) fits 32 bits.
+  // The factor 4 covers the reference's raw-exp sums in the subnormal range, where each of the up to 750
+  // de novo terms may round UP by half an ulp (a factor 1.5 would do; see the header of trio_screen.cuh).
   const double thr_eff = p.method == DNV_METHOD_LRT ? p.lrt_threshold : 1.0;
   const bool fits = log2r[0] < 60.0L && log2r[1] < 60.0L;
   t->c_hom_fx = fits ? (uint32_t)llroundl(log2r[0] * 65536.0L) : 0;
@@ -117,7 +119,7 @@ void build_tables(const dnv_params& p, Tables* t) {
     }
   }
   t->early_ok = (t->fast_ok && fits && log2r[0] > log2r[1] && p.method != DNV_METHOD_MAP && thr_eff > 0.0 && std::isfinite(thr_eff) &&
-                 5334.0 * mu / (1.0 - mu) < 0.999 * thr_eff) ? 1 : 0;
+                 4.0 * 5334.0 * mu / (1.0 - mu) < 0.999 * thr_eff) ? 1 : 0;
   t->mm2 = (double)((logl(le) - logl(3.0L)) * l2e);
   t->k_men = (1.0 - mu) / 4 / 64;
   const int nd[4] = {9, 8, 7, 6};

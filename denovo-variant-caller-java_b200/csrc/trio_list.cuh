@@ -44,7 +44,7 @@ struct ListShared {
   unsigned long long excl;
 };
 
-// counters: [in_slot] calls before this chunk, [out_slot] <- calls after it, [1] <- undecided sites,
+// counters: [in_slot] calls before this chunk, [out_slot] <- calls after it, [1] += undecided sites,
 //           [4] += hard sites, [7] barrier arrivals, [5] CTAs gone (the last CTA to leave resets
 //           both for the next launch).
 // status word: [63:34] epoch of this launch, [33:32] 1 = tile aggregate, 2 = inclusive prefix, [31:0] value.
@@ -131,7 +131,7 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
   const unsigned long long calls_before = counters[in_slot];
   const unsigned long long tag = epoch << 34;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    counters[1] = total_items;
+    atomicAdd(&counters[1], (unsigned long long)total_items);  // summed over the chunks of a batch
     if (n_tiles == 0) {  // nothing undecided: the call total carries over
       counters[out_slot] = calls_before;
       if (count_out) *count_out = (int64_t)calls_before;

@@ -9,9 +9,12 @@
 //     Lmen >= P(g_d) P(g_m) T(g_d, g_m, g_c) a b e >= ((1 - mu) / 256) * a b e
 // (a, b, e = the likelihoods of the chosen genotypes, each within a factor 2 of the maximum).
 // Hence Lden / Lmen <= 8000 * 256 / 384 * mu / (1 - mu) = 5334 mu / (1 - mu): whenever that is
-// below the decision threshold (mu < 1.8e-4 for BAYES) the site is provably NOT de novo — also
-// under the reference's raw-exp underflow semantics (terms of Lden are then below those of
-// Lmen, so Lden flushes to zero first; 0/0 = NaN compares false).  The most likely genotype of
+// below the decision threshold the site is provably NOT de novo — also under the reference's
+// raw-exp underflow semantics: every term of Lden is below that one term M of Lmen by the factor
+// 5.33 mu, so Lden flushes to zero first (0/0 = NaN compares false); and when M is subnormal each
+// of the <= 750 terms of Lden that does not flush may round up by half an ulp, at most doubling it,
+// so 2 * 5334 mu / (1 - mu) < T still proves Lden <= T * Lmen.  tables.cpp enables the screen
+// with a factor 4 (mu < 4.7e-5 for BAYES; the default is 1e-8).  The most likely genotype of
 // a person follows from integer counts alone: the best homozygote is the most frequent allele
 // (k_hom reads), the best heterozygote the two most frequent ones (k_het reads), and
 // r_hom^k_hom vs r_het^k_het is compared as k * log2(r) in 16.16 fixed point.

@@ -42,6 +42,19 @@ def check_against_oracle(counts, eps=1e-2, mu=1e-8, lrt=1.0, method="BAYES", for
     with D.TrioEngine(eps, mu, lrt, method, force_direct=force_direct) as eng:
         calls, d = eng.infer(counts, dense=dense)
         stats = eng.stats()
+        # calls only: BAYES / LRT then take the headline path (integer screen + list kernel), and the
+        # compact uint8 input the same path with 12-byte sites
+        variants = [eng.infer(counts)[0]]
+        if counts.size and counts.max() < 256:
+            variants.append(eng.infer(counts.astype(np.uint8))[0])
+    for other in variants:
+        for f in ("site", "dad", "mom", "child", "max_ll", "counts", "is_denovo"):
+            assert np.array_equal(other[f], calls[f]), ("calls-only path differs from the dense path", f)
+        same = (other["flags"] == 0) & (calls["flags"] == 0)  # hard sites: sequential vs warp-parallel exact sums
+        for f in ("p", "lr", "log_men", "log_den"):
+            a, b = other[f], calls[f]
+            assert np.array_equal(a[same], b[same], equal_nan=True), ("calls-only path differs from the dense path", f)
+            assert np.all(close(a[~same], b[~same], log_domain=f.startswith("log")) | (np.isnan(a[~same]) & np.isnan(b[~same])))
     want = ref[METHOD_FIELD[method]].astype(bool)
     # ---- called sites: bit-exact set, input order
     assert np.array_equal(calls["site"], np.nonzero(want)[0])
@@ -246,3 +259,87 @@ def test_async_batches_match_synchronous_calls(method):
         eng.infer_device_async(bufs[3], sizes[3], outs[3], sizes[3], h_nc.data_ptr())
         k = eng.infer_device(bufs[0], sizes[0], outs[0], sizes[0])
         assert outs[0][:k].cpu().numpy().tobytes() == want[0]
+
+
+def _adversarial_counts(rng, n):
+    """Pileups built to sit on the integer screen's decision boundaries: one or two dominant alleles with
+    0..6 stray reads, equal counts (ties between genotypes), depths around the uint8 and power-table
+    limits, empty persons."""
+    c = np.zeros((n, 3, 4), np.int64)
+    kind = rng.integers(0, 8, n)
+    depth = rng.choice([1, 2, 5, 12, 30, 31, 60, 127, 128, 254, 255, 256, 300, 1022, 1023, 1024, 1100, 4000], n)
+    for i in range(n):
+        x, y = rng.choice(4, 2, replace=False)
+        for p in range(3):
+            d = int(depth[i]) if kind[i] != 7 else int(rng.integers(0, 40))
+            k = kind[i]
+            if k == 0:      # everybody homozygous X with a few errors
+                stray = int(rng.integers(0, 7))
+                c[i, p, x] = max(d - stray, 0)
+                c[i, p, rng.integers(0, 4)] += stray
+            elif k == 1:    # one parent het, child anything
+                if p == int(rng.integers(0, 2)):
+                    c[i, p, x] = d // 2; c[i, p, y] = d - d // 2
+                else:
+                    c[i, p, x] = d
+            elif k == 2:    # child het, parents hom: the de novo pattern, with 0..3 alt reads leaking into a parent
+                if p == 2:
+                    a = int(rng.integers(0, d + 1)); c[i, p, x] = d - a; c[i, p, y] = a
+                else:
+                    a = int(rng.integers(0, 4)); c[i, p, x] = max(d - a, 0); c[i, p, y] = min(a, d)
+            elif k == 3:    # exact ties
+                c[i, p, x] = d; c[i, p, y] = d
+            elif k == 4:    # hom-vs-het boundary: n_X * log2 r_hom ~ N * log2 r_het
+                a = int(round(d * rng.uniform(0.08, 0.16))); c[i, p, x] = d - a; c[i, p, y] = a
+            elif k == 5:    # three alleles present
+                parts = rng.multinomial(d, [0.5, 0.3, 0.2]); c[i, p, x] = parts[0]; c[i, p, y] = parts[1]
+                c[i, p, min(set(range(4)) - {int(x), int(y)})] += parts[2]
+            elif k == 6:    # an empty person
+                if p != int(rng.integers(0, 3)):
+                    c[i, p, x] = d
+            else:           # uniform noise
+                c[i, p] = rng.integers(0, 12, 4)
+    return np.minimum(c, 65535).astype(np.uint16)
+
+
+@pytest.mark.parametrize("eps,mu,lrt", [(1e-2, 1e-8, 1.0), (1e-3, 1e-10, 1.0), (1e-1, 1e-6, 0.05), (0.3, 1e-5, 20.0),
+                                        (1e-2, 1e-3, 1.0), (2e-2, 1.7e-4, 1.0), (2e-2, 4.5e-5, 1.0)])
+def test_screen_boundaries_against_oracle(eps, mu, lrt):
+    """BAYES and LRT on adversarial pileups, for parameters where the integer screen is valid (small mu),
+    barely valid (mu = 4.5e-5, just under its limit) and invalid (mu >= 1.7e-4: every site takes the FP64 path)."""
+    rng = np.random.default_rng(int(eps * 1e6) + int(-np.log10(mu)))
+    c = _adversarial_counts(rng, 6000)
+    for method in ("BAYES", "LRT"):
+        check_against_oracle(c, eps=eps, mu=mu, lrt=lrt, method=method)
+
+
+def test_multi_chunk_device_path_matches_single_chunk():
+    """A device call walks its input in chunks of 2^27 sites; DNV_DEVICE_CHUNK shrinks the chunk so a
+    small input crosses several boundaries (ragged last chunk, running call total, site offsets)."""
+    import subprocess, sys, os
+    code = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+import denovo_b200 as D
+n = 300_001
+out = []
+for method in ("BAYES", "MAP"):
+    with D.TrioEngine(method=method) as eng:
+        c = torch.empty((n, 12), dtype=torch.int16, device="cuda")
+        eng.synth_counts_device(0x5EED0003, 77, n, c, depth=30)
+        calls = torch.zeros((n, D.CALL_DT.itemsize), dtype=torch.uint8, device="cuda")
+        k = eng.infer_device(c, n, calls, n)
+        st = eng.stats()
+        out.append(calls[:k].cpu().numpy().tobytes())
+        out.append(np.array([k, st["n_calls"], st["n_screened_out"]], np.int64).tobytes())
+sys.stdout.buffer.write(b"".join(out))
+""" % os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "denovo-variant-caller-java_b200", "python")
+    res = []
+    for chunk in (None, "65536", "1280"):
+        env = dict(os.environ)
+        if chunk:
+            env["DNV_DEVICE_CHUNK"] = chunk
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stderr.decode()[-2000:]
+        res.append(r.stdout)
+    assert len(res[0]) > 1000 and res[0] == res[1] == res[2]
