@@ -26,7 +26,8 @@ struct Tables {
   double pw_m[2][kPowTable];   // mantissa in [1,2) of r_j^k
   int32_t pw_e[2][kPowTable];  // binary exponent of r_j^k
   int32_t fast_ok;             // both ratios > 1 (always, unless eps is absurdly large)
-  int32_t early_ok;            // the integer screen (trio_screen.cuh) is valid for these parameters
+  int32_t early_ok;            // the integer screen (trio_screen.cuh) is valid for these parameters (BAYES / LRT)
+  int32_t map_screen_ok;       // ... and for the MAP decision
   uint32_t c_hom_fx, c_het_fx; // log2(r_j) in 16.16 fixed point
   uint32_t scr_w[4];           // screen level 1: signed-byte weights (A,C,G,T) when allele X is the candidate
   double mm2;                  // log2(eps/3)

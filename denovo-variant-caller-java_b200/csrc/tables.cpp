@@ -120,6 +120,11 @@ void build_tables(const dnv_params& p, Tables* t) {
   }
   t->early_ok = (t->fast_ok && fits && log2r[0] > log2r[1] && p.method != DNV_METHOD_MAP && thr_eff > 0.0 && std::isfinite(thr_eff) &&
                  4.0 * 5334.0 * mu / (1.0 - mu) < 0.999 * thr_eff) ? 1 : 0;
+  // MAP through the same screen: the chosen Mendelian triple t* (each genotype within a factor 2 of its
+  // person's best) has ll(t*) >= sum Lmax - 3 ln 2 + log((1/16)(1/16)(1-mu)/4); every de novo triple has
+  // ll <= sum Lmax + log((1/8)(1/8) mu/6).  The gap is log(0.046875 (1-mu)/mu): with mu < 0.01 it exceeds
+  // 1.5 nats, rounding of the four-term sums is ~1e-13, so the argmax is Mendelian: not de novo, exactly.
+  t->map_screen_ok = (t->fast_ok && fits && log2r[0] > log2r[1] && p.method == DNV_METHOD_MAP && mu < 0.01) ? 1 : 0;
   t->mm2 = (double)((logl(le) - logl(3.0L)) * l2e);
   t->k_men = (1.0 - mu) / 4 / 64;
   const int nd[4] = {9, 8, 7, 6};

@@ -1,12 +1,12 @@
 // trio.cu — READ-mode pipeline on one chunk of sites resident in HBM.
 //
-// BAYES / LRT, calls only (the BASELINE workload) — two kernels:
+// Calls only (the BASELINE workload; BAYES / LRT, and MAP through the same screen) — two kernels:
 //   S   trio_screen_kernel (trio_screen.cuh): exact integer screen of EVERY site at HBM speed; the
 //         ~1 % it cannot prove non-de-novo leave as per-warp sorted segments
 //   L   trio_list_kernel (trio_list.cuh, cooperative): fused FP64 likelihood + posterior on those
 //         sites, order-preserving compaction (decoupled look-back), dnv_call records
 //
-// MAP, dense output, DNV_F_NO_SCREEN, DNV_F_FORCE_DIRECT — three kernels:
+// Dense output, DNV_F_NO_SCREEN, DNV_F_FORCE_DIRECT, parameters outside the screen's validity — three kernels:
 //   K1  trio_fast_kernel (trio_fast.cuh) or trio_direct_all_kernel: counts -> decision bit per site
 //         (+ dense record); hard sites are re-evaluated inside the kernel by the whole warp with the
 //         exact direct form
@@ -258,7 +258,9 @@ int launch_trio_chunk(dnv_ctx* ctx, const void* d_counts, int64_t site_base, int
 
   const bool direct = (ctx->prm.flags & DNV_F_FORCE_DIRECT) != 0;
   const bool timed = (ctx->prm.flags & DNV_F_TIME_KERNELS) != 0 && ctx->n_timed < 64;
-  const bool screen = !direct && ctx->h_tab.early_ok && !d_dense && !(ctx->prm.flags & DNV_F_NO_SCREEN);
+  const bool map = ctx->prm.method == DNV_METHOD_MAP;
+  const bool screen = !direct && (map ? ctx->h_tab.map_screen_ok : ctx->h_tab.early_ok) && !d_dense &&
+                      !(ctx->prm.flags & DNV_F_NO_SCREEN);
   if (timed) DNV_CUDA(cudaEventRecord(ctx->ev_k0[ctx->n_timed], st));
   if (direct) {
     const int64_t want = (n + kExactThreads - 1) / kExactThreads;
@@ -266,7 +268,7 @@ int launch_trio_chunk(dnv_ctx* ctx, const void* d_counts, int64_t site_base, int
     trio_direct_all_kernel<<<grid, kExactThreads, 0, st>>>(ctx->d_tab, d_counts, ctx->count_bytes, n, ctx->d_bits, d_dense,
                                                           ctx->d_counters);
   } else if (screen) {
-    // BAYES / LRT, calls only: exact integer screen at HBM speed, then ONE kernel for the sites it could
+    // calls only: exact integer screen at HBM speed, then ONE kernel for the sites it could
     // not decide (fused FP64 posterior, ordered compaction, call records)
     ScreenConsts sk;
     sk.c_hom = ctx->h_tab.c_hom_fx;
@@ -279,8 +281,12 @@ int launch_trio_chunk(dnv_ctx* ctx, const void* d_counts, int64_t site_base, int
     if (rc) return rc;
     if (timed) DNV_CUDA(cudaEventRecord(ctx->ev_s1[ctx->n_timed], st));
     const int in_slot = ctx->calls_slot, out_slot = in_slot == 0 ? 3 : 0;
-    rc = u8 ? launch_trio_list<true>(ctx, d_counts, n, site_base, sgrid, in_slot, out_slot, d_calls, cap)
-            : launch_trio_list<false>(ctx, d_counts, n, site_base, sgrid, in_slot, out_slot, d_calls, cap);
+    if (map)
+      rc = u8 ? launch_trio_list<true, true>(ctx, d_counts, n, site_base, sgrid, in_slot, out_slot, d_calls, cap)
+              : launch_trio_list<false, true>(ctx, d_counts, n, site_base, sgrid, in_slot, out_slot, d_calls, cap);
+    else
+      rc = u8 ? launch_trio_list<true, false>(ctx, d_counts, n, site_base, sgrid, in_slot, out_slot, d_calls, cap)
+              : launch_trio_list<false, false>(ctx, d_counts, n, site_base, sgrid, in_slot, out_slot, d_calls, cap);
     if (rc) return rc;
     if (timed) DNV_CUDA(cudaEventRecord(ctx->ev_k1[ctx->n_timed++], st));
     ctx->calls_slot = out_slot;

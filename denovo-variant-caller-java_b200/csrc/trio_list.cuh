@@ -15,6 +15,8 @@
 //      (everything, from the exact evaluation, for hard sites);
 //   3. after a grid-wide barrier (cooperative launch: every CTA is resident), ONE THREAD PER
 //      CALL completes the record with the exact pruned log-domain sweep (MAP triple, max_ll).
+//      (MAP method, kMap: the roles swap — the sweep is the decision of phase 1 and phase 2 adds
+//      p / LR / log-likelihoods from the linear form.)
 //      Called sites are ~1 in 5 of the list, so doing this densely instead of inside the
 //      divergent decision loop takes the sweep off every warp's critical path.
 // No decision bitmap, no separate compaction or record kernels, no sort.
@@ -48,7 +50,7 @@ struct ListShared {
 //           [4] += hard sites, [7] barrier arrivals, [5] CTAs gone (the last CTA to leave resets
 //           both for the next launch).
 // status word: [63:34] epoch of this launch, [33:32] 1 = tile aggregate, 2 = inclusive prefix, [31:0] value.
-template <bool kU8>
+template <bool kU8, bool kMap>
 __global__ void __launch_bounds__(kListThreads, 3)
 trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsigned char* __restrict__ counts,
                  int64_t n, int64_t site_base, const uint32_t* __restrict__ list, const uint32_t* __restrict__ wcount,
@@ -175,26 +177,45 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
     fetch_counts(site_cur, words_cur);
     LinOut lo_;
     lo_.hard = false; lo_.dn = false; lo_.zd = lo_.zm = 2; lo_.den_s = lo_.men_s = lo_.s2 = 0.0;
-    if (live) {
-      if (k.lin_ok) linear_site(pw, c, k.k_men, k.kd9, k.kd8, k.kd7, k.kd6, k.thr, k.mm2, k.method, k.lrt_threshold, lo_);
-      else lo_.hard = true;  // eps so large that r <= 1: the table scheme does not apply
-    }
-    bool dn = lo_.dn;
-    // hard sites: the whole warp evaluates them one at a time with the exact direct form
+    bool dn = false;
     ExactOut ex;
     ex.is_denovo = false;
-    uint32_t hword = __ballot_sync(0xffffffffu, lo_.hard);
-    if (hword) {
-      if (lane == 0) atomicAdd(&counters[4], (unsigned long long)__popc(hword));
-      while (hword) {
-        const int h = __ffs(hword) - 1;
-        hword &= hword - 1;
+    int map_best = 0;
+    double map_ll = 0.0;
+    if (kMap) {
+      // MAP: the decision is the exact pruned log-domain sweep itself (no hard sites); p / LR / logs of the
+      // called sites are filled in by phase 2
+      if (live) {
         uint16_t cu[12];
 #pragma unroll
-        for (int q = 0; q < 12; q++) cu[q] = (uint16_t)__shfl_sync(0xffffffffu, c[q], h);
-        ExactOut r;
-        exact_site_warp(cu, s.rel, s.isden, s.warp_L[warp], k.hm, k.ht, k.mm, k.method, k.lrt_threshold, &r);
-        if (lane == h) { ex = r; dn = r.is_denovo; }
+        for (int q = 0; q < 12; q++) cu[q] = (uint16_t)c[q];
+        double Ld[10], Lm[10], Lc[10];
+        exact_read_loglik(cu + 0, k.hm, k.ht, k.mm, Ld);
+        exact_read_loglik(cu + 4, k.hm, k.ht, k.mm, Lm);
+        exact_read_loglik(cu + 8, k.hm, k.ht, k.mm, Lc);
+        exact_map_pruned(Ld, Lm, Lc, s.rel, s.rmax, &map_best, &map_ll);
+        dn = (s.isden[map_best >> 5] >> (map_best & 31)) & 1u;
+      }
+    } else {
+      if (live) {
+        if (k.lin_ok) linear_site(pw, c, k.k_men, k.kd9, k.kd8, k.kd7, k.kd6, k.thr, k.mm2, k.method, k.lrt_threshold, lo_);
+        else lo_.hard = true;  // eps so large that r <= 1: the table scheme does not apply
+      }
+      dn = lo_.dn;
+      // hard sites: the whole warp evaluates them one at a time with the exact direct form
+      uint32_t hword = __ballot_sync(0xffffffffu, lo_.hard);
+      if (hword) {
+        if (lane == 0) atomicAdd(&counters[4], (unsigned long long)__popc(hword));
+        while (hword) {
+          const int h = __ffs(hword) - 1;
+          hword &= hword - 1;
+          uint16_t cu[12];
+#pragma unroll
+          for (int q = 0; q < 12; q++) cu[q] = (uint16_t)__shfl_sync(0xffffffffu, c[q], h);
+          ExactOut r;
+          exact_site_warp(cu, s.rel, s.isden, s.warp_L[warp], k.hm, k.ht, k.mm, k.method, k.lrt_threshold, &r);
+          if (lane == h) { ex = r; dn = r.is_denovo; }
+        }
       }
     }
     if (tile == blockIdx.x) stamp(2);
@@ -246,7 +267,12 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
       const unsigned long long pos = calls_before + s.excl + (unsigned long long)(warp_off + __popc(dw & ((1u << lane) - 1u)));
       if (pos < (unsigned long long)cap) {
         dnv_call o;
-        if (lo_.hard) {
+        if (kMap) {  // phase 2 fills in p, LR and the log-likelihoods
+          o.dad = (uint8_t)(map_best / 100); o.mom = (uint8_t)((map_best / 10) % 10); o.child = (uint8_t)(map_best % 10);
+          o.max_ll = map_ll;
+          o.p = o.lr = o.log_men = o.log_den = 0.0;
+          o.flags = 0;
+        } else if (lo_.hard) {
           o.dad = (uint8_t)ex.dad; o.mom = (uint8_t)ex.mom; o.child = (uint8_t)ex.child;
           o.max_ll = ex.max_ll; o.p = ex.p; o.lr = ex.lr; o.log_men = ex.log_men; o.log_den = ex.log_den;
           o.flags = 1;
@@ -290,7 +316,29 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
       const uint4* src = reinterpret_cast<const uint4*>(stage + (pos - calls_before));
 #pragma unroll
       for (int i = 0; i < 5; i++) u.v[i] = __ldcg(src + i);
-      if (!(u.r.flags & 1u)) {  // hard sites are complete already
+      if (kMap) {
+        // values of a MAP call: the factored linear form unless the site is hard (gray zone, deeper than
+        // the tables), then the exact direct form in the reference's own order — as call_details_kernel does
+        int ci[12];
+#pragma unroll
+        for (int q = 0; q < 12; q++) ci[q] = u.r.counts[q];
+        LinOut lv;
+        if (k.lin_ok) {
+          linear_site(pw, ci, k.k_men, k.kd9, k.kd8, k.kd7, k.kd6, 1.0, k.mm2, DNV_METHOD_BAYES, 1.0, lv);
+          lv.hard = lv.zd == 2 || lv.zm == 2;
+        } else {
+          lv.hard = true;
+        }
+        if (lv.hard) {
+          ExactOut r;
+          exact_site(u.r.counts, s.rel, s.isden, k.hm, k.ht, k.mm, k.method, k.lrt_threshold, &r);
+          u.r.p = r.p; u.r.lr = r.lr; u.r.log_men = r.log_men; u.r.log_den = r.log_den;
+          u.r.flags = 1;
+          atomicAdd(&counters[4], 1ull);
+        } else {
+          linear_values(lv, u.r.p, u.r.lr, u.r.log_men, u.r.log_den);
+        }
+      } else if (!(u.r.flags & 1u)) {  // hard sites are complete already
         double Ld[10], Lm[10], Lc[10];
         exact_read_loglik(u.r.counts + 0, k.hm, k.ht, k.mm, Ld);
         exact_read_loglik(u.r.counts + 4, k.hm, k.ht, k.mm, Lm);
@@ -317,13 +365,13 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
   }
 }
 
-template <bool kU8>
+template <bool kU8, bool kMap>
 static int launch_trio_list(dnv_ctx* ctx, const void* d_counts, int64_t n, int64_t site_base, int screen_grid_size,
                             int in_slot, int out_slot, dnv_call* d_calls, int64_t cap) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
   const size_t smem = sizeof(ListShared);
-  auto kern = trio_list_kernel<kU8>;
+  auto kern = trio_list_kernel<kU8, kMap>;
   DNV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 1;
   DNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kListThreads, smem));
