@@ -122,6 +122,16 @@ def pileup(n_sites, depth=30):
                 eng.pileup_device(d[0], d[1], d[2], d[3], len(rs), d[4], n_sites, d_counts)
         ms = timed(step, stream, reps=5)
         got = d_counts.cpu().numpy().view(np.uint16).reshape(n_sites, 3, 4)
+        # secondary metric of SURVEY.md 8(d): reads -> counts -> calls, chained on the device
+        cap = max(n_sites // 20, 1024)
+        d_calls = torch.zeros((cap, D.CALL_DT.itemsize), dtype=torch.uint8, device="cuda")
+        chain = {}
+
+        def step2():
+            with torch.cuda.stream(stream):
+                eng.pileup_device(d[0], d[1], d[2], d[3], len(rs), d[4], n_sites, d_counts)
+                chain["calls"] = eng.infer_device(d_counts, n_sites, d_calls, cap)
+        ms_chain = timed(step2, stream, reps=5)
     m = 20000
     sel = slice(n_sites // 2, n_sites // 2 + m)
     lo, hi = pos[sel][0] - 200, pos[sel][-1] + 1
@@ -138,7 +148,9 @@ def pileup(n_sites, depth=30):
                       "sites_per_s": n_sites / ms * 1e3, "algorithmic_bytes_per_site": alg_bytes / n_sites,
                       "algorithmic_GBps": alg_bytes / ms / 1e6, "hbm_peak_GBps": HBM,
                       "frac_of_hbm": alg_bytes / ms / 1e6 / HBM,
-                      "bit_exact_vs_oracle_window": bool(rc == 0 and np.array_equal(got[sel], want))}), flush=True)
+                      "bit_exact_vs_oracle_window": bool(rc == 0 and np.array_equal(got[sel], want)),
+                      "reads_to_calls_ms": ms_chain, "reads_to_calls_sites_per_s": n_sites / ms_chain * 1e3,
+                      "reads_to_calls_calls": int(chain["calls"])}), flush=True)
 
 
 def genome(total=3_095_693_983, chunk=1 << 26, depth=30):

