@@ -343,3 +343,32 @@ sys.stdout.buffer.write(b"".join(out))
         assert r.returncode == 0, r.stderr.decode()[-2000:]
         res.append(r.stdout)
     assert len(res[0]) > 1000 and res[0] == res[1] == res[2]
+
+
+def test_batch_pipeline_two_contexts_matches_single_engine():
+    """D.BatchPipeline (two contexts, two streams, batches fed alternately) must return, batch for batch,
+    exactly what one engine returns."""
+    import torch
+    n, nb = 150_000, 7
+    with D.TrioEngine() as eng, D.BatchPipeline(depth=2) as pipe:
+        bufs = []
+        for i in range(nb):
+            c = torch.empty((n, 12), dtype=torch.int16, device="cuda")
+            eng.synth_counts_device(0x5EED0003, i * n, n, c, depth=30)
+            bufs.append(c)
+        torch.cuda.synchronize()
+        want = []
+        for c in bufs:
+            calls = torch.zeros((n, D.CALL_DT.itemsize), dtype=torch.uint8, device="cuda")
+            k = eng.infer_device(c, n, calls, n)
+            want.append(calls[:k].cpu().numpy().tobytes())
+        outs = [torch.zeros((n, D.CALL_DT.itemsize), dtype=torch.uint8, device="cuda") for _ in range(nb)]
+        h_nc = torch.full((nb,), -1, dtype=torch.int64).pin_memory()
+        torch.cuda.synchronize()
+        for i in range(nb):
+            pipe.submit(bufs[i], n, outs[i], n, h_nc.data_ptr() + 8 * i)
+        st = pipe.sync()
+        got = h_nc.tolist()
+        assert st["n_sites"] == n * nb and st["n_calls"] == sum(got)
+        for i in range(nb):
+            assert outs[i][:got[i]].cpu().numpy().tobytes() == want[i], i
