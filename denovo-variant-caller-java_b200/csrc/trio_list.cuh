@@ -377,8 +377,6 @@ static int launch_trio_list(dnv_ctx* ctx, const void* d_counts, int64_t n, int64
   int per_sm = 1;
   DNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kListThreads, smem));
   if (per_sm < 1) per_sm = 1;
-  static const int max_per_sm = getenv("DNV_LIST_CTAS_PER_SM") ? atoi(getenv("DNV_LIST_CTAS_PER_SM")) : 0;  // tuning knob
-  if (max_per_sm > 0 && per_sm > max_per_sm) per_sm = max_per_sm;
   const int64_t want = (n + kListThreads - 1) / kListThreads;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sms * per_sm));
   const uint32_t n_tiles = (uint32_t)((n + kScreenSites - 1) / kScreenSites);

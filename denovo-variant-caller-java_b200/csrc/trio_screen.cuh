@@ -37,9 +37,6 @@
 
 namespace dnv {
 
-#ifndef DNV_SCREEN_MINB
-#define DNV_SCREEN_MINB 4
-#endif
 constexpr int kScreenThreads = 256;
 constexpr int kScreenWarps = kScreenThreads / 32;
 constexpr int kScreenBufs = 2;  // tile buffers per warp, refilled as soon as their tile sits in registers
@@ -149,7 +146,7 @@ __host__ __device__ __forceinline__ uint32_t screen_range_lo(uint32_t g, uint32_
 }
 
 template <bool kU8>
-__global__ void __launch_bounds__(kScreenThreads, DNV_SCREEN_MINB)
+__global__ void __launch_bounds__(kScreenThreads, 4)
 trio_screen_kernel(const unsigned char* __restrict__ counts, int64_t n, const ScreenConsts k,
                    uint32_t* __restrict__ list, uint32_t* __restrict__ wcount) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -295,12 +292,8 @@ static int screen_grid(dnv_ctx* ctx, int64_t n, size_t* smem_out) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
   constexpr int kTile = kScreenSites * (kU8 ? 12 : 24);
-  size_t smem = (size_t)kScreenWarps * kScreenBufs * kTile + kScreenWarps * kScreenBufs * 8 +
-                (size_t)kScreenWarps * 2 * kScreenRing * 4;
-  // tuning knob: request at least this much shared memory per CTA (fewer, fatter CTAs per SM leave room
-  // for another context's list kernel to run beside the screen)
-  static const int min_smem_kb = getenv("DNV_SCREEN_SMEM_KB") ? atoi(getenv("DNV_SCREEN_SMEM_KB")) : 0;
-  if ((size_t)min_smem_kb * 1024 > smem) smem = (size_t)min_smem_kb * 1024;
+  const size_t smem = (size_t)kScreenWarps * kScreenBufs * kTile + kScreenWarps * kScreenBufs * 8 +
+                      (size_t)kScreenWarps * 2 * kScreenRing * 4;
   auto kern = trio_screen_kernel<kU8>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
   int per_sm = 1;
