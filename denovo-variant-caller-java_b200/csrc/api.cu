@@ -227,6 +227,10 @@ static int infer_device_async_impl(dnv_ctx* ctx, const void* d_counts, int bps, 
     set_error("dnv_infer_counts_device_async: invalid argument");
     return DNV_E_INVALID;
   }
+  if (reinterpret_cast<uintptr_t>(d_counts) & (bps == 24 ? 7 : 3)) {  // the kernels read sites as 8- / 4-byte words
+    set_error("d_counts must be 8-byte aligned (uint16 layout) or 4-byte aligned (uint8 layout)");
+    return DNV_E_INVALID;
+  }
   if (ctx->n_async >= 64) {
     set_error("dnv_infer_counts_device_async: 64 batches in flight, call dnv_sync first");
     return DNV_E_INVALID;
@@ -263,6 +267,10 @@ static int infer_device_impl(dnv_ctx* ctx, const void* d_counts, int bps, int64_
                              dnv_call* d_calls, int64_t cap, int64_t* n_calls) {
   if (!ctx || !n_calls || n < 0 || cap < 0 || (n > 0 && !d_counts) || (cap > 0 && !d_calls)) {
     set_error("dnv_infer_counts_device: invalid argument");
+    return DNV_E_INVALID;
+  }
+  if (reinterpret_cast<uintptr_t>(d_counts) & (bps == 24 ? 7 : 3)) {  // the kernels read sites as 8- / 4-byte words
+    set_error("d_counts must be 8-byte aligned (uint16 layout) or 4-byte aligned (uint8 layout)");
     return DNV_E_INVALID;
   }
   DNV_CUDA(cudaSetDevice(ctx->device));

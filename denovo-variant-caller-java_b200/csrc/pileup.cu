@@ -64,6 +64,11 @@ int dnv_pileup_device(dnv_ctx* ctx, const int64_t* d_read_start, const int64_t* 
     return DNV_E_INVALID;
   }
   if (n_sites == 0) return DNV_OK;
+  if ((reinterpret_cast<uintptr_t>(d_counts_out) & 7) || (reinterpret_cast<uintptr_t>(d_read_start) & 7) ||
+      (reinterpret_cast<uintptr_t>(d_base_off) & 7) || (reinterpret_cast<uintptr_t>(d_site_pos) & 7)) {
+    set_error("dnv_pileup_device: counts, read_start, base_off and site_pos must be 8-byte aligned");
+    return DNV_E_INVALID;
+  }
   DNV_CUDA(cudaSetDevice(ctx->device));
   int rc = ensure_scratch(ctx, 64);
   if (rc) return rc;

@@ -176,7 +176,8 @@ int dnv_infer_counts(dnv_ctx *ctx, const uint16_t *counts, int64_t n,
                      dnv_site_result *dense, dnv_call *calls, int64_t cap,
                      int64_t *n_calls);
 /* Same with DEVICE buffers already resident in HBM (d_dense may be NULL); d_calls must be
- * 16-byte aligned (any cudaMalloc pointer is).
+ * 16-byte aligned and d_counts 8-byte aligned (any cudaMalloc pointer is; a 16-byte aligned
+ * d_counts also enables the bulk-copy path).
  * n_calls is a host pointer.  Runs on the ctx's own stream and synchronises it. */
 int dnv_infer_counts_device(dnv_ctx *ctx, const uint16_t *d_counts, int64_t n,
                             dnv_site_result *d_dense, dnv_call *d_calls,

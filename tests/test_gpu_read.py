@@ -372,3 +372,34 @@ def test_batch_pipeline_two_contexts_matches_single_engine():
         assert st["n_sites"] == n * nb and st["n_calls"] == sum(got)
         for i in range(nb):
             assert outs[i][:got[i]].cpu().numpy().tobytes() == want[i], i
+
+
+def test_device_entry_points_reject_bad_arguments():
+    """Misaligned device pointers, a missing count slot and too many batches in flight fail with
+    DNV_E_INVALID and a message; the context stays usable."""
+    import ctypes as C
+    import torch
+    from denovo_b200 import _lib as L
+    n = 1000
+    with D.TrioEngine() as eng:
+        c = torch.zeros((n + 1, 12), dtype=torch.int16, device="cuda")
+        calls = torch.zeros((n + 1, D.CALL_DT.itemsize), dtype=torch.uint8, device="cuda")
+        h_nc = torch.zeros(1, dtype=torch.int64).pin_memory()
+        nc = C.c_int64(0)
+        lib = eng.lib
+        assert lib.dnv_infer_counts_device(eng._h, C.c_void_p(c.data_ptr() + 2), n, None, C.c_void_p(calls.data_ptr()), n,
+                                           C.byref(nc)) == D.DNV_E_INVALID
+        assert b"aligned" in lib.dnv_last_error()
+        assert lib.dnv_infer_counts_device(eng._h, C.c_void_p(c.data_ptr()), n, None, C.c_void_p(calls.data_ptr() + 8), n,
+                                           C.byref(nc)) == D.DNV_E_INVALID
+        assert b"16-byte" in lib.dnv_last_error()
+        assert lib.dnv_infer_counts_device_async(eng._h, C.c_void_p(c.data_ptr()), n, C.c_void_p(calls.data_ptr()), n,
+                                                 None) == D.DNV_E_INVALID
+        for i in range(64):
+            eng.infer_device_async(c, n, calls, n, h_nc)
+        with pytest.raises(D.DenovoError) as ei:
+            eng.infer_device_async(c, n, calls, n, h_nc)
+        assert ei.value.code == D.DNV_E_INVALID and "dnv_sync" in str(ei.value)
+        eng.sync()
+        assert eng.stats()["n_sites"] == 64 * n
+        assert eng.infer_device(c, n, calls, n) == 0  # all-zero pileups: nothing is called
