@@ -155,7 +155,8 @@ def main():
     ap.add_argument("--method", default="BAYES")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-screen", action="store_true", help="evaluate every site with the fused FP64 kernel")
-    ap.add_argument("--single-context", action="store_true", help="one context / one stream instead of the two-context pipeline")
+    ap.add_argument("--contexts", type=int, default=4, help="contexts (each on its own stream) the batches are fed to in turn")
+    ap.add_argument("--single-context", action="store_true", help="same as --contexts 1")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -180,12 +181,13 @@ def main():
     K, W = args.steps, max(args.warmup, 3)
 
     # eng: the context used for generation, kernel timing (event brackets) and the host-API leg;
-    # pipe: two untimed contexts on two streams, fed alternately — the production way to walk a stream of
-    # batches (the latency-bound list kernel of one batch runs beside the bandwidth-bound screen of the next)
+    # pipe: `depth` untimed contexts, each on its own stream, fed in turn — the production way to walk a stream
+    # of batches (the latency-bound list / finish kernels of one batch run beside the bandwidth-bound screen of
+    # the next ones)
     eng = D.TrioEngine(EPS, MU, LRT, args.method, device=local, time_kernels=True, no_screen=args.no_screen)
     stream = torch.cuda.Stream(device=local)          # main stream: timing events, inter-GPU barrier
     eng.set_stream(stream.cuda_stream)
-    depth = 1 if args.single_context else 2
+    depth = 1 if args.single_context else max(1, args.contexts)
     pstreams = [torch.cuda.Stream(device=local) for _ in range(depth)]
     pipe = D.BatchPipeline(depth=depth, streams=[st.cuda_stream for st in pstreams], seq_err_rate=EPS,
                            denovo_mut_rate=MU, lrt_threshold=LRT, method=args.method, device=local,
@@ -256,7 +258,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    run_steps(W)
+    run_steps(max(W, 2 * depth))  # every context allocates its scratch on its first batch: all of them warm up
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
@@ -386,7 +388,8 @@ def main():
                        "sites_per_gpu": n, "l2": "input 240 MB per pass > 126 MB L2 (no flush needed)",
                        "calls_per_step": int(total_calls), "hard_sites_per_step": int(n_hard),
                        "step": "asynchronous batches (dnv_infer_counts_device_async) fed alternately to %d contexts on %d streams, one dnv_sync per %d steps; kernel times from a separate timed context" % (depth, depth, GROUP),
-                       "ms_per_step_synchronous_api": sync_ms},
+                       "ms_per_step_synchronous_api": sync_ms, "contexts": depth,
+                       "warmup_steps_run": max(W, 2 * depth)},
             "e2e": {"value": e2e_value, "unit": "sites/s", "h2d_bytes_per_step": n * (12 if u8 else 24),
                     "input_format": "uint8 counts, 12 B/site (dnv_infer_counts8)" if u8 else "uint16 counts, 24 B/site",
                     "d2h_bytes_per_step": int(e2e_calls) * D.CALL_DT.itemsize + 64, "steps": Ke,

@@ -38,7 +38,9 @@ print("rc", eng.lib.dnv_debug_list_trace(eng._h, out.ctypes.data_as(C.c_void_p),
 t = out[:, :6].astype(np.int64)
 t0 = t[:, 0].min()
 rel = (t - t0) / 1000.0
-names = ["start", "prologue_done", "trip1_compute_done", "loop_done", "barrier_done", "end"]
+names = ["start", "prologue_done", "first_tile_compute_done", "loop_done", None, "end"]
 for i, nm in enumerate(names):
+    if nm is None:
+        continue
     col = rel[:, i]
     print("%-20s min %7.2f  med %7.2f  max %7.2f us" % (nm, col.min(), np.median(col), col.max()))

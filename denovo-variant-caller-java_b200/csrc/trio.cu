@@ -1,10 +1,11 @@
 // trio.cu — READ-mode pipeline on one chunk of sites resident in HBM.
 //
-// Calls only (the BASELINE workload; BAYES / LRT, and MAP through the same screen) — two kernels:
+// Calls only (the BASELINE workload; BAYES / LRT, and MAP through the same screen) — three kernels:
 //   S   trio_screen_kernel (trio_screen.cuh): exact integer screen of EVERY site at HBM speed; the
 //         ~1 % it cannot prove non-de-novo leave as per-warp sorted segments
-//   L   trio_list_kernel (trio_list.cuh, cooperative): fused FP64 likelihood + posterior on those
-//         sites, order-preserving compaction (decoupled look-back), dnv_call records
+//   L   trio_list_kernel (trio_list.cuh): fused FP64 likelihood + posterior on those sites,
+//         order-preserving compaction (decoupled look-back), records staged in input order
+//   F   trio_calls_finish_kernel: one thread per call completes the record (exact MAP sweep)
 //
 // Dense output, DNV_F_NO_SCREEN, DNV_F_FORCE_DIRECT, parameters outside the screen's validity — three kernels:
 //   K1  trio_fast_kernel (trio_fast.cuh) or trio_direct_all_kernel: counts -> decision bit per site
@@ -268,8 +269,8 @@ int launch_trio_chunk(dnv_ctx* ctx, const void* d_counts, int64_t site_base, int
     trio_direct_all_kernel<<<grid, kExactThreads, 0, st>>>(ctx->d_tab, d_counts, ctx->count_bytes, n, ctx->d_bits, d_dense,
                                                           ctx->d_counters);
   } else if (screen) {
-    // calls only: exact integer screen at HBM speed, then ONE kernel for the sites it could
-    // not decide (fused FP64 posterior, ordered compaction, call records)
+    // calls only: exact integer screen at HBM speed, then the list kernel for the sites it could not decide
+    // (fused FP64 posterior, ordered compaction) and the per-call finish kernel
     ScreenConsts sk;
     sk.c_hom = ctx->h_tab.c_hom_fx;
     sk.c_het = ctx->h_tab.c_het_fx;
@@ -290,7 +291,7 @@ int launch_trio_chunk(dnv_ctx* ctx, const void* d_counts, int64_t site_base, int
     if (rc) return rc;
     if (timed) DNV_CUDA(cudaEventRecord(ctx->ev_k1[ctx->n_timed++], st));
     ctx->calls_slot = out_slot;
-    ctx->stats.n_launches += 2;
+    ctx->stats.n_launches += 3;
     ctx->screened = true;
     return DNV_OK;
   } else {

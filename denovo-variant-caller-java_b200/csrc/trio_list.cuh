@@ -1,4 +1,4 @@
-// trio_list.cuh — the tail of the screened READ pipeline in ONE kernel.
+// trio_list.cuh — the tail of the screened READ pipeline: the list kernel and the finish kernel.
 //
 // Input: the sites the integer screen (trio_screen.cuh) could not decide, as per-warp sorted
 // segments of `list` plus their lengths wcount[] — concatenated in warp order they are the
@@ -10,16 +10,17 @@
 //      the exact direct form (trio_exact.cuh: exact_site_warp);
 //   2. an order-preserving compaction of the called sites across the grid (tiles of 128 list
 //      items handed out by ticket, decoupled look-back over the tile totals), so that the
-//      thread that decided a site writes its dnv_call record straight to its final,
-//      input-ordered position: site, counts, p / LR / log-likelihoods from the linear form
-//      (everything, from the exact evaluation, for hard sites);
-//   3. after a grid-wide barrier (cooperative launch: every CTA is resident), ONE THREAD PER
-//      CALL completes the record with the exact pruned log-domain sweep (MAP triple, max_ll).
-//      (MAP method, kMap: the roles swap — the sweep is the decision of phase 1 and phase 2 adds
-//      p / LR / log-likelihoods from the linear form.)
+//      thread that decided a site stages its dnv_call record at its final, input-ordered index
+//      (local HBM): site, counts, p / LR / log-likelihoods from the linear form (everything,
+//      from the exact evaluation, for hard sites);
+//   3. trio_calls_finish_kernel, ONE THREAD PER CALL, completes the record with the exact pruned
+//      log-domain sweep (MAP triple, max_ll) and writes it to the caller's buffer.
+//      (MAP method, kMap: the roles swap — the sweep is the decision of the list kernel and the
+//      finish kernel adds p / LR / log-likelihoods from the linear form.)
 //      Called sites are ~1 in 5 of the list, so doing this densely instead of inside the
-//      divergent decision loop takes the sweep off every warp's critical path.
-// No decision bitmap, no separate compaction or record kernels, no sort.
+//      divergent decision loop takes the sweep off every warp's critical path; as a second,
+//      small kernel it also frees most SMs early for whatever runs next (BatchPipeline).
+// No decision bitmap, no separate compaction kernel, no sort, no grid-wide barrier.
 //
 // Replaces, for the ~1 % of sites that need it, BayesInfer.infer -> performInference ->
 // isDenovo (M/BayesInfer.java:50-69, M/DenovoBayesNet.java:247-289, M/DenovoUtil.java:261-288)
@@ -44,12 +45,13 @@ struct ListShared {
   uint32_t woff[kScreenMaxWarps + 1];  // exclusive scan of wcount[]
   uint32_t part[kListWarps];
   int warp_sum[kListWarps];
+  unsigned int ticket[2];  // next tile, handed from thread 0 to the CTA (double buffered by trip parity)
   unsigned long long excl;
 };
 
 // counters: [in_slot] calls before this chunk, [out_slot] <- calls after it, [1] += undecided sites,
-//           [4] += hard sites, [7] barrier arrivals, [5] CTAs gone (the last CTA to leave resets
-//           both for the next launch).
+//           [4] += hard sites, [6] tile ticket, [5] CTAs gone (the last CTA to leave resets both for
+//           the next launch).
 // status word: [63:34] epoch of this launch, [33:32] 1 = tile aggregate, 2 = inclusive prefix, [31:0] value.
 template <bool kU8, bool kMap>
 __global__ void __launch_bounds__(kListThreads, 3)
@@ -57,7 +59,7 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
                  int64_t n, int64_t site_base, const uint32_t* __restrict__ list, const uint32_t* __restrict__ wcount,
                  uint32_t n_warps, uint32_t range_base, uint32_t range_rem, unsigned long long* status,
                  unsigned long long epoch, unsigned long long* counters, int in_slot, int out_slot,
-                 dnv_call* __restrict__ calls, int64_t cap, int64_t* count_out, dnv_call* __restrict__ stage) {
+                 int64_t cap, int64_t* count_out, dnv_call* __restrict__ stage) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ListShared& s = *reinterpret_cast<ListShared*>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -69,6 +71,9 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
   auto stamp = [&](int) {};
 #endif
   stamp(0);
+  // the first tile is claimed before the prologue: by the time any CTA asks for its second tile, every
+  // running CTA holds a first one, so tile order stays close to processing order (short look-back waits)
+  if (threadIdx.x == 0) s.ticket[0] = (unsigned int)atomicAdd(&counters[6], 1ull);
 
   // Prologue: every global load is issued before the first one is consumed (one round trip, not a
   // dependent chain): wcount[] (coalesced, kScreenMaxWarps / kListThreads words per thread) and this
@@ -143,10 +148,10 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
   const GmemPow pw{tab};
   stamp(1);
 
-  // Tiles are dealt statically (tile = blockIdx.x + trip * gridDim.x): every CTA is resident (cooperative
-  // launch), so the look-back below always finds its predecessors running.  The inputs of the next
-  // trip (list entry -> site -> packed counts, two dependent global loads) are requested before this
-  // trip's arithmetic starts.
+  // Tiles are handed out by ticket, in increasing order, to CTAs that are running: the look-back below
+  // therefore only ever waits for tiles held by running CTAs (no co-residency assumption).  A CTA claims
+  // its next tile at the start of each trip and requests that tile's inputs (list entry -> site ->
+  // packed counts, two dependent global loads) while the current tile is still being finished.
   auto fetch_site = [&](uint32_t tile) -> uint32_t {
     const uint32_t item = tile * kListThreads + threadIdx.x;
     if (tile >= n_tiles || item >= total_items) return 0u;  // dead lanes read site 0 (harmless) and are masked by `live`
@@ -162,20 +167,22 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
 #pragma unroll
     for (int q = 0; q < kBps / 4; q++) words[q] = __ldg(src + q);
   };
-  // two-deep software pipeline: list entries are requested two trips ahead, packed counts one trip ahead
-  uint32_t site_cur = fetch_site(blockIdx.x), site_nxt = fetch_site(blockIdx.x + gridDim.x);
+  uint32_t tile = s.ticket[0];  // written before the prologue's barriers
+  uint32_t site_cur = fetch_site(tile), site_nxt = 0;
   uint32_t words_cur[kBps / 4];
   fetch_counts(site_cur, words_cur);
-  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  bool first_trip = true;
+  int trip = 0;
+  while (tile < n_tiles) {
+    trip ^= 1;
+    if (threadIdx.x == 0) s.ticket[trip] = (unsigned int)atomicAdd(&counters[6], 1ull);  // read after this trip's first barrier
     const uint32_t item = tile * kListThreads + threadIdx.x;
     const bool live = item < total_items;
     const uint32_t site = site_cur;
     int c[12];
     if (kU8) unpack_counts8(words_cur, c);
     else unpack_counts(reinterpret_cast<const uint2*>(words_cur), c);
-    site_cur = site_nxt;
-    site_nxt = fetch_site(tile + 2 * gridDim.x);
-    fetch_counts(site_cur, words_cur);
+
     LinOut lo_;
     lo_.hard = false; lo_.dn = false; lo_.zd = lo_.zm = 2; lo_.den_s = lo_.men_s = lo_.s2 = 0.0;
     bool dn = false;
@@ -219,11 +226,14 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
         }
       }
     }
-    if (tile == blockIdx.x) stamp(2);
+    if (first_trip) stamp(2);
+    first_trip = false;
     // order-preserving rank of the called sites inside the tile
     const uint32_t dw = __ballot_sync(0xffffffffu, dn);
-    __syncthreads();  // s.warp_sum / s.excl of the previous trip are no longer read
+    __syncthreads();  // s.warp_sum / s.excl of the previous trip are no longer read; s.ticket is written
     if (lane == 0) s.warp_sum[warp] = __popc(dw);
+    const uint32_t tile_nxt = s.ticket[trip];
+    site_nxt = fetch_site(tile_nxt);  // the list entry of my item in the next tile: in flight during the look-back
     __syncthreads();
     int warp_off = 0, total = 0;
 #pragma unroll
@@ -262,8 +272,10 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
         }
       }
     }
-    if (total == 0) continue;  // block-uniform
-    __syncthreads();
+    if (total != 0) __syncthreads();  // block-uniform: s.excl is published
+    site_cur = site_nxt;
+    fetch_counts(site_cur, words_cur);  // next tile's counts: in flight while this tile's records are staged
+    if (total != 0) {
     if (dn) {
       const unsigned long long pos = calls_before + s.excl + (unsigned long long)(warp_off + __popc(dw & ((1u << lane) - 1u)));
       if (pos < (unsigned long long)cap) {
@@ -287,28 +299,49 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
 #pragma unroll
         for (int q = 0; q < 12; q++) o.counts[q] = (uint16_t)c[q];
         o.is_denovo = 1;
-        stage[pos - calls_before] = o;  // local scratch; phase 2 completes it and writes the caller's buffer once
+        stage[pos - calls_before] = o;  // local scratch; trio_calls_finish_kernel completes it and writes the caller's buffer
       }
     }
+    }
+    tile = tile_nxt;
   }
-
-  // ---- grid-wide barrier: every record of phase 1 and the call total are now in global memory
-  __syncthreads();
   stamp(3);
+  __syncthreads();
+  stamp(5);
+  // the last CTA to leave resets the ticket for the next launch (every ticket has been taken by then)
   if (threadIdx.x == 0) {
     __threadfence();
-    atomicAdd(&counters[7], 1ull);
-    while (*(volatile unsigned long long*)&counters[7] < (unsigned long long)gridDim.x) {}
-    __threadfence();
+    if (atomicAdd(&counters[5], 1ull) == (unsigned long long)gridDim.x - 1ull) {
+      counters[5] = 0;
+      counters[6] = 0;
+    }
   }
-  __syncthreads();
+}
 
-  stamp(4);
-  // ---- phase 2: one thread per call, exact pruned MAP sweep (bit-identical to the reference's argmax)
+// One thread per call: completes the records staged by trio_list_kernel and writes them, whole, to the
+// caller's buffer.  Call j goes to CTA j % gridDim.x so that every SM gets the same share.
+struct FinishShared {
+  double rel[1000];
+  double rmax[110];
+  uint32_t isden[32];
+};
+
+template <bool kMap>
+__global__ void __launch_bounds__(kListThreads)
+trio_calls_finish_kernel(const Tables* __restrict__ tab, const FastConsts k, unsigned long long* __restrict__ counters,
+                         int in_slot, int out_slot, const dnv_call* __restrict__ stage, dnv_call* __restrict__ calls,
+                         int64_t cap) {
+  const unsigned long long calls_before = counters[in_slot];
+  unsigned long long all = counters[out_slot];
+  if (all > (unsigned long long)cap) all = (unsigned long long)cap;
+  if (calls_before + blockIdx.x >= all) return;  // block-uniform: this CTA has no call
+  __shared__ FinishShared s;
+  stage_exact_tables(tab, s.rel, s.isden);
+  stage_map_bounds(tab, s.rmax);
+  __syncthreads();
+  const GmemPow pw{tab};
+  (void)pw;
   {
-    unsigned long long all = *(volatile unsigned long long*)&counters[out_slot];
-    if (all > (unsigned long long)cap) all = (unsigned long long)cap;
-    // call j goes to CTA j % gridDim.x: every SM gets the same share of the sweep
     for (unsigned long long pos = calls_before + (unsigned long long)threadIdx.x * gridDim.x + blockIdx.x; pos < all;
          pos += (unsigned long long)gridDim.x * kListThreads) {
       // 80-byte record as five 16-byte words: read from the local scratch, written once to the caller's
@@ -355,15 +388,6 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
       for (int i = 0; i < 5; i++) dst[i] = u.v[i];
     }
   }
-  __syncthreads();
-  stamp(5);
-  // the last CTA to leave resets the barrier for the next launch
-  if (threadIdx.x == 0) {
-    if (atomicAdd(&counters[5], 1ull) == (unsigned long long)gridDim.x - 1ull) {
-      counters[5] = 0;
-      counters[7] = 0;
-    }
-  }
 }
 
 template <bool kU8, bool kMap>
@@ -394,17 +418,15 @@ static int launch_trio_list(dnv_ctx* ctx, const void* d_counts, int64_t n, int64
     DNV_CUDA(cudaMalloc(&ctx->d_list_stage, (size_t)need * sizeof(dnv_call)));
     ctx->list_stage_cap = need;
   }
-  // cooperative launch: the in-kernel barrier needs every CTA resident (grid <= sms * per_sm by construction)
-  const Tables* a_tab = ctx->d_tab;
-  FastConsts a_k = make_fast_consts(ctx->h_tab);
-  const unsigned char* a_counts = (const unsigned char*)d_counts;
-  const uint32_t* a_list = ctx->d_list;
-  const uint32_t* a_wcount = ctx->d_wcount;
-  uint32_t a_base = n_tiles / n_warps, a_rem = n_tiles % n_warps, a_warps = n_warps;
-  unsigned long long a_epoch = ++ctx->epoch;
-  void* args[] = {&a_tab, &a_k, &a_counts, &n, &site_base, &a_list, &a_wcount, &a_warps, &a_base, &a_rem,
-                  &ctx->d_tile_status, &a_epoch, &ctx->d_counters, &in_slot, &out_slot, &d_calls, &cap, &ctx->count_out, &ctx->d_list_stage};
-  DNV_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(kListThreads), args, smem, ctx->stream));
+  const FastConsts fk = make_fast_consts(ctx->h_tab);
+  kern<<<grid, kListThreads, smem, ctx->stream>>>(ctx->d_tab, fk, (const unsigned char*)d_counts, n, site_base, ctx->d_list,
+                                                  ctx->d_wcount, n_warps, n_tiles / n_warps, n_tiles % n_warps,
+                                                  ctx->d_tile_status, ++ctx->epoch, ctx->d_counters, in_slot, out_slot, cap,
+                                                  ctx->count_out, ctx->d_list_stage);
+  // one thread per call; CTAs beyond the number of calls leave at once
+  const int fgrid = (int)std::max<int64_t>(1, std::min<int64_t>((need + kListThreads - 1) / kListThreads, (int64_t)sms * 2));
+  trio_calls_finish_kernel<kMap><<<fgrid, kListThreads, 0, ctx->stream>>>(ctx->d_tab, fk, ctx->d_counters, in_slot, out_slot,
+                                                                          ctx->d_list_stage, d_calls, cap);
   DNV_CUDA(cudaGetLastError());
   return DNV_OK;
 }
