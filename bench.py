@@ -24,7 +24,7 @@ METRIC = "trio candidate sites/sec (READ-mode BAYES, 30x)"
 SITES_PER_GPU = 10_000_000
 SEED = 0x5EED0003
 DEPTH, EPS, MU, LRT = 30, 1e-2, 1e-8, 1.0
-GROUP = 32  # asynchronous steps per host synchronisation (and per inter-GPU barrier)
+GROUP = 64  # asynchronous steps per host synchronisation (and per inter-GPU barrier); <= 64 per context
 # ALGORITHMIC work per site:
 #   integer screen (dominant kernel, HBM-bound): 24 B of counts in + 1 bit of decision out
 #   list kernel (only the sites the screen cannot decide): sparse factored FP64 form, FMA = 2
@@ -220,6 +220,9 @@ def main():
     counts_ptr = d_counts.data_ptr()
     calls_ptrs = [t.data_ptr() for t in d_calls]
     nc_ptrs = [h_nc.data_ptr() + 8 * i for i in range(64)]
+    if peer:  # per-generation destinations in rank 0's HBM, computed once
+        rec_ptrs = [peer.records_ptr(i) for i in range(GROUP)]
+        cnt_ptrs = [peer.count_ptr(i) for i in range(GROUP)]
 
     def join():
         """The main stream waits for both pipeline streams (no host synchronisation)."""
@@ -240,7 +243,7 @@ def main():
             else:
                 for i in range(m):
                     if peer:
-                        pipe.submit(counts_ptr, n, peer.records_ptr(i), cap, peer.count_ptr(i))
+                        pipe.submit(counts_ptr, n, rec_ptrs[i], cap, cnt_ptrs[i])
                     else:
                         pipe.submit(counts_ptr, n, calls_ptrs[i % depth], cap, nc_ptrs[i])
                 if peer:
@@ -337,7 +340,7 @@ def main():
     # ---- roofline of the dominant kernel
     fp64_peak, _ = eng.measure_fp64_peak()
     hbm_peak, peak_src = load_peaks()
-    k_ms = fused_ms / K          # both kernels of a step: integer screen + list kernel
+    k_ms = fused_ms / K          # the kernels of a step: integer screen + list kernel + finish kernel
     s_ms = screen_ms / K         # the screen alone
     if s_ms > 0:
         # BAYES/LRT: the integer screen streams every site's counts and is the dominant kernel (HBM-bound)
@@ -347,13 +350,13 @@ def main():
         ach_tf = FLOP_PER_SITE * n_fp64 / (f_ms * 1e-3) / 1e12
         roofline = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                     "traffic": NCU_TRAFFIC_BYTES_PER_SITE * n, "kernel": "trio_screen_kernel", "kernel_ms": s_ms,
-                    # share of the step's kernel time (screen + list kernel, each timed alone on the timed
+                    # share of the step's kernel time (screen + list + finish kernel, timed alone on the timed
                     # context: comparable with the serialised ncu launch list); the value loop overlaps the
                     # list kernel of one batch with the screen of the next, so ms_per_step < their sum
                     "kernel_share_of_step": s_ms / k_ms, "step_kernels_ms": k_ms, "bytes_per_site": BYTES_PER_SITE,
                     "peak_source": peak_src,
                     "sites_decided_by_screen": int(screened_out), "sites_to_fp64_kernel": int(n_fp64),
-                    "fp64_kernel": {"kernel": "trio_list_kernel (fused FP64 posterior + ordered compaction + call records)", "kernel_ms": f_ms, "sites": int(n_fp64),
+                    "fp64_kernel": {"kernel": "trio_list_kernel + trio_calls_finish_kernel (fused FP64 posterior, ordered compaction, call records)", "kernel_ms": f_ms, "sites": int(n_fp64),
                                     "flop_per_site": FLOP_PER_SITE, "achieved_tflops": ach_tf,
                                     "fp64_peak_tflops": fp64_peak,
                                     "peak_source": "dependent-free DFMA chains on all SMs, measured in this run"}}

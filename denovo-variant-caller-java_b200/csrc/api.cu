@@ -97,6 +97,8 @@ int dnv_create(const dnv_params* p, dnv_ctx** out) {
   ctx->prm = *p;
   ctx->device = p->device;
   build_tables(*p, &ctx->h_tab);
+  ctx->sms = 148;
+  cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, p->device);
   DNV_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
   ctx->stream = ctx->own_stream;
   if (p->flags & DNV_F_TIME_KERNELS)

@@ -80,6 +80,10 @@ struct dnv_ctx {
   void* d_scratch;
   size_t scratch_bytes;
   dnv_stats stats;
+  // launch configuration, queried once per context (attribute and occupancy calls are not free on the host)
+  int sms;                  // multiprocessors of the device
+  int screen_per_sm[2];     // resident CTAs per SM of trio_screen_kernel<u16 / u8>, 0 = not queried yet
+  int list_per_sm[2][2];    // ... of trio_list_kernel<u16 / u8><BAYES-LRT / MAP>
   // asynchronous batches (dnv_infer_counts*_device_async): per-batch counters land in a pinned ring
   unsigned long long* h_ring;  // [64][8]
   int n_async;                 // batches enqueued since the last dnv_sync

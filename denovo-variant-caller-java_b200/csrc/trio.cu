@@ -254,8 +254,7 @@ int launch_trio_chunk(dnv_ctx* ctx, const void* d_counts, int64_t site_base, int
   cudaStream_t st = ctx->stream;
   const int64_t n_words = (n + 31) / 32;
   const int n_blocks = (int)((n_words + kCompactThreads - 1) / kCompactThreads);
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  const int sms = ctx->sms;
 
   const bool direct = (ctx->prm.flags & DNV_F_FORCE_DIRECT) != 0;
   const bool timed = (ctx->prm.flags & DNV_F_TIME_KERNELS) != 0 && ctx->n_timed < 64;

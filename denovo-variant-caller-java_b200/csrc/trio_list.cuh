@@ -393,14 +393,16 @@ trio_calls_finish_kernel(const Tables* __restrict__ tab, const FastConsts k, uns
 template <bool kU8, bool kMap>
 static int launch_trio_list(dnv_ctx* ctx, const void* d_counts, int64_t n, int64_t site_base, int screen_grid_size,
                             int in_slot, int out_slot, dnv_call* d_calls, int64_t cap) {
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  const int sms = ctx->sms;
   const size_t smem = sizeof(ListShared);
   auto kern = trio_list_kernel<kU8, kMap>;
-  DNV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int per_sm = 1;
-  DNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kListThreads, smem));
-  if (per_sm < 1) per_sm = 1;
+  int& per_sm = ctx->list_per_sm[kU8 ? 1 : 0][kMap ? 1 : 0];
+  if (per_sm == 0) {  // first launch on this context
+    DNV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int q = 1;
+    DNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, kListThreads, smem));
+    per_sm = std::max(q, 1);
+  }
   const int64_t want = (n + kListThreads - 1) / kListThreads;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sms * per_sm));
   const uint32_t n_tiles = (uint32_t)((n + kScreenSites - 1) / kScreenSites);

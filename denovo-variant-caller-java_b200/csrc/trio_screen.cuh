@@ -289,15 +289,18 @@ trio_screen_kernel(const unsigned char* __restrict__ counts, int64_t n, const Sc
 // grid of the screen (and so the warp -> tile-range map the list kernel has to reproduce)
 template <bool kU8>
 static int screen_grid(dnv_ctx* ctx, int64_t n, size_t* smem_out) {
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  const int sms = ctx->sms;
   constexpr int kTile = kScreenSites * (kU8 ? 12 : 24);
   const size_t smem = (size_t)kScreenWarps * kScreenBufs * kTile + kScreenWarps * kScreenBufs * 8 +
                       (size_t)kScreenWarps * 2 * kScreenRing * 4;
   auto kern = trio_screen_kernel<kU8>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-  int per_sm = 1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kScreenThreads, smem) != cudaSuccess) return -1;
+  int& per_sm = ctx->screen_per_sm[kU8 ? 1 : 0];
+  if (per_sm == 0) {  // first launch on this context
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    int q = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, kScreenThreads, smem) != cudaSuccess) return -1;
+    per_sm = std::max(q, 1);
+  }
   const int64_t want = ((n + kScreenSites - 1) / kScreenSites + kScreenWarps - 1) / kScreenWarps;
   int64_t grid = std::min<int64_t>(std::max<int64_t>(want, 1), (int64_t)sms * std::max(per_sm, 1));
   grid = std::min<int64_t>(grid, kScreenMaxWarps / kScreenWarps);
