@@ -319,11 +319,14 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
 }
 
 // One thread per call: completes the records staged by trio_list_kernel and writes them, whole, to the
-// caller's buffer.  Call j goes to CTA j % gridDim.x so that every SM gets the same share.
+// caller's buffer.  A warp owns 32 consecutive calls: its records (2560 contiguous bytes) go through shared
+// memory so that both the read of the staged records and the write of the finished ones are coalesced
+// 512-byte accesses — the destination may be a peer GPU's HBM, where scattered 16-byte stores are expensive.
 struct FinishShared {
   double rel[1000];
   double rmax[110];
   uint32_t isden[32];
+  alignas(16) uint4 rec[kListWarps][32 * 5];  // one warp's 32 records
 };
 
 template <bool kMap>
@@ -334,22 +337,33 @@ trio_calls_finish_kernel(const Tables* __restrict__ tab, const FastConsts k, uns
   const unsigned long long calls_before = counters[in_slot];
   unsigned long long all = counters[out_slot];
   if (all > (unsigned long long)cap) all = (unsigned long long)cap;
-  if (calls_before + blockIdx.x >= all) return;  // block-uniform: this CTA has no call
+  if (calls_before + (unsigned long long)blockIdx.x * kListThreads >= all) return;  // block-uniform: no call for this CTA
   __shared__ FinishShared s;
   stage_exact_tables(tab, s.rel, s.isden);
   stage_map_bounds(tab, s.rmax);
   __syncthreads();
   const GmemPow pw{tab};
   (void)pw;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   {
-    for (unsigned long long pos = calls_before + (unsigned long long)threadIdx.x * gridDim.x + blockIdx.x; pos < all;
-         pos += (unsigned long long)gridDim.x * kListThreads) {
-      // 80-byte record as five 16-byte words: read from the local scratch, written once to the caller's
-      // buffer (which may live in a peer GPU's HBM: no read-back over NVLink)
-      union { dnv_call r; uint4 v[5]; } u;
-      const uint4* src = reinterpret_cast<const uint4*>(stage + (pos - calls_before));
+    // warp-uniform loop: the warp's first call, 32 consecutive calls per trip
+    for (unsigned long long w0 = calls_before + (unsigned long long)blockIdx.x * kListThreads + (unsigned long long)warp * 32;
+         w0 < all; w0 += (unsigned long long)gridDim.x * kListThreads) {
+      const int n_rec = (int)min((unsigned long long)32, all - w0);
+      const unsigned long long pos = w0 + lane;
+      // coalesced read of the warp's staged records (local HBM) into shared memory
+      const uint4* src = reinterpret_cast<const uint4*>(stage + (w0 - calls_before));
+      __syncwarp();
 #pragma unroll
-      for (int i = 0; i < 5; i++) u.v[i] = __ldcg(src + i);
+      for (int i = 0; i < 5; i++) {
+        const int q = i * 32 + lane;
+        if (q < n_rec * 5) s.rec[warp][q] = __ldcg(src + q);
+      }
+      __syncwarp();
+      union { dnv_call r; uint4 v[5]; } u;
+#pragma unroll
+      for (int i = 0; i < 5; i++) u.v[i] = s.rec[warp][min(lane, n_rec - 1) * 5 + i];
+      if (lane < n_rec) {
       if (kMap) {
         // values of a MAP call: the factored linear form unless the site is hard (gray zone, deeper than
         // the tables), then the exact direct form in the reference's own order — as call_details_kernel does
@@ -383,9 +397,19 @@ trio_calls_finish_kernel(const Tables* __restrict__ tab, const FastConsts k, uns
         u.r.dad = (uint8_t)(best / 100); u.r.mom = (uint8_t)((best / 10) % 10); u.r.child = (uint8_t)(best % 10);
         u.r.max_ll = max_ll;
       }
-      uint4* dst = reinterpret_cast<uint4*>(calls + pos);
+      }
+      (void)pos;
+      __syncwarp();
 #pragma unroll
-      for (int i = 0; i < 5; i++) dst[i] = u.v[i];
+      for (int i = 0; i < 5; i++) s.rec[warp][lane * 5 + i] = u.v[i];
+      __syncwarp();
+      // coalesced write of the finished records (the caller's buffer, possibly in a peer GPU's HBM)
+      uint4* dst = reinterpret_cast<uint4*>(calls + w0);
+#pragma unroll
+      for (int i = 0; i < 5; i++) {
+        const int q = i * 32 + lane;
+        if (q < n_rec * 5) dst[q] = s.rec[warp][q];
+      }
     }
   }
 }
