@@ -44,7 +44,7 @@ class BatchPipeline:
     A batch is kernels with opposite characters: a bandwidth-bound integer screen over every site, then
     two short latency-bound kernels for the ~1 % it cannot decide.  Several contexts, each on its own
     CUDA stream and fed in turn, let the short kernels of one batch run beside the screens of the next
-    ones (measured on B200, 10 M-site batches: 89 us with one context, 70 with two, 63 with four).  Batches are independent, so nothing else
+    ones (measured on B200, 10 M-site batches: 87 us with one context, 68 with two, 61 with four).  Batches are independent, so nothing else
     changes: every batch writes its own records and call count (dnv_infer_counts_device_async), and
     `sync()` waits for all of them."""
 
