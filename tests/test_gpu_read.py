@@ -12,6 +12,7 @@ import pytest
 
 import denovo_b200 as D
 import oracle_lib as O
+import synth_inputs as S
 
 pytestmark = pytest.mark.gpu
 G = D.GENOTYPES
@@ -261,54 +262,13 @@ def test_async_batches_match_synchronous_calls(method):
         assert outs[0][:k].cpu().numpy().tobytes() == want[0]
 
 
-def _adversarial_counts(rng, n):
-    """Pileups built to sit on the integer screen's decision boundaries: one or two dominant alleles with
-    0..6 stray reads, equal counts (ties between genotypes), depths around the uint8 and power-table
-    limits, empty persons."""
-    c = np.zeros((n, 3, 4), np.int64)
-    kind = rng.integers(0, 8, n)
-    depth = rng.choice([1, 2, 5, 12, 30, 31, 60, 127, 128, 254, 255, 256, 300, 1022, 1023, 1024, 1100, 4000], n)
-    for i in range(n):
-        x, y = rng.choice(4, 2, replace=False)
-        for p in range(3):
-            d = int(depth[i]) if kind[i] != 7 else int(rng.integers(0, 40))
-            k = kind[i]
-            if k == 0:      # everybody homozygous X with a few errors
-                stray = int(rng.integers(0, 7))
-                c[i, p, x] = max(d - stray, 0)
-                c[i, p, rng.integers(0, 4)] += stray
-            elif k == 1:    # one parent het, child anything
-                if p == int(rng.integers(0, 2)):
-                    c[i, p, x] = d // 2; c[i, p, y] = d - d // 2
-                else:
-                    c[i, p, x] = d
-            elif k == 2:    # child het, parents hom: the de novo pattern, with 0..3 alt reads leaking into a parent
-                if p == 2:
-                    a = int(rng.integers(0, d + 1)); c[i, p, x] = d - a; c[i, p, y] = a
-                else:
-                    a = int(rng.integers(0, 4)); c[i, p, x] = max(d - a, 0); c[i, p, y] = min(a, d)
-            elif k == 3:    # exact ties
-                c[i, p, x] = d; c[i, p, y] = d
-            elif k == 4:    # hom-vs-het boundary: n_X * log2 r_hom ~ N * log2 r_het
-                a = int(round(d * rng.uniform(0.08, 0.16))); c[i, p, x] = d - a; c[i, p, y] = a
-            elif k == 5:    # three alleles present
-                parts = rng.multinomial(d, [0.5, 0.3, 0.2]); c[i, p, x] = parts[0]; c[i, p, y] = parts[1]
-                c[i, p, min(set(range(4)) - {int(x), int(y)})] += parts[2]
-            elif k == 6:    # an empty person
-                if p != int(rng.integers(0, 3)):
-                    c[i, p, x] = d
-            else:           # uniform noise
-                c[i, p] = rng.integers(0, 12, 4)
-    return np.minimum(c, 65535).astype(np.uint16)
-
-
 @pytest.mark.parametrize("eps,mu,lrt", [(1e-2, 1e-8, 1.0), (1e-3, 1e-10, 1.0), (1e-1, 1e-6, 0.05), (0.3, 1e-5, 20.0),
                                         (1e-2, 1e-3, 1.0), (2e-2, 1.7e-4, 1.0), (2e-2, 4.5e-5, 1.0)])
 def test_screen_boundaries_against_oracle(eps, mu, lrt):
     """BAYES and LRT on adversarial pileups, for parameters where the integer screen is valid (small mu),
     barely valid (mu = 4.5e-5, just under its limit) and invalid (mu >= 1.7e-4: every site takes the FP64 path)."""
     rng = np.random.default_rng(int(eps * 1e6) + int(-np.log10(mu)))
-    c = _adversarial_counts(rng, 6000)
+    c = S.adversarial_counts(rng, 6000)
     for method in ("BAYES", "LRT"):
         check_against_oracle(c, eps=eps, mu=mu, lrt=lrt, method=method)
 
