@@ -65,6 +65,37 @@ static int ensure_stage(dnv_ctx* ctx, int64_t n, bool dense, int64_t calls_cap) 
   return DNV_OK;
 }
 
+// everything dnv_create allocates; on failure the caller hands the half-built context to dnv_destroy
+static int init_ctx(dnv_ctx* ctx) {
+  const dnv_params* p = &ctx->prm;
+  build_tables(*p, &ctx->h_tab);
+  ctx->sms = 148;
+  cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, p->device);
+  DNV_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+  ctx->stream = ctx->own_stream;
+  if (p->flags & DNV_F_TIME_KERNELS)
+    for (int i = 0; i < 64; i++) {
+      DNV_CUDA(cudaEventCreate(&ctx->ev_k0[i]));
+      DNV_CUDA(cudaEventCreate(&ctx->ev_k1[i]));
+      DNV_CUDA(cudaEventCreate(&ctx->ev_s1[i]));
+    }
+  DNV_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) {
+    DNV_CUDA(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
+    DNV_CUDA(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+  }
+  DNV_CUDA(cudaMalloc(&ctx->d_tab, sizeof(Tables)));
+  DNV_CUDA(cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)));
+  DNV_CUDA(cudaMalloc(&ctx->d_wcount, 8192 * sizeof(uint32_t)));
+  DNV_CUDA(cudaHostAlloc((void**)&ctx->h_ring, 64 * 8 * sizeof(unsigned long long), cudaHostAllocDefault));
+  // the kernels run on non-blocking streams, which do not order against the legacy default stream: the
+  // uploads go through the context's own stream and are complete before dnv_create returns
+  DNV_CUDA(cudaMemcpyAsync(ctx->d_tab, &ctx->h_tab, sizeof(Tables), cudaMemcpyHostToDevice, ctx->own_stream));
+  DNV_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), ctx->own_stream));
+  DNV_CUDA(cudaStreamSynchronize(ctx->own_stream));
+  return DNV_OK;
+}
+
 }  // namespace dnv
 
 using namespace dnv;
@@ -96,28 +127,13 @@ int dnv_create(const dnv_params* p, dnv_ctx** out) {
   memset(ctx, 0, sizeof(*ctx));
   ctx->prm = *p;
   ctx->device = p->device;
-  build_tables(*p, &ctx->h_tab);
-  ctx->sms = 148;
-  cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, p->device);
-  DNV_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
-  ctx->stream = ctx->own_stream;
-  if (p->flags & DNV_F_TIME_KERNELS)
-    for (int i = 0; i < 64; i++) {
-      DNV_CUDA(cudaEventCreate(&ctx->ev_k0[i]));
-      DNV_CUDA(cudaEventCreate(&ctx->ev_k1[i]));
-      DNV_CUDA(cudaEventCreate(&ctx->ev_s1[i]));
-    }
-  DNV_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; i++) {
-    DNV_CUDA(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
-    DNV_CUDA(cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming));
+  const int rc = init_ctx(ctx);
+  if (rc != DNV_OK) {  // nothing leaks on a failed create: dnv_destroy copes with a half-built context
+    const std::string msg = g_last_error;
+    dnv_destroy(ctx);
+    set_error(msg);
+    return rc;
   }
-  DNV_CUDA(cudaMalloc(&ctx->d_tab, sizeof(Tables)));
-  DNV_CUDA(cudaMemcpy(ctx->d_tab, &ctx->h_tab, sizeof(Tables), cudaMemcpyHostToDevice));
-  DNV_CUDA(cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)));
-  DNV_CUDA(cudaMemset(ctx->d_counters, 0, 8 * sizeof(unsigned long long)));
-  DNV_CUDA(cudaMalloc(&ctx->d_wcount, 8192 * sizeof(uint32_t)));
-  DNV_CUDA(cudaHostAlloc((void**)&ctx->h_ring, 64 * 8 * sizeof(unsigned long long), cudaHostAllocDefault));
   *out = ctx;
   return DNV_OK;
 }
@@ -125,19 +141,24 @@ int dnv_create(const dnv_params* p, dnv_ctx** out) {
 int dnv_destroy(dnv_ctx* ctx) {
   if (!ctx) return DNV_OK;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
-  cudaStreamSynchronize(ctx->copy_stream);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   cudaFree(ctx->d_tab); cudaFree(ctx->d_bits); cudaFree(ctx->d_tile_status); cudaFree(ctx->d_list);
   cudaFree(ctx->d_call_idx); cudaFree(ctx->d_counters); cudaFree(ctx->d_wcount); cudaFree(ctx->d_list_stage); cudaFree(ctx->d_stage_calls); cudaFree(ctx->d_scratch);
   for (int i = 0; i < 2; i++) {
     cudaFree(ctx->d_stage_counts[i]); cudaFree(ctx->d_stage_dense[i]);
-    cudaEventDestroy(ctx->ev_h2d[i]); cudaEventDestroy(ctx->ev_done[i]);
+    if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
+    if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
   }
-  if (ctx->prm.flags & DNV_F_TIME_KERNELS)
-    for (int i = 0; i < 64; i++) { cudaEventDestroy(ctx->ev_k0[i]); cudaEventDestroy(ctx->ev_k1[i]); cudaEventDestroy(ctx->ev_s1[i]); }
-  cudaStreamDestroy(ctx->own_stream);
-  cudaStreamDestroy(ctx->copy_stream);
-  cudaFreeHost(ctx->h_ring);
+  for (int i = 0; i < 64; i++) {
+    if (ctx->ev_k0[i]) cudaEventDestroy(ctx->ev_k0[i]);
+    if (ctx->ev_k1[i]) cudaEventDestroy(ctx->ev_k1[i]);
+    if (ctx->ev_s1[i]) cudaEventDestroy(ctx->ev_s1[i]);
+  }
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->h_ring) cudaFreeHost(ctx->h_ring);
+  cudaGetLastError();  // a half-built context may have produced sticky-free errors above: leave none behind
   delete ctx;
   return DNV_OK;
 }

@@ -64,7 +64,8 @@ struct dnv_ctx {
   int64_t list_stage_cap;
   bool screened;           // the last call used the screen
   unsigned long long* d_tile_status;  // decoupled look-back status per compaction block
-  unsigned long long epoch;           // launch counter tagging d_tile_status entries
+  unsigned long long epoch;           // launch counter tagging d_tile_status entries (low 30 bits, see next_epoch)
+  size_t tile_status_bytes;           // bytes of d_tile_status that the look-backs use
   int calls_slot;                     // counters[] slot holding the running call total (0 or 3)
   int count_bytes;                    // bytes per site of the current call's counts: 24 (uint16) or 12 (uint8)
   int64_t* d_call_idx;     // global site index of every call, input order
@@ -107,4 +108,18 @@ int launch_trio_chunk(dnv_ctx* ctx, const void* d_counts, int64_t site_base, int
                       dnv_site_result* d_dense, dnv_call* d_calls, int64_t cap);
 int ensure_chunk_scratch(dnv_ctx* ctx, int64_t n);
 int ensure_scratch(dnv_ctx* ctx, size_t bytes);
+// The look-back status words carry a 30-bit launch tag ([63:34]).  Returns the tag of the next launch on this
+// context (never 0: zeroed status memory must not look like a published word); when the counter wraps, the
+// status array is re-zeroed in stream order first, so a stale word of the same tag cannot be mistaken for a
+// fresh one (2^30 launches apart).
+inline int next_epoch(dnv_ctx* ctx, unsigned long long* tag_out) {
+  constexpr unsigned long long kMask = (1ull << 30) - 1;
+  if (((++ctx->epoch) & kMask) == 0) {
+    if (ctx->d_tile_status && ctx->tile_status_bytes)
+      DNV_CUDA(cudaMemsetAsync(ctx->d_tile_status, 0, ctx->tile_status_bytes, ctx->stream));
+    ++ctx->epoch;
+  }
+  *tag_out = ctx->epoch & kMask;
+  return DNV_OK;
+}
 }  // namespace dnv

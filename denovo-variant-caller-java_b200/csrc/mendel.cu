@@ -59,9 +59,11 @@ struct MendelArrays {
   unsigned long long* st_sum[3];   // admitted counts per person
   unsigned long long* st_max[3];   // running max of end (+1; 0 = none) per parent
   unsigned long long* st_found;    // PositionCalls
-  unsigned long long* totals;      // [0..2] admitted per person, [3] PositionCalls, [4] error index+1, [5] error kind, [6],[7] tickets
+  unsigned long long* totals;      // [0..2] admitted per person, [3] PositionCalls, [4] error: (record index + 1) << 2 | kind, [6],[7] tickets
 };
 
+// error word: index and kind travel in ONE atomicMax, so the reported kind always belongs to the reported record
+constexpr unsigned long long kErrUnsorted = 1, kErrBadBase = 2;
 constexpr unsigned long long kStAgg = 1ull << 62, kStPre = 2ull << 62, kStVal = (1ull << 62) - 1;
 
 // one warp: exclusive combination (sum or max) of all predecessor blocks' values
@@ -138,7 +140,7 @@ mendel_admit_compact_kernel(const dnv_vcall* __restrict__ calls, int64_t n, Mend
       bool bad = false;
       if (i > 0 && calls[i - 1].start > v.start) bad = true;  // stream must be sorted by start
       if (adm && (v.end <= v.start || v.start < 0 || v.end >= (1ll << 60))) bad = true;  // outside the batch-equivalence domain
-      if (bad) { atomicMax(&A.totals[4], (unsigned long long)(i + 1)); A.totals[5] = (unsigned long long)(-DNV_E_UNSORTED); }
+      if (bad) atomicMax(&A.totals[4], ((unsigned long long)(i + 1) << 2) | kErrUnsorted);
     }
     uint32_t code = kCodeBlock, ref = 0xFF;
     if (adm) {
@@ -347,7 +349,7 @@ mendel_join_emit_kernel(const Tables* __restrict__ tab, MendelArrays A, dnv_pcal
         else { if (c == kCodeBad) bad = true; g[par] = c; }
       }
       // the reference evaluates the child genotype first, so a bad child base throws even without parents
-      if (bad) { atomicMax(&A.totals[4], (unsigned long long)(A.src[i] + 1)); A.totals[5] = (unsigned long long)(-DNV_E_BADBASE); found = false; }
+      if (bad) { atomicMax(&A.totals[4], ((unsigned long long)(A.src[i] + 1) << 2) | kErrBadBase); found = false; }
       if (found) pk = (uint32_t)g[kChild] | ((uint32_t)g[kMom] << 8) | ((uint32_t)g[kDad] << 16);
     }
     const uint32_t m = __ballot_sync(0xffffffffu, found);
@@ -439,7 +441,8 @@ int dnv_mendel_filter_device(dnv_ctx* ctx, const dnv_vcall* d_calls, int64_t n, 
   ctx->stats.n_calls = (int64_t)h[3];
   ctx->stats.n_launches = 2;
   if (h[4] != 0) {
-    const int kind = -(int)h[5];
+    const int kind = (h[4] & 3) == kErrBadBase ? DNV_E_BADBASE : DNV_E_UNSORTED;
+    h[4] >>= 2;
     set_error(kind == DNV_E_BADBASE
                   ? "mendel filter: base outside ACGT at record " + std::to_string(h[4] - 1) +
                         " (the reference throws IllegalArgumentException, M/VariantsBuffer.java:235-236)"

@@ -18,7 +18,7 @@
 
 namespace dnv {
 
-// meta[0..3] person offsets, meta[4] max read length, meta[5] error (1+read index), meta[6] error kind
+// meta[0..3] person offsets, meta[4] max read length, meta[5] error word (pileup_err: index and kind in ONE atomicMax)
 __global__ void __launch_bounds__(256)
 pileup_prep_kernel(const int64_t* __restrict__ read_start, const int64_t* __restrict__ base_off,
                    const uint8_t* __restrict__ person, int64_t n_reads, long long* __restrict__ meta) {
@@ -27,14 +27,13 @@ pileup_prep_kernel(const int64_t* __restrict__ read_start, const int64_t* __rest
     const long long len = base_off[r + 1] - base_off[r];
     lmax = len > lmax ? len : lmax;
     const int p = person[r];
-    if (p > 2 || len < 0) { atomicMax((unsigned long long*)&meta[5], (unsigned long long)(r + 1)); meta[6] = DNV_E_INVALID; continue; }
+    if (p > 2 || len < 0) { atomicMax((unsigned long long*)&meta[5], pileup_err(r, false, kPileErrInvalid)); continue; }
     if (r == 0) {
       for (int q = 0; q <= p; q++) meta[q] = 0;
     } else {
       const int pp = person[r - 1];
       if (pp > p || (pp == p && read_start[r - 1] > read_start[r])) {
-        atomicMax((unsigned long long*)&meta[5], (unsigned long long)(r + 1));
-        meta[6] = DNV_E_UNSORTED;
+        atomicMax((unsigned long long*)&meta[5], pileup_err(r, false, kPileErrUnsorted));
       }
       for (int q = pp + 1; q <= p; q++) meta[q] = r;
     }
@@ -89,9 +88,12 @@ int dnv_pileup_device(dnv_ctx* ctx, const int64_t* d_read_start, const int64_t* 
   DNV_CUDA(cudaMemcpyAsync(h, meta, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
   DNV_CUDA(cudaStreamSynchronize(ctx->stream));
   if (h[5] != 0) {
-    const int kind = (int)h[6] ? (int)h[6] : DNV_E_INVALID;
+    const unsigned long long w = (unsigned long long)h[5];
+    const int kind = (w & 7) == kPileErrBadBase ? DNV_E_BADBASE : (w & 7) == kPileErrUnsorted ? DNV_E_UNSORTED : DNV_E_INVALID;
+    const bool at_site = (w >> 3) & 1;
+    h[5] = (long long)(w >> 4);
     set_error(kind == DNV_E_BADBASE
-                  ? std::string("pileup: base outside {A,C,G,T,-} ") + (h[7] ? "at site " : "in read ") + std::to_string(h[5] - 1) +
+                  ? std::string("pileup: base outside {A,C,G,T,-} ") + (at_site ? "at site " : "in read ") + std::to_string(h[5] - 1) +
                         " (the reference throws IllegalArgumentException, M/ReadSummary.java:55)"
                   : kind == DNV_E_UNSORTED ? "pileup: reads must be sorted by (person, start); first violation at read " +
                                                  std::to_string(h[5] - 1)

@@ -30,6 +30,13 @@ constexpr int kPS_ReadCap = 384;            // read descriptors per chunk
 constexpr int kPS_StageBytes = 20 * 1024;   // staged bases per chunk (small: ~7 CTAs per SM cover each other's staging)
 constexpr int kPS_Pad = 32;                 // readable slack on both sides of the staged bytes
 
+// error word of the pileup kernels: (index + 1) << 4 | at_site << 3 | kind — one atomicMax carries the kind
+// together with the index it belongs to
+constexpr unsigned long long kPileErrInvalid = 1, kPileErrUnsorted = 2, kPileErrBadBase = 3;
+__host__ __device__ __forceinline__ unsigned long long pileup_err(long long index, bool at_site, unsigned long long kind) {
+  return ((unsigned long long)(index + 1) << 4) | (at_site ? 8ull : 0ull) | kind;
+}
+
 struct PileStageShared {
   alignas(16) unsigned char stage[kPS_Pad + kPS_StageBytes + kPS_Pad];
   int rel[kPS_ReadCap];    // read start - P0
@@ -62,7 +69,7 @@ template <int S>
 __device__ __forceinline__ void ps_person(PileStageShared& sh, int64_t c_first, int64_t c_last,
                                           const int64_t* __restrict__ read_start,
                                           const int64_t* __restrict__ base_off, const char* __restrict__ bases,
-                                          long long n_bases, int64_t P0, int my_off, int lmax,
+                                          long long n_bases, int64_t P0, int my_off, int n_live, int lmax,
                                           uint32_t (&out01)[S], uint32_t (&out23)[S], bool& bad, bool& over) {
   constexpr int NW = S / 4;
   uint32_t acc[S];
@@ -134,9 +141,11 @@ __device__ __forceinline__ void ps_person(PileStageShared& sh, int64_t c_first, 
       for (int i = 0; i <= NW; i++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x[i]) : "r"(wa + 4 * i));
 #pragma unroll
       for (int i = 0; i < NW; i++) w[i] = __funnelshift_r(x[i], x[i + 1], shft);
-      // bytes of my window outside [0, len) of this read are not its bases: turn them into '-' (branch free).
-      // t_lo in [0, S-1], t_hi in [1, S]
-      const int t_lo = max(0, -q), t_hi = min(S, len - q);
+      // bytes of my window outside [0, len) of this read are not its bases, and window positions at or past
+      // n_live (last, partial tile) are not requested sites — the reference only looks at the base AT a
+      // candidate position (M/ReadSummary.java:48-55), so an 'N' next to the last site must not fail the
+      // batch: turn both kinds into '-' (branch free).  t_lo in [0, S-1], t_hi <= S (<= 0: nothing of mine)
+      const int t_lo = max(0, -q), t_hi = min(min(S, len - q), n_live - my_off);
 #pragma unroll
       for (int i = 0; i < NW; i += 2) {  // 8 window bytes at a time as one 64-bit mask
         const int a = min(max(t_lo - 4 * i, 0), 8), b = min(max(t_hi - 4 * i, 0), 8);
@@ -209,7 +218,7 @@ pileup_stage_kernel(const int64_t* __restrict__ read_start, const int64_t* __res
 #pragma unroll 1
       for (int p = 0; p < 3; p++) {
         uint32_t o01[S], o23[S];
-        ps_person<S>(sh, sh.win[p][0], sh.win[p][1], read_start, base_off, bases, n_bases, P0, my_off, lmax, o01, o23, bad, over);
+        ps_person<S>(sh, sh.win[p][0], sh.win[p][1], read_start, base_off, bases, n_bases, P0, my_off, n_live, lmax, o01, o23, bad, over);
 #pragma unroll
         for (int k = 0; k < S; k++) {
           const int64_t s = s0 + my_off + k;
@@ -252,11 +261,9 @@ pileup_stage_kernel(const int64_t* __restrict__ read_start, const int64_t* __res
       }
     }
     if (bad && my_off < n_live) {
-      atomicMax((unsigned long long*)&meta[5], (unsigned long long)(s0 + my_off + 1));
-      meta[6] = DNV_E_BADBASE; meta[7] = 1;
+      atomicMax((unsigned long long*)&meta[5], pileup_err(s0 + my_off, true, kPileErrBadBase));
     } else if (over && my_off < n_live) {  // more than 65535 reads over one site
-      atomicMax((unsigned long long*)&meta[5], 1ull);
-      meta[6] = DNV_E_INVALID;
+      atomicMax((unsigned long long*)&meta[5], pileup_err(0, false, kPileErrInvalid));
     }
   }
 }

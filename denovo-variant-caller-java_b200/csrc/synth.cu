@@ -150,13 +150,17 @@ int dnv_synth_counts_at(dnv_ctx* ctx, uint64_t seed, const int64_t* index, int64
   if (cudaMalloc(&d_index, (size_t)n * 8) != cudaSuccess || cudaMalloc(&d_counts, (size_t)n * 24) != cudaSuccess) {
     set_error("dnv_synth_counts_at: device allocation failed"); rc = DNV_E_NOMEM;
   }
-  if (rc == DNV_OK && cudaMemcpy(d_index, index, (size_t)n * 8, cudaMemcpyHostToDevice) != cudaSuccess) {
+  // copies go through the context's stream: the generator kernel runs there, and a non-blocking stream does
+  // not order against the legacy default stream a plain cudaMemcpy would use
+  if (rc == DNV_OK && cudaMemcpyAsync(d_index, index, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
     set_error("dnv_synth_counts_at: H2D copy failed"); rc = DNV_E_CUDA;
   }
   if (rc == DNV_OK) rc = synth_launch(ctx, seed, 0, d_index, n, thr, n_thr, err_thr, d_counts);
-  if (rc == DNV_OK && cudaMemcpy(counts, d_counts, (size_t)n * 24, cudaMemcpyDeviceToHost) != cudaSuccess) {
+  if (rc == DNV_OK && (cudaMemcpyAsync(counts, d_counts, (size_t)n * 24, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                       cudaStreamSynchronize(ctx->stream) != cudaSuccess)) {
     set_error("dnv_synth_counts_at: D2H copy failed"); rc = DNV_E_CUDA;
   }
+  cudaStreamSynchronize(ctx->stream);  // nothing in flight may outlive the buffers freed below
   cudaFree(d_index); cudaFree(d_counts);
   return rc;
 }

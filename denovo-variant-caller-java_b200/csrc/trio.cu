@@ -228,6 +228,7 @@ int ensure_chunk_scratch(dnv_ctx* ctx, int64_t n) {
   DNV_CUDA(cudaMalloc(&ctx->d_tile_status, (size_t)n_status_alloc * 8));
   DNV_CUDA(cudaMalloc(&ctx->d_list, ((size_t)n + kScreenSites) * 4));
   DNV_CUDA(cudaMemsetAsync(ctx->d_tile_status, 0, (size_t)n_status * 8, ctx->stream));
+  ctx->tile_status_bytes = (size_t)n_status * 8;
   ctx->chunk_cap = n;
   return DNV_OK;
 }
@@ -299,8 +300,11 @@ int launch_trio_chunk(dnv_ctx* ctx, const void* d_counts, int64_t site_base, int
   }
   if (timed) DNV_CUDA(cudaEventRecord(ctx->ev_k1[ctx->n_timed++], st));
   const int in_slot = ctx->calls_slot, out_slot = in_slot == 0 ? 3 : 0;
+  unsigned long long tag = 0;
+  rc = next_epoch(ctx, &tag);
+  if (rc) return rc;
   compact_calls_kernel<<<n_blocks, kCompactThreads, 0, st>>>(site_base, ctx->d_bits, n_words, ctx->d_tile_status,
-                                                            ++ctx->epoch, ctx->d_counters, in_slot, out_slot,
+                                                            tag, ctx->d_counters, in_slot, out_slot,
                                                             ctx->d_call_idx, ctx->call_idx_cap);
   call_details_kernel<<<sms * 4, kDetailThreads, 0, st>>>(ctx->d_tab, d_counts, ctx->count_bytes, site_base,
                                                          ctx->d_call_idx, ctx->d_counters, in_slot, out_slot, d_calls,

@@ -445,9 +445,11 @@ static int launch_trio_list(dnv_ctx* ctx, const void* d_counts, int64_t n, int64
     ctx->list_stage_cap = need;
   }
   const FastConsts fk = make_fast_consts(ctx->h_tab);
+  unsigned long long tag = 0;
+  { const int erc = next_epoch(ctx, &tag); if (erc) return erc; }
   kern<<<grid, kListThreads, smem, ctx->stream>>>(ctx->d_tab, fk, (const unsigned char*)d_counts, n, site_base, ctx->d_list,
                                                   ctx->d_wcount, n_warps, n_tiles / n_warps, n_tiles % n_warps,
-                                                  ctx->d_tile_status, ++ctx->epoch, ctx->d_counters, in_slot, out_slot, cap,
+                                                  ctx->d_tile_status, tag, ctx->d_counters, in_slot, out_slot, cap,
                                                   ctx->count_out, ctx->d_list_stage);
   // one thread per call; CTAs beyond the number of calls leave at once
   const int fgrid = (int)std::max<int64_t>(1, std::min<int64_t>((need + kListThreads - 1) / kListThreads, (int64_t)sms * 2));

@@ -85,8 +85,13 @@ typedef struct {
 } dnv_params;
 
 /* One called site = BayesCallResult + BayesInferenceResult
- * (M/BayesInfer.java:74-106, M/BayesInferenceResult.java:23-51).  Values come
- * from the exact direct-form evaluation of that site. */
+ * (M/BayesInfer.java:74-106, M/BayesInferenceResult.java:23-51).
+ * dad/mom/child and max_ll always come from the exact log-domain sweep (bit-identical
+ * to the reference's argmax, M/DenovoBayesNet.java:260-278).  p, lr, log_men, log_den
+ * come from the factored linear form (within 1e-9 relative of the reference's direct
+ * form); for HARD sites (flags bit0: threshold-ambiguous, underflow gray zone, deeper
+ * than the power tables) and under DNV_F_FORCE_DIRECT they come from the exact
+ * direct-form evaluation in the reference's own operation order. */
 typedef struct {
   int64_t site;        /* index into the input batch */
   uint16_t counts[12]; /* DAD,MOM,CHILD x A,C,G,T (for the readCounts= field) */

@@ -55,6 +55,35 @@ def test_pileup_sparse_sites_and_edges():
         assert ei.value.code == D.DNV_E_UNSORTED
 
 
+@pytest.mark.parametrize("n_sites", [1003, 1021, 8 * 128 + 1])
+def test_pileup_dense_bad_base_only_at_requested_sites(n_sites):
+    """Dense (staged) path, n_sites % 8 != 0: a non-ACGT base within the 7 positions AFTER the last site is
+    not at a candidate position — the reference never looks at it (M/ReadSummary.java:48-55) — while the
+    same base AT the last site is its IllegalArgumentException."""
+    rs, bo, ba, pe = S.make_reads(14, 1000, 3000, depth=30)
+    pos = np.arange(1000, 1000 + n_sites, dtype=np.int64)
+    last = int(pos[-1])
+    lens = np.diff(bo)
+    near = ba.copy()
+    for r in np.nonzero((rs <= last + 7) & (rs + lens > last + 1))[0]:   # reads reaching past the last site
+        for q in range(last + 1, last + 8):
+            off = q - rs[r]
+            if 0 <= off < lens[r]:
+                near[bo[r] + off] = ord("N")
+    assert (near != ba).sum() > 50
+    rc, want = O.pileup(rs, bo, near, pe, pos)
+    assert rc == 0
+    with D.TrioEngine() as eng:
+        assert np.array_equal(eng.pileup(rs, bo, near, pe, pos), want)
+        at = near.copy()
+        r = int(np.nonzero((rs <= last) & (rs + lens > last))[0][0])
+        at[bo[r] + (last - rs[r])] = ord("N")
+        assert O.pileup(rs, bo, at, pe, pos)[0] < 0
+        with pytest.raises(D.DenovoError) as ei:
+            eng.pileup(rs, bo, at, pe, pos)
+        assert ei.value.code == D.DNV_E_BADBASE
+
+
 def test_pileup_then_inference_end_to_end():
     """reads -> counts -> calls on the device equals oracle pileup -> oracle inference."""
     rs, bo, ba, pe = S.make_reads(13, 1, 20000, depth=30, err=2e-2)
