@@ -226,6 +226,7 @@ def main():
 
     def join():
         """The main stream waits for both pipeline streams (no host synchronisation)."""
+        pipe.flush()
         for st in pstreams:
             stream.wait_stream(st)
 

@@ -44,10 +44,72 @@ void set_error(const std::string& msg);
 
 }  // namespace dnv
 
+namespace dnv {
+// How a chunk's kernels learn where its call records start and publish where they end.  Chunks of one batch
+// (and batches among each other) may run on different lanes (streams); the kernels that extend the chain — the
+// list kernel or the compaction kernel — are serialised by an event, everything else overlaps.
+struct CallChain {
+  const unsigned long long* before;  // calls of this batch before this chunk: the previous chunk's pair[1]; nullptr = 0
+  unsigned long long* pair;          // this chunk's private words: [0] <- calls before it, [1] <- calls up to and including it
+  unsigned long long* acc;           // since the host last collected: [0] calls (added by a batch's last chunk),
+                                     // [1] sites the screen left undecided, [2] hard sites
+  unsigned long long* work;          // [0] tile / block ticket, [1] CTAs gone (reset by the launch that used them)
+  int64_t* count_out;                // where the batch's running call total is published for the caller, or null
+  int last;                          // last chunk of its batch
+  unsigned long long* ktrace;        // DNV_KTRACE: the lane's time-line slots (6 words per chunk), or null
+  const unsigned int* ktrace_seq;    // ... and which slot the lane is at (bumped after every chunk, so graph replays advance)
+};
+
+constexpr int kMaxLanes = 4;
+
+// A batch whose arguments repeat (a ring of buffers walked chunk by chunk, a benchmark loop) is captured once into
+// a CUDA graph and replayed with ONE launch call instead of a dozen stream operations — at ~50 us of GPU work per
+// batch the host would otherwise be the bottleneck.
+constexpr int kGraphSlots = 8;
+struct GraphKey {
+  const void* counts; const void* calls; const void* count_out; const void* dense;
+  int64_t n, site_base, cap;
+  int bps;
+  bool operator==(const GraphKey& o) const {
+    return counts == o.counts && calls == o.calls && count_out == o.count_out && dense == o.dense && n == o.n &&
+           site_base == o.site_base && cap == o.cap && bps == o.bps;
+  }
+};
+struct GraphEntry {
+  GraphKey key;
+  cudaGraphExec_t exec;    // null until the key has been seen twice
+  int seen;
+  unsigned long long stamp;  // last use (LRU)
+};
+
+// One lane = one stream + the scratch that lives between a chunk's kernels.  A context feeds its chunks to the
+// lanes in turn, so the bandwidth-bound screen of one chunk runs beside the latency-bound list / finish kernels
+// of the previous ones (what several contexts on several streams did in round 1, now inside one dnv_ctx).
+struct TrioLane {
+  cudaStream_t own;        // the lane's screen stream, low priority (unused when the context runs serially)
+  cudaStream_t tail;       // the lane's tail stream (list / finish kernels), HIGH priority: its short kernels are
+                           // dispatched into the room beside the resident screens ahead of any queued screen CTAs
+  cudaEvent_t ev_screen;   // the lane's latest screen has finished
+  cudaEvent_t ev_done;     // everything enqueued on the lane so far
+  bool used;               // has work the front stream has not waited for yet
+  cudaEvent_t ev_flush;    // recorded on the screen stream after the lane's latest submission (what flush waits for)
+  int parity;              // which of the lane's two chain pairs the next chunk uses
+  uint32_t* d_list;        // sites the integer screen could not decide (chunk-relative), per-warp sorted segments
+  int64_t list_cap;
+  uint32_t* d_wcount;      // length of every screen warp's segment of d_list
+  dnv_call* d_list_stage;  // list kernel: records between its two phases (local HBM)
+  int64_t list_stage_cap;
+  unsigned long long* d_tile_status;  // decoupled look-back status per list tile / compaction block (all zero between launches)
+  int64_t tile_cap;                   // sites the status array is sized for
+  size_t tile_status_bytes;
+  GraphEntry graphs[kGraphSlots];     // replayable asynchronous batches of this lane
+};
+}  // namespace dnv
+
 struct dnv_ctx {
   dnv_params prm;
   int device;
-  cudaStream_t stream;       // compute (own_stream unless dnv_set_stream)
+  cudaStream_t stream;       // FRONT stream: orders the context against its caller (own_stream unless dnv_set_stream)
   cudaStream_t own_stream;
   cudaEvent_t ev_k0[64], ev_k1[64], ev_s1[64];  // kernel brackets (DNV_F_TIME_KERNELS): start, end, end of the screen
   int n_timed;
@@ -55,22 +117,33 @@ struct dnv_ctx {
   cudaEvent_t ev_h2d[2], ev_done[2];
   dnv::Tables h_tab;
   dnv::Tables* d_tab;
-  // per-chunk scratch (sized for chunk_cap sites)
-  int64_t chunk_cap;
-  uint32_t* d_bits;        // decision bit per site
-  uint32_t* d_list;        // sites the integer screen could not decide (chunk-relative), per-warp sorted segments
-  uint32_t* d_wcount;      // length of every screen warp's segment of d_list
-  dnv_call* d_list_stage;  // list kernel: records between its two phases (local HBM)
-  int64_t list_stage_cap;
+  // lanes (n_lanes == 1: serial, everything on the front stream — timed contexts, DNV_LANES=1)
+  int n_lanes;
+  int lane_next;
+  dnv::TrioLane lane[dnv::kMaxLanes];
+  cudaEvent_t ev_sub;        // front stream at the time of the current submission (inputs are ready)
+  cudaEvent_t ev_chain;      // the list / compaction kernel of the previous chunk of the batch being enqueued
+  const unsigned long long* chain_prev;  // pair[1] of the previous chunk of the batch being enqueued
+  // scratch of the unscreened path (always lane 0)
+  int64_t bits_cap;
+  uint32_t* d_bits;        // decision bit per site (unscreened path)
+  unsigned long long* d_cstatus;      // look-back status of the compaction kernel (tagged words, see next_epoch)
+  size_t cstatus_bytes;
+  unsigned long long epoch;           // launch tag of the compaction kernel's status words
   bool screened;           // the last call used the screen
-  unsigned long long* d_tile_status;  // decoupled look-back status per compaction block
-  unsigned long long epoch;           // launch counter tagging d_tile_status entries (low 30 bits, see next_epoch)
-  size_t tile_status_bytes;           // bytes of d_tile_status that the look-backs use
-  int calls_slot;                     // counters[] slot holding the running call total (0 or 3)
+  bool capturing;          // a CUDA graph of the current submission is being captured (no allocation allowed)
+  bool use_graphs;         // DNV_GRAPHS=0 turns graph replay off
+  bool use_graphs_async;   // DNV_GRAPHS_ASYNC=1: also replay asynchronous batches
+  bool tail_prio;          // DNV_TAIL_PRIO=1: list / finish kernels on a separate high-priority stream per lane
+  bool sub_pending;        // ev_sub was recorded for the current submission (the front stream had work pending)
+  unsigned long long graph_clock;
+  dnv::GraphEntry sync_graphs[dnv::kGraphSlots];  // replayable synchronous calls (dnv_infer_counts*_device)
   int count_bytes;                    // bytes per site of the current call's counts: 24 (uint16) or 12 (uint8)
-  int64_t* d_call_idx;     // global site index of every call, input order
+  int64_t* d_call_idx;     // global site index of every call, input order (unscreened path)
   int64_t call_idx_cap;
-  unsigned long long* d_counters;  // [0]/[3] running call total (ping-pong per chunk) [4] hard sites [6] block ticket
+  // [0..15] chain pairs (lane x parity x 2), [16..19] acc, [23] always zero, [24 + 2 * lane ..] tickets of the lane
+  unsigned long long* d_counters;
+  unsigned long long* h_acc;       // pinned [4]: acc as last collected
   // staging of the host API
   uint16_t* d_stage_counts[2];
   dnv_site_result* d_stage_dense[2];
@@ -85,12 +158,12 @@ struct dnv_ctx {
   int sms;                  // multiprocessors of the device
   int screen_per_sm[2];     // resident CTAs per SM of trio_screen_kernel<u16 / u8>, 0 = not queried yet
   int list_per_sm[2][2];    // ... of trio_list_kernel<u16 / u8><BAYES-LRT / MAP>
-  // asynchronous batches (dnv_infer_counts*_device_async): per-batch counters land in a pinned ring
-  unsigned long long* h_ring;  // [64][8]
+  // DNV_KTRACE=1: device-side time line, 6 words per chunk (screen, list, finish: first CTA start / last CTA end)
+  unsigned long long* d_ktrace;   // [lane][kKtraceSlots][6]
+  unsigned int* d_ktrace_seq;     // [lane]
+  // asynchronous batches (dnv_infer_counts*_device_async)
   int n_async;                 // batches enqueued since the last dnv_sync
-  int ring_slot[64];           // which counter slot holds each batch's call total
   int64_t async_sites;
-  int64_t* count_out;          // where the details kernel stores the batch's call total (async batches), else null
 };
 
 #define DNV_CUDA(call)                                                        \
@@ -103,20 +176,60 @@ struct dnv_ctx {
   } while (0)
 
 namespace dnv {
-// kernels / launchers (defined in the .cu files)
-int launch_trio_chunk(dnv_ctx* ctx, const void* d_counts, int64_t site_base, int64_t n,
-                      dnv_site_result* d_dense, dnv_call* d_calls, int64_t cap);
-int ensure_chunk_scratch(dnv_ctx* ctx, int64_t n);
+constexpr int kCtrAcc = 16, kCtrZero = 23, kCtrWork = 24, kCtrWords = 32;
+
+// one chunk of sites resident in HBM through the READ pipeline (trio.cu)
+struct ChunkArgs {
+  const void* d_counts;
+  int64_t site_base;       // added to chunk-relative site indices in the records
+  int64_t n;
+  dnv_site_result* d_dense;
+  dnv_call* d_calls;
+  int64_t cap;
+  bool first, last;        // first / last chunk of its batch
+  bool no_sub_wait;        // the caller has already ordered the lane's stream after the context's ev_sub
+  bool tail_alone;         // no other chunk's screen will run beside this chunk's list / finish kernels
+  cudaEvent_t wait_ev;     // the chunk's input is ready (null: the context's ev_sub)
+  int64_t* count_out;
+  dnv_site_result* dense_host;  // host API: where the chunk's dense records go (copied on the chunk's stream), or null
+  cudaEvent_t done_ev;     // recorded when the chunk no longer needs its input (staging ring of the host API), or null
+};
+constexpr int kKtraceSlots = 1024;  // per lane
+// which: 0 screen, 1 list, 2 finish; first CTA start -> word 2*which (min), last CTA end -> word 2*which+1 (max)
+__device__ __forceinline__ void ktrace_stamp(unsigned long long* base, const unsigned int* seq, int which, bool end) {
+  if (base) {
+    unsigned long long* slot = base + 6 * (*seq & (kKtraceSlots - 1)) + 2 * which;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (end) atomicMax(slot + 1, t); else atomicMin(slot, t);
+  }
+}
+constexpr int kWcountWords = 8192;  // >= kScreenMaxWarps (trio_screen.cuh)
+// Enqueues the chunk on the next lane.
+int launch_trio_chunk(dnv_ctx* ctx, const ChunkArgs& a);
 int ensure_scratch(dnv_ctx* ctx, size_t bytes);
-// The look-back status words carry a 30-bit launch tag ([63:34]).  Returns the tag of the next launch on this
-// context (never 0: zeroed status memory must not look like a published word); when the counter wraps, the
-// status array is re-zeroed in stream order first, so a stale word of the same tag cannot be mistaken for a
-// fresh one (2^30 launches apart).
-inline int next_epoch(dnv_ctx* ctx, unsigned long long* tag_out) {
+// the pipeline as the entry points see it (api.cu)
+int begin_submit(dnv_ctx* ctx);
+int flush_lanes(dnv_ctx* ctx);
+int collect(dnv_ctx* ctx);
+void reset_call_state(dnv_ctx* ctx);
+int ensure_stage_calls(dnv_ctx* ctx, int64_t calls_cap);
+int enqueue_device_batch(dnv_ctx* ctx, const void* d_counts, int bps, int64_t n, int64_t site_base, dnv_site_result* d_dense,
+                         dnv_call* d_calls, int64_t cap, int64_t* count_out, bool split, bool no_sub_wait);
+bool will_screen(const dnv_ctx* ctx, bool dense);
+int enqueue_host_batch(dnv_ctx* ctx, const void* counts, int bps, int64_t n, int64_t site_base, dnv_site_result* dense,
+                       dnv_call* d_calls, int64_t cap, int64_t* count_out);
+inline bool parallel(const dnv_ctx* ctx) { return ctx->n_lanes > 1; }
+inline cudaStream_t lane_stream(const dnv_ctx* ctx, int l) { return parallel(ctx) ? ctx->lane[l].own : ctx->stream; }
+inline cudaStream_t lane_tail(const dnv_ctx* ctx, int l) { return parallel(ctx) ? (ctx->lane[l].tail ? ctx->lane[l].tail : ctx->lane[l].own) : ctx->stream; }
+// The compaction kernel's look-back status words carry a 30-bit launch tag ([63:34]).  Returns the tag of its next
+// launch on this context (never 0: zeroed status memory must not look like a published word); when the counter wraps,
+// the status array is re-zeroed in stream order first, so a stale word of the same tag cannot be mistaken for a
+// fresh one (2^30 launches apart).  (The list kernel needs no tag: it clears what it used.)
+inline int next_epoch(dnv_ctx* ctx, cudaStream_t st, unsigned long long* tag_out) {
   constexpr unsigned long long kMask = (1ull << 30) - 1;
   if (((++ctx->epoch) & kMask) == 0) {
-    if (ctx->d_tile_status && ctx->tile_status_bytes)
-      DNV_CUDA(cudaMemsetAsync(ctx->d_tile_status, 0, ctx->tile_status_bytes, ctx->stream));
+    if (ctx->d_cstatus && ctx->cstatus_bytes) DNV_CUDA(cudaMemsetAsync(ctx->d_cstatus, 0, ctx->cstatus_bytes, st));
     ++ctx->epoch;
   }
   *tag_out = ctx->epoch & kMask;

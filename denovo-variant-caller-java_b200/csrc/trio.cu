@@ -16,7 +16,8 @@
 //
 // Replaces the per-site task of ReadCaller.runBayesDenovoInference
 // (M/ReadCaller.java:111-130) -> BayesInfer.infer (M/BayesInfer.java:50-69).
-// Nothing here synchronises with the host; the caller reads counters at the end.
+// Chunks are fed to the context's lanes in turn (dnv_internal.cuh: TrioLane), so the screen of one chunk runs
+// beside the list / finish kernels of the previous ones.  Nothing here synchronises with the host.
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -36,7 +37,7 @@ constexpr int kExactThreads = 128;
 __global__ void __launch_bounds__(kExactThreads)
 trio_direct_all_kernel(const Tables* __restrict__ tab, const void* __restrict__ counts, int bps,
                        int64_t n, uint32_t* __restrict__ bits, dnv_site_result* __restrict__ dense,
-                       unsigned long long* __restrict__ counters) {
+                       unsigned long long* __restrict__ acc) {
   __shared__ double s_rel[1000];
   __shared__ uint32_t s_isden[32];
   stage_exact_tables(tab, s_rel, s_isden);
@@ -58,7 +59,7 @@ trio_direct_all_kernel(const Tables* __restrict__ tab, const void* __restrict__ 
     const uint32_t word = __ballot_sync(0xffffffffu, dn);
     if ((threadIdx.x & 31) == 0 && site < n) {
       bits[site >> 5] = word;
-      atomicAdd(&counters[4], (unsigned long long)min((int64_t)32, n - site));  // every site took the exact path
+      atomicAdd(&acc[2], (unsigned long long)min((int64_t)32, n - site));  // every site took the exact path
     }
   }
 }
@@ -67,22 +68,24 @@ trio_direct_all_kernel(const Tables* __restrict__ tab, const void* __restrict__ 
 // Single-pass, order-preserving compaction of the decision bits (decoupled look-back over
 // blocks of 8192 sites): the global site index of every called site, in INPUT order.
 // status word: [63:34] epoch of this launch, [33:32] 1 = block aggregate, 2 = inclusive prefix, [31:0] value.
-// counters: [in_slot] calls before this chunk, [out_slot] <- calls after it, [6] block ticket.
+// ch (CallChain): *before = calls before this chunk, pair[0..1] <- calls before / after it, work[0] block ticket.
 constexpr int kCompactThreads = 256;
+static_assert(kWcountWords >= kScreenMaxWarps, "wcount buffers hold one word per screen warp");
 static_assert(kCompactThreads == kScanThreads, "one bit-word per thread");
 
 __global__ void __launch_bounds__(kCompactThreads)
 compact_calls_kernel(int64_t site_base, const uint32_t* __restrict__ bits, int64_t n_words,
-                     unsigned long long* status, unsigned long long epoch, unsigned long long* counters,
-                     int in_slot, int out_slot, int64_t* __restrict__ call_idx, int64_t call_idx_cap) {
+                     unsigned long long* status, unsigned long long epoch, const CallChain ch,
+                     int64_t* __restrict__ call_idx, int64_t call_idx_cap) {
   __shared__ int s_warp_sum[kCompactThreads / 32];
   __shared__ unsigned int s_bid;
   __shared__ unsigned long long s_excl;
-  if (threadIdx.x == 0) s_bid = (unsigned int)atomicAdd(&counters[6], 1ull);  // blocks ordered by start time
+  if (threadIdx.x == 0) s_bid = (unsigned int)atomicAdd(&ch.work[0], 1ull);  // blocks ordered by start time
   __syncthreads();
   const unsigned int b = s_bid;
-  if (b == gridDim.x - 1 && threadIdx.x == 0) counters[6] = 0;  // every ticket is taken: reset for the next launch
+  if (b == gridDim.x - 1 && threadIdx.x == 0) ch.work[0] = 0;  // every ticket is taken: reset for the next launch
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned long long calls_before = ch.before ? *ch.before : 0ull;
   const int64_t w = (int64_t)b * kCompactThreads + threadIdx.x;
   uint32_t word = (w < n_words) ? bits[w] : 0u;
   const int cnt = __popc(word);
@@ -125,12 +128,17 @@ compact_calls_kernel(int64_t site_base, const uint32_t* __restrict__ bits, int64
     if (lane == 0) {
       atomicExch(&status[b], tag | (2ull << 32) | (excl + (unsigned long long)total));
       s_excl = excl;
-      if (b == gridDim.x - 1) counters[out_slot] = counters[in_slot] + excl + (unsigned long long)total;
+      if (b == gridDim.x - 1) {
+        const unsigned long long all = calls_before + excl + (unsigned long long)total;
+        ch.pair[0] = calls_before;
+        ch.pair[1] = all;
+        if (ch.last) atomicAdd(&ch.acc[0], all);
+      }
     }
   }
   if (total == 0) return;  // block-uniform
   __syncthreads();
-  int64_t pos = (int64_t)counters[in_slot] + (int64_t)s_excl + warp_off + x - cnt;
+  int64_t pos = (int64_t)calls_before + (int64_t)s_excl + warp_off + x - cnt;
   while (word) {
     const int bit = __ffs(word) - 1;
     word &= word - 1;
@@ -140,7 +148,7 @@ compact_calls_kernel(int64_t site_base, const uint32_t* __restrict__ bits, int64
 }
 
 // ---------------------------------------------------------------- K3 call records
-// One THREAD per called site (calls [counters[in_slot], counters[out_slot]) of this chunk).
+// One THREAD per called site (calls [pair[0], pair[1]) of this chunk).
 // Values: the factored form (power tables read through L1) unless the site is hard, then the
 // exact direct form in the reference's own order.  maxGenoType / max_ll: always the exact
 // (pruned) log-domain argmax.
@@ -148,11 +156,11 @@ constexpr int kDetailThreads = 64;
 
 __global__ void __launch_bounds__(kDetailThreads)
 call_details_kernel(const Tables* __restrict__ tab, const void* __restrict__ counts, int bps, int64_t site_base,
-                    const int64_t* __restrict__ call_idx, const unsigned long long* __restrict__ counters,
-                    int in_slot, int out_slot, dnv_call* __restrict__ calls, int64_t cap, const FastConsts k,
-                    int64_t* count_out) {
-  const unsigned long long lo = counters[in_slot];
-  unsigned long long hi = counters[out_slot];
+                    const int64_t* __restrict__ call_idx, const CallChain ch, dnv_call* __restrict__ calls, int64_t cap,
+                    const FastConsts k) {
+  int64_t* count_out = ch.count_out;
+  const unsigned long long lo = ch.pair[0];
+  unsigned long long hi = ch.pair[1];
   // asynchronous batches: the running call total goes where the caller wants it (pinned host memory,
   // or a peer GPU's HBM next to the records) — a plain store, ordered by the stream like the records
   if (count_out && blockIdx.x == 0 && threadIdx.x == 0) *count_out = (int64_t)hi;
@@ -210,26 +218,54 @@ call_details_kernel(const Tables* __restrict__ tab, const void* __restrict__ cou
   }
 }
 
+__global__ void ktrace_bump_kernel(unsigned int* seq) { *seq += 1; }
+
 // ---------------------------------------------------------------- launcher
-int ensure_chunk_scratch(dnv_ctx* ctx, int64_t n) {
-  if (n <= ctx->chunk_cap) return DNV_OK;
-  cudaFree(ctx->d_bits); cudaFree(ctx->d_tile_status); cudaFree(ctx->d_list);
-  ctx->d_bits = nullptr; ctx->d_tile_status = nullptr; ctx->d_list = nullptr;
-  ctx->chunk_cap = 0;
-  const int64_t n_words = (n + 31) / 32;
-  // look-back status: one entry per compaction block (256 bit-words) or per list tile (128 undecided sites)
-  const int64_t n_status = std::max((n_words + kCompactThreads - 1) / kCompactThreads, (n + kListThreads - 1) / kListThreads) + 1;
-  DNV_CUDA(cudaMalloc(&ctx->d_bits, (size_t)(n_words + 1) * 4));
+// look-back status of the lane (list tiles / compaction blocks), zero between launches; `st` = the stream the next
+// kernel that uses it runs on.  Decision bits of the unscreened path live in the context (lane 0 only).
+static int ensure_lane_status(dnv_ctx* ctx, TrioLane& ln, int64_t n, cudaStream_t st) {
+  if (n <= ln.tile_cap) return DNV_OK;
+  if (ctx->capturing) { set_error("internal: scratch growth during graph capture"); return DNV_E_INVALID; }
+  cudaFree(ln.d_tile_status);  // (cudaFree synchronises the device)
+  ln.d_tile_status = nullptr;
+  ln.tile_cap = 0;
+  const int64_t n_status = (n + kListThreads - 1) / kListThreads + 1;  // one entry per list tile (kListThreads undecided sites)
 #ifdef DNV_LIST_TRACE
   const int64_t n_status_alloc = (1 << 20) + 8 * 8192;  // room for the per-CTA time stamps of trio_list_kernel
 #else
   const int64_t n_status_alloc = n_status;
 #endif
-  DNV_CUDA(cudaMalloc(&ctx->d_tile_status, (size_t)n_status_alloc * 8));
-  DNV_CUDA(cudaMalloc(&ctx->d_list, ((size_t)n + kScreenSites) * 4));
-  DNV_CUDA(cudaMemsetAsync(ctx->d_tile_status, 0, (size_t)n_status * 8, ctx->stream));
-  ctx->tile_status_bytes = (size_t)n_status * 8;
-  ctx->chunk_cap = n;
+  DNV_CUDA(cudaMalloc(&ln.d_tile_status, (size_t)n_status_alloc * 8));
+  DNV_CUDA(cudaMemsetAsync(ln.d_tile_status, 0, (size_t)n_status * 8, st));
+  ln.tile_status_bytes = (size_t)n_status * 8;
+  ln.tile_cap = n;
+  return DNV_OK;
+}
+
+// unscreened path: decision bits and the compaction kernel's (tagged) look-back status
+static int ensure_bits(dnv_ctx* ctx, int64_t n, cudaStream_t st) {
+  if (n <= ctx->bits_cap) return DNV_OK;
+  cudaFree(ctx->d_bits); cudaFree(ctx->d_cstatus);
+  ctx->d_bits = nullptr; ctx->d_cstatus = nullptr;
+  ctx->bits_cap = 0;
+  const int64_t n_words = (n + 31) / 32;
+  const int64_t n_status = (n_words + kCompactThreads - 1) / kCompactThreads + 1;
+  DNV_CUDA(cudaMalloc(&ctx->d_bits, (size_t)(n_words + 1) * 4));
+  DNV_CUDA(cudaMalloc(&ctx->d_cstatus, (size_t)n_status * 8));
+  DNV_CUDA(cudaMemsetAsync(ctx->d_cstatus, 0, (size_t)n_status * 8, st));
+  ctx->cstatus_bytes = (size_t)n_status * 8;
+  ctx->bits_cap = n;
+  return DNV_OK;
+}
+
+static int ensure_lane_list(dnv_ctx* ctx, TrioLane& ln, int64_t n) {
+  if (n <= ln.list_cap) return DNV_OK;
+  if (ctx->capturing) { set_error("internal: scratch growth during graph capture"); return DNV_E_INVALID; }
+  cudaFree(ln.d_list);
+  ln.d_list = nullptr;
+  ln.list_cap = 0;
+  DNV_CUDA(cudaMalloc(&ln.d_list, ((size_t)n + kScreenSites) * 4));
+  ln.list_cap = n;
   return DNV_OK;
 }
 
@@ -243,79 +279,128 @@ static int ensure_call_idx(dnv_ctx* ctx, int64_t cap) {
   return DNV_OK;
 }
 
-// One chunk (n < 2^31): two kernels.  The caller zeroes the counters and ctx->calls_slot
-// before the first chunk of a batch and reads counters[ctx->calls_slot] at the end.
-int launch_trio_chunk(dnv_ctx* ctx, const void* d_counts, int64_t site_base, int64_t n,
-                      dnv_site_result* d_dense, dnv_call* d_calls, int64_t cap) {
+// One chunk (n < 2^31) on the next lane.  The caller has recorded ctx->ev_sub on the front stream (parallel
+// contexts) and reads the totals through collect() at the end.
+int launch_trio_chunk(dnv_ctx* ctx, const ChunkArgs& a) {
+  const int64_t n = a.n;
   if (n <= 0) return DNV_OK;
-  int rc = ensure_chunk_scratch(ctx, n);
-  if (rc) return rc;
-  rc = ensure_call_idx(ctx, cap);
-  if (rc) return rc;
-  cudaStream_t st = ctx->stream;
-  const int64_t n_words = (n + 31) / 32;
-  const int n_blocks = (int)((n_words + kCompactThreads - 1) / kCompactThreads);
-  const int sms = ctx->sms;
-
   const bool direct = (ctx->prm.flags & DNV_F_FORCE_DIRECT) != 0;
   const bool timed = (ctx->prm.flags & DNV_F_TIME_KERNELS) != 0 && ctx->n_timed < 64;
   const bool map = ctx->prm.method == DNV_METHOD_MAP;
-  const bool screen = !direct && (map ? ctx->h_tab.map_screen_ok : ctx->h_tab.early_ok) && !d_dense &&
-                      !(ctx->prm.flags & DNV_F_NO_SCREEN);
+  const bool screen = will_screen(ctx, a.d_dense != nullptr);
+  // the unscreened path keeps its decision bits in shared scratch: always lane 0 (its chunks serialise)
+  const int li = screen ? ctx->lane_next : 0;
+  if (screen) ctx->lane_next = (ctx->lane_next + 1) % ctx->n_lanes;
+  TrioLane& ln = ctx->lane[li];
+  // st: where the chunk starts (the screen, or the whole unscreened path); tl: where its tail runs
+  cudaStream_t st = lane_stream(ctx, li), tl = screen ? lane_tail(ctx, li) : st;
+  // (the lane's own stream has already waited for the lane's previous tail — see the end of this function — so
+  // the lane's scratch is free again)
+  if (a.wait_ev) DNV_CUDA(cudaStreamWaitEvent(st, a.wait_ev, 0));
+  else if (parallel(ctx) && !a.no_sub_wait && ctx->sub_pending) DNV_CUDA(cudaStreamWaitEvent(st, ctx->ev_sub, 0));
+  int rc = screen ? ensure_lane_status(ctx, ln, n, tl) : ensure_bits(ctx, n, st);
+  if (rc) return rc;
+  const int sms = ctx->sms;
+
+  CallChain ch;
+  ch.before = a.first ? nullptr : ctx->chain_prev;
+  ch.pair = ctx->d_counters + (li * 2 + ln.parity) * 2;
+  ln.parity ^= 1;
+  ch.acc = ctx->d_counters + kCtrAcc;
+  ch.work = ctx->d_counters + kCtrWork + 2 * li;
+  ch.count_out = a.count_out;
+  ch.last = a.last ? 1 : 0;
+  ch.ktrace = ctx->d_ktrace ? ctx->d_ktrace + (size_t)li * kKtraceSlots * 6 : nullptr;
+  ch.ktrace_seq = ctx->d_ktrace ? ctx->d_ktrace_seq + li : nullptr;
+  ctx->chain_prev = ch.pair + 1;
+
   if (timed) DNV_CUDA(cudaEventRecord(ctx->ev_k0[ctx->n_timed], st));
-  if (direct) {
-    const int64_t want = (n + kExactThreads - 1) / kExactThreads;
-    const int grid = (int)(want < (int64_t)sms * 16 ? want : (int64_t)sms * 16);
-    trio_direct_all_kernel<<<grid, kExactThreads, 0, st>>>(ctx->d_tab, d_counts, ctx->count_bytes, n, ctx->d_bits, d_dense,
-                                                          ctx->d_counters);
-  } else if (screen) {
+  if (screen) {
     // calls only: exact integer screen at HBM speed, then the list kernel for the sites it could not decide
     // (fused FP64 posterior, ordered compaction) and the per-call finish kernel
+    rc = ensure_lane_list(ctx, ln, n);
+    if (rc) return rc;
     ScreenConsts sk;
     sk.c_hom = ctx->h_tab.c_hom_fx;
     sk.c_het = ctx->h_tab.c_het_fx;
     for (int x = 0; x < 4; x++) sk.w[x] = ctx->h_tab.scr_w[x];
     sk.shift32 = 32;
+    sk.ktrace = ch.ktrace;
+    sk.ktrace_seq = ch.ktrace_seq;
     const bool u8 = ctx->count_bytes == 12;
     int sgrid = 0;
-    rc = u8 ? launch_screen<true>(ctx, d_counts, n, sk, &sgrid) : launch_screen<false>(ctx, d_counts, n, sk, &sgrid);
+    rc = u8 ? launch_screen<true>(ctx, ln, st, a.d_counts, n, sk, &sgrid) : launch_screen<false>(ctx, ln, st, a.d_counts, n, sk, &sgrid);
     if (rc) return rc;
     if (timed) DNV_CUDA(cudaEventRecord(ctx->ev_s1[ctx->n_timed], st));
-    const int in_slot = ctx->calls_slot, out_slot = in_slot == 0 ? 3 : 0;
+    if (tl != st) {
+      DNV_CUDA(cudaEventRecord(ln.ev_screen, st));
+      DNV_CUDA(cudaStreamWaitEvent(tl, ln.ev_screen, 0));
+    }
+    const bool beside = parallel(ctx) && !a.tail_alone;
     if (map)
-      rc = u8 ? launch_trio_list<true, true>(ctx, d_counts, n, site_base, sgrid, in_slot, out_slot, d_calls, cap)
-              : launch_trio_list<false, true>(ctx, d_counts, n, site_base, sgrid, in_slot, out_slot, d_calls, cap);
+      rc = u8 ? launch_trio_list<true, true>(ctx, ln, tl, a.d_counts, n, a.site_base, sgrid, ch, a.d_calls, a.cap, beside)
+              : launch_trio_list<false, true>(ctx, ln, tl, a.d_counts, n, a.site_base, sgrid, ch, a.d_calls, a.cap, beside);
     else
-      rc = u8 ? launch_trio_list<true, false>(ctx, d_counts, n, site_base, sgrid, in_slot, out_slot, d_calls, cap)
-              : launch_trio_list<false, false>(ctx, d_counts, n, site_base, sgrid, in_slot, out_slot, d_calls, cap);
+      rc = u8 ? launch_trio_list<true, false>(ctx, ln, tl, a.d_counts, n, a.site_base, sgrid, ch, a.d_calls, a.cap, beside)
+              : launch_trio_list<false, false>(ctx, ln, tl, a.d_counts, n, a.site_base, sgrid, ch, a.d_calls, a.cap, beside);
     if (rc) return rc;
-    if (timed) DNV_CUDA(cudaEventRecord(ctx->ev_k1[ctx->n_timed++], st));
-    ctx->calls_slot = out_slot;
-    ctx->stats.n_launches += 3;
+    if (timed) DNV_CUDA(cudaEventRecord(ctx->ev_k1[ctx->n_timed++], tl));
     ctx->screened = true;
-    return DNV_OK;
   } else {
-    rc = launch_trio_fast(ctx, d_counts, n, d_dense);
+    rc = ensure_call_idx(ctx, a.cap);
     if (rc) return rc;
+    const int64_t n_words = (n + 31) / 32;
+    const int n_blocks = (int)((n_words + kCompactThreads - 1) / kCompactThreads);
+    if (direct) {
+      const int64_t want = (n + kExactThreads - 1) / kExactThreads;
+      const int grid = (int)(want < (int64_t)sms * 16 ? want : (int64_t)sms * 16);
+      trio_direct_all_kernel<<<grid, kExactThreads, 0, st>>>(ctx->d_tab, a.d_counts, ctx->count_bytes, n, ctx->d_bits,
+                                                            a.d_dense, ch.acc);
+    } else {
+      rc = launch_trio_fast(ctx, st, a.d_counts, n, a.d_dense, ch.acc);
+      if (rc) return rc;
+    }
+    if (timed) DNV_CUDA(cudaEventRecord(ctx->ev_k1[ctx->n_timed++], st));
+    unsigned long long tag = 0;
+    rc = next_epoch(ctx, st, &tag);
+    if (rc) return rc;
+    compact_calls_kernel<<<n_blocks, kCompactThreads, 0, st>>>(a.site_base, ctx->d_bits, n_words, ctx->d_cstatus, tag, ch,
+                                                              ctx->d_call_idx, ctx->call_idx_cap);
+    call_details_kernel<<<sms * 4, kDetailThreads, 0, st>>>(ctx->d_tab, a.d_counts, ctx->count_bytes, a.site_base,
+                                                           ctx->d_call_idx, ch, a.d_calls, a.cap,
+                                                           make_fast_consts(ctx->h_tab));
   }
-  if (timed) DNV_CUDA(cudaEventRecord(ctx->ev_k1[ctx->n_timed++], st));
-  const int in_slot = ctx->calls_slot, out_slot = in_slot == 0 ? 3 : 0;
-  unsigned long long tag = 0;
-  rc = next_epoch(ctx, &tag);
-  if (rc) return rc;
-  compact_calls_kernel<<<n_blocks, kCompactThreads, 0, st>>>(site_base, ctx->d_bits, n_words, ctx->d_tile_status,
-                                                            tag, ctx->d_counters, in_slot, out_slot,
-                                                            ctx->d_call_idx, ctx->call_idx_cap);
-  call_details_kernel<<<sms * 4, kDetailThreads, 0, st>>>(ctx->d_tab, d_counts, ctx->count_bytes, site_base,
-                                                         ctx->d_call_idx, ctx->d_counters, in_slot, out_slot, d_calls,
-                                                         cap, make_fast_consts(ctx->h_tab), ctx->count_out);
-  ctx->calls_slot = out_slot;
   ctx->stats.n_launches += 3;
   DNV_CUDA(cudaGetLastError());
+  if (ctx->d_ktrace) ktrace_bump_kernel<<<1, 1, 0, tl>>>(ctx->d_ktrace_seq + li);
+  if (a.dense_host && a.d_dense)
+    DNV_CUDA(cudaMemcpyAsync(a.dense_host, a.d_dense, (size_t)n * sizeof(dnv_site_result), cudaMemcpyDeviceToHost, tl));
+  if (a.done_ev) DNV_CUDA(cudaEventRecord(a.done_ev, tl));
+  if (parallel(ctx)) {
+    // the lane's screen stream rejoins its tail stream: the next chunk on this lane starts after this one has
+    // finished with the lane's scratch, and one event on the screen stream (ev_flush) covers the whole lane
+    if (tl != st) {
+      DNV_CUDA(cudaEventRecord(ln.ev_done, tl));
+      DNV_CUDA(cudaStreamWaitEvent(st, ln.ev_done, 0));
+    }
+    ln.used = true;
+  }
   return DNV_OK;
 }
 
 }  // namespace dnv
+
+// DNV_KTRACE=1: the device-side time line of the chunks run so far, lane by lane: out[lane][kKtraceSlots][6]
+// (screen start / end, list start / end, finish start / end in %globaltimer nanoseconds; a lane's slots wrap) and
+// seq[lane] = chunks the lane has run.  Returns the number of lanes.
+extern "C" int dnv_debug_ktrace(dnv_ctx* ctx, unsigned long long* out, unsigned int* seq) {
+  if (!ctx || !ctx->d_ktrace) return 0;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  if (cudaMemcpy(out, ctx->d_ktrace, (size_t)ctx->n_lanes * dnv::kKtraceSlots * 48, cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+  if (cudaMemcpy(seq, ctx->d_ktrace_seq, (size_t)ctx->n_lanes * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -2;
+  return ctx->n_lanes;
+}
 
 #ifdef DNV_LIST_TRACE
 extern "C" int dnv_debug_list_trace(dnv_ctx* ctx, unsigned long long* out, int n_ctas) {

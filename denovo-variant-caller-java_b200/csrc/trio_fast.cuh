@@ -239,7 +239,7 @@ __device__ __forceinline__ void unpack_counts(const uint2* p, int* c) {
 template <bool kLin, bool kMap, bool kDense, int kMinBlocks, bool kU8>
 __global__ void __launch_bounds__(kFastThreads, kMinBlocks)
 trio_fast_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsigned char* __restrict__ counts, int64_t n,
-                 uint32_t* __restrict__ bits, unsigned long long* __restrict__ counters,
+                 uint32_t* __restrict__ bits, unsigned long long* __restrict__ acc,
                  dnv_site_result* __restrict__ dense) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FastShared& s = *reinterpret_cast<FastShared*>(smem_raw);
@@ -337,7 +337,7 @@ trio_fast_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
     // warp evaluates them one at a time with the exact direct form
     uint32_t hword = __ballot_sync(0xffffffffu, hard);
     if (hword) {
-      if (lane == 0) atomicAdd(&counters[4], (unsigned long long)__popc(hword));
+      if (lane == 0) atomicAdd(&acc[2], (unsigned long long)__popc(hword));
       while (hword) {
         const int h = __ffs(hword) - 1;
         hword &= hword - 1;
@@ -358,7 +358,8 @@ trio_fast_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
 }
 
 template <bool kLin, bool kMap, bool kDense, int kMinBlocks, bool kU8>
-static int launch_fast_kernel(dnv_ctx* ctx, const void* d_counts, int64_t n, dnv_site_result* d_dense) {
+static int launch_fast_kernel(dnv_ctx* ctx, cudaStream_t st, const void* d_counts, int64_t n, dnv_site_result* d_dense,
+                              unsigned long long* acc) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
   const size_t smem = sizeof(FastShared);
@@ -371,23 +372,24 @@ static int launch_fast_kernel(dnv_ctx* ctx, const void* d_counts, int64_t n, dnv
   const int64_t persistent = (int64_t)sms * per_sm;  // one resident wave; every warp walks its tiles
   const int grid = (int)(want < persistent ? want : persistent);
   const FastConsts k = make_fast_consts(ctx->h_tab);
-  kern<<<grid, kFastThreads, smem, ctx->stream>>>(ctx->d_tab, k, (const unsigned char*)d_counts, n, ctx->d_bits,
-                                                  ctx->d_counters, d_dense);
+  kern<<<grid, kFastThreads, smem, st>>>(ctx->d_tab, k, (const unsigned char*)d_counts, n, ctx->d_bits, acc, d_dense);
   DNV_CUDA(cudaGetLastError());
   return DNV_OK;
 }
 
 template <bool kLin, bool kMap, bool kDense, int kMinBlocks>
-static int launch_fast_variant(dnv_ctx* ctx, const void* d_counts, int64_t n, dnv_site_result* d_dense) {
-  if (ctx->count_bytes == 12) return launch_fast_kernel<kLin, kMap, kDense, kMinBlocks, true>(ctx, d_counts, n, d_dense);
-  return launch_fast_kernel<kLin, kMap, kDense, kMinBlocks, false>(ctx, d_counts, n, d_dense);
+static int launch_fast_variant(dnv_ctx* ctx, cudaStream_t st, const void* d_counts, int64_t n, dnv_site_result* d_dense,
+                               unsigned long long* acc) {
+  if (ctx->count_bytes == 12) return launch_fast_kernel<kLin, kMap, kDense, kMinBlocks, true>(ctx, st, d_counts, n, d_dense, acc);
+  return launch_fast_kernel<kLin, kMap, kDense, kMinBlocks, false>(ctx, st, d_counts, n, d_dense, acc);
 }
 
-inline int launch_trio_fast(dnv_ctx* ctx, const void* d_counts, int64_t n, dnv_site_result* d_dense) {
+inline int launch_trio_fast(dnv_ctx* ctx, cudaStream_t st, const void* d_counts, int64_t n, dnv_site_result* d_dense,
+                            unsigned long long* acc) {
   const bool map = ctx->prm.method == DNV_METHOD_MAP;
-  if (d_dense) return launch_fast_variant<true, true, true, 2>(ctx, d_counts, n, d_dense);
-  if (map) return launch_fast_variant<false, true, false, 4>(ctx, d_counts, n, nullptr);
-  return launch_fast_variant<true, false, false, 3>(ctx, d_counts, n, nullptr);
+  if (d_dense) return launch_fast_variant<true, true, true, 2>(ctx, st, d_counts, n, d_dense, acc);
+  if (map) return launch_fast_variant<false, true, false, 4>(ctx, st, d_counts, n, nullptr, acc);
+  return launch_fast_variant<true, false, false, 3>(ctx, st, d_counts, n, nullptr, acc);
 }
 
 }  // namespace dnv

@@ -34,8 +34,19 @@
 
 namespace dnv {
 
+// The tail kernels are built to run BESIDE the screen of the next chunk.  An SM's register file is four
+// sub-partitions of 16384 registers; two resident screen CTAs (trio_screen.cuh) put four 64-register warps on
+// each, which leaves 8192 registers per sub-partition: TWO tail warps if — and only if — a tail thread needs at
+// most 128 registers.  Hence __launch_bounds__(128, 4) on both kernels (ptxas keeps them at 128 registers; the
+// few spills go to L1) and CTAs of four warps, one per sub-partition: two tail CTAs per SM fit next to the
+// screen, and the shared-memory request of the screen is padded so that a third screen CTA cannot take their
+// room.  Measured (benchmarks/ktrace.py): the list kernel of chunk k then starts ~2 us after its screen ends and
+// runs while the screen of chunk k+1 streams.
 constexpr int kListThreads = 128;
 constexpr int kListWarps = kListThreads / 32;
+constexpr int kFinishThreads = 128;
+constexpr int kFinishWarps = kFinishThreads / 32;
+constexpr int kTailCtasPerSm = 4;  // launch bound of both tail kernels: 128 registers per thread
 
 struct ListShared {
   double rel[1000];               // exact path: getRelationshipLogLikelihood
@@ -49,17 +60,18 @@ struct ListShared {
   unsigned long long excl;
 };
 
-// counters: [in_slot] calls before this chunk, [out_slot] <- calls after it, [1] += undecided sites,
-//           [4] += hard sites, [6] tile ticket, [5] CTAs gone (the last CTA to leave resets both for
-//           the next launch).
-// status word: [63:34] epoch of this launch, [33:32] 1 = tile aggregate, 2 = inclusive prefix, [31:0] value.
+// ch (CallChain, dnv_internal.cuh): *before = calls of this batch before this chunk, *after <- calls up to and
+//           including it (pair[0..1], private to the chunk), acc[1] += undecided sites, acc[2] += hard sites, work[0] tile ticket, work[1] CTAs gone
+//           (the last CTA to leave resets both for the next launch).
+// status word: [33:32] 1 = tile aggregate, 2 = inclusive prefix (0 = not published yet), [31:0] value.  The array is
+// all zero between launches: the last CTA to leave clears the entries the launch used, so a launch needs no tag and
+// can be replayed from a CUDA graph with identical arguments.
 template <bool kU8, bool kMap>
-__global__ void __launch_bounds__(kListThreads, 3)
+__global__ void __launch_bounds__(kListThreads, kTailCtasPerSm)
 trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsigned char* __restrict__ counts,
                  int64_t n, int64_t site_base, const uint32_t* __restrict__ list, const uint32_t* __restrict__ wcount,
                  uint32_t n_warps, uint32_t range_base, uint32_t range_rem, unsigned long long* status,
-                 unsigned long long epoch, unsigned long long* counters, int in_slot, int out_slot,
-                 int64_t cap, int64_t* count_out, dnv_call* __restrict__ stage) {
+                 const CallChain ch, int64_t cap, dnv_call* __restrict__ stage) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ListShared& s = *reinterpret_cast<ListShared*>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -71,27 +83,35 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
   auto stamp = [&](int) {};
 #endif
   stamp(0);
+  if (threadIdx.x == 0) ktrace_stamp(ch.ktrace, ch.ktrace_seq, 1, false);
   // the first tile is claimed before the prologue: by the time any CTA asks for its second tile, every
   // running CTA holds a first one, so tile order stays close to processing order (short look-back waits)
-  if (threadIdx.x == 0) s.ticket[0] = (unsigned int)atomicAdd(&counters[6], 1ull);
+  if (threadIdx.x == 0) s.ticket[0] = (unsigned int)atomicAdd(&ch.work[0], 1ull);
 
   // Prologue: every global load is issued before the first one is consumed (one round trip, not a
   // dependent chain): wcount[] (coalesced, kScreenMaxWarps / kListThreads words per thread) and this
   // thread's slice of the exact tables; then the block-wide scan of wcount[] in shared memory.
-  constexpr int kWLoads = kScreenMaxWarps / kListThreads;
+  constexpr int kWLoads = (kScreenMaxWarps + kListThreads - 1) / kListThreads;
   uint32_t wv[kWLoads];
 #pragma unroll
   for (int i = 0; i < kWLoads; i++) {
     const uint32_t j = i * kListThreads + threadIdx.x;
     wv[i] = j < n_warps ? __ldg(wcount + j) : 0u;
   }
-  double2 relv[4];
+  constexpr int kRelLoads = (500 + kListThreads - 1) / kListThreads;  // 500 double2 = rel[1000]
+  constexpr int kRmaxLoads = (110 + kListThreads - 1) / kListThreads;
+  double2 relv[kRelLoads];
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const int j = threadIdx.x + i * kListThreads;  // 500 double2 = rel[1000]
+  for (int i = 0; i < kRelLoads; i++) {
+    const int j = threadIdx.x + i * kListThreads;
     relv[i] = j < 500 ? __ldg(reinterpret_cast<const double2*>(tab->rel) + j) : make_double2(0.0, 0.0);
   }
-  const double rmaxv = threadIdx.x < 110 ? (threadIdx.x < 100 ? tab->rmax_dm[threadIdx.x] : tab->rmax_d[threadIdx.x - 100]) : 0.0;
+  double rmaxv[kRmaxLoads];
+#pragma unroll
+  for (int i = 0; i < kRmaxLoads; i++) {
+    const int j = threadIdx.x + i * kListThreads;
+    rmaxv[i] = j < 110 ? (j < 100 ? tab->rmax_dm[j] : tab->rmax_d[j - 100]) : 0.0;
+  }
   const uint32_t isdenv = threadIdx.x < 32 ? tab->isden[threadIdx.x] : 0u;
 #pragma unroll
   for (int i = 0; i < kWLoads; i++) {
@@ -99,11 +119,15 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
     if (j < n_warps) s.woff[j] = wv[i];
   }
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
+  for (int i = 0; i < kRelLoads; i++) {
     const int j = threadIdx.x + i * kListThreads;
     if (j < 500) reinterpret_cast<double2*>(s.rel)[j] = relv[i];
   }
-  if (threadIdx.x < 110) s.rmax[threadIdx.x] = rmaxv;
+#pragma unroll
+  for (int i = 0; i < kRmaxLoads; i++) {
+    const int j = threadIdx.x + i * kListThreads;
+    if (j < 110) s.rmax[j] = rmaxv[i];
+  }
   if (threadIdx.x < 32) s.isden[threadIdx.x] = isdenv;
   __syncthreads();
   // one contiguous run of `per` entries per thread (odd or not, scalar accesses at stride `per` words
@@ -136,13 +160,15 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
   __syncthreads();
 
   const uint32_t n_tiles = (total_items + kListThreads - 1) / kListThreads;
-  const unsigned long long calls_before = counters[in_slot];
-  const unsigned long long tag = epoch << 34;
+  const unsigned long long calls_before = ch.before ? *ch.before : 0ull;
+  constexpr unsigned long long tag = 0;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
-    atomicAdd(&counters[1], (unsigned long long)total_items);  // summed over the chunks of a batch
+    atomicAdd(&ch.acc[1], (unsigned long long)total_items);  // summed until the host collects the statistics
     if (n_tiles == 0) {  // nothing undecided: the call total carries over
-      counters[out_slot] = calls_before;
-      if (count_out) *count_out = (int64_t)calls_before;
+      ch.pair[0] = calls_before;
+      ch.pair[1] = calls_before;
+      if (ch.count_out) *ch.count_out = (int64_t)calls_before;
+      if (ch.last) atomicAdd(&ch.acc[0], calls_before);
     }
   }
   const GmemPow pw{tab};
@@ -175,7 +201,7 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
   int trip = 0;
   while (tile < n_tiles) {
     trip ^= 1;
-    if (threadIdx.x == 0) s.ticket[trip] = (unsigned int)atomicAdd(&counters[6], 1ull);  // read after this trip's first barrier
+    if (threadIdx.x == 0) s.ticket[trip] = (unsigned int)atomicAdd(&ch.work[0], 1ull);  // read after this trip's first barrier
     const uint32_t item = tile * kListThreads + threadIdx.x;
     const bool live = item < total_items;
     const uint32_t site = site_cur;
@@ -213,7 +239,7 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
       // hard sites: the whole warp evaluates them one at a time with the exact direct form
       uint32_t hword = __ballot_sync(0xffffffffu, lo_.hard);
       if (hword) {
-        if (lane == 0) atomicAdd(&counters[4], (unsigned long long)__popc(hword));
+        if (lane == 0) atomicAdd(&ch.acc[2], (unsigned long long)__popc(hword));
         while (hword) {
           const int h = __ffs(hword) - 1;
           hword &= hword - 1;
@@ -250,7 +276,7 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
           const int p = hi_t - lane;
           unsigned long long v = tag | (2ull << 32);  // lanes before tile 0 act as an empty inclusive prefix
           if (p >= 0) {
-            do { v = *(volatile unsigned long long*)&status[p]; } while ((v >> 34) != epoch);
+            do { v = *(volatile unsigned long long*)&status[p]; } while (((v >> 32) & 3ull) == 0ull);
           }
           const uint32_t is_prefix = __ballot_sync(0xffffffffu, ((v >> 32) & 3ull) == 2ull);
           const int stop = is_prefix ? __ffs(is_prefix) - 1 : 31;  // nearest inclusive prefix in this window
@@ -267,8 +293,10 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
         s.excl = excl;
         if (tile == n_tiles - 1) {
           const unsigned long long all = calls_before + excl + (unsigned long long)total;
-          counters[out_slot] = all;
-          if (count_out) *count_out = (int64_t)all;
+          ch.pair[0] = calls_before;
+          ch.pair[1] = all;
+          if (ch.count_out) *ch.count_out = (int64_t)all;
+          if (ch.last) atomicAdd(&ch.acc[0], all);
         }
       }
     }
@@ -308,12 +336,20 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
   stamp(3);
   __syncthreads();
   stamp(5);
-  // the last CTA to leave resets the ticket for the next launch (every ticket has been taken by then)
+  // the last CTA to leave clears the status entries this launch used and resets the ticket for the next launch
+  // (by then every ticket has been taken and every look-back has finished)
+  __shared__ int s_is_last;
   if (threadIdx.x == 0) {
+    ktrace_stamp(ch.ktrace, ch.ktrace_seq, 1, true);
     __threadfence();
-    if (atomicAdd(&counters[5], 1ull) == (unsigned long long)gridDim.x - 1ull) {
-      counters[5] = 0;
-      counters[6] = 0;
+    s_is_last = atomicAdd(&ch.work[1], 1ull) == (unsigned long long)gridDim.x - 1ull;
+  }
+  __syncthreads();
+  if (s_is_last) {
+    for (uint32_t i = threadIdx.x; i < n_tiles; i += kListThreads) status[i] = 0ull;
+    if (threadIdx.x == 0) {
+      ch.work[1] = 0;
+      ch.work[0] = 0;
     }
   }
 }
@@ -326,18 +362,18 @@ struct FinishShared {
   double rel[1000];
   double rmax[110];
   uint32_t isden[32];
-  alignas(16) uint4 rec[kListWarps][32 * 5];  // one warp's 32 records
+  alignas(16) uint4 rec[kFinishWarps][32 * 5];  // one warp's 32 records
 };
 
 template <bool kMap>
-__global__ void __launch_bounds__(kListThreads)
-trio_calls_finish_kernel(const Tables* __restrict__ tab, const FastConsts k, unsigned long long* __restrict__ counters,
-                         int in_slot, int out_slot, const dnv_call* __restrict__ stage, dnv_call* __restrict__ calls,
-                         int64_t cap) {
-  const unsigned long long calls_before = counters[in_slot];
-  unsigned long long all = counters[out_slot];
+__global__ void __launch_bounds__(kFinishThreads, kTailCtasPerSm)
+trio_calls_finish_kernel(const Tables* __restrict__ tab, const FastConsts k, const CallChain ch,
+                         const dnv_call* __restrict__ stage, dnv_call* __restrict__ calls, int64_t cap) {
+  if (threadIdx.x == 0) ktrace_stamp(ch.ktrace, ch.ktrace_seq, 2, false);
+  const unsigned long long calls_before = ch.pair[0];  // written by the list kernel of this chunk
+  unsigned long long all = ch.pair[1];
   if (all > (unsigned long long)cap) all = (unsigned long long)cap;
-  if (calls_before + (unsigned long long)blockIdx.x * kListThreads >= all) return;  // block-uniform: no call for this CTA
+  if (calls_before + (unsigned long long)blockIdx.x * kFinishThreads >= all) return;  // block-uniform: no call for this CTA
   __shared__ FinishShared s;
   stage_exact_tables(tab, s.rel, s.isden);
   stage_map_bounds(tab, s.rmax);
@@ -347,8 +383,8 @@ trio_calls_finish_kernel(const Tables* __restrict__ tab, const FastConsts k, uns
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   {
     // warp-uniform loop: the warp's first call, 32 consecutive calls per trip
-    for (unsigned long long w0 = calls_before + (unsigned long long)blockIdx.x * kListThreads + (unsigned long long)warp * 32;
-         w0 < all; w0 += (unsigned long long)gridDim.x * kListThreads) {
+    for (unsigned long long w0 = calls_before + (unsigned long long)blockIdx.x * kFinishThreads + (unsigned long long)warp * 32;
+         w0 < all; w0 += (unsigned long long)gridDim.x * kFinishThreads) {
       const int n_rec = (int)min((unsigned long long)32, all - w0);
       const unsigned long long pos = w0 + lane;
       // coalesced read of the warp's staged records (local HBM) into shared memory
@@ -382,7 +418,7 @@ trio_calls_finish_kernel(const Tables* __restrict__ tab, const FastConsts k, uns
           exact_site(u.r.counts, s.rel, s.isden, k.hm, k.ht, k.mm, k.method, k.lrt_threshold, &r);
           u.r.p = r.p; u.r.lr = r.lr; u.r.log_men = r.log_men; u.r.log_den = r.log_den;
           u.r.flags = 1;
-          atomicAdd(&counters[4], 1ull);
+          atomicAdd(&ch.acc[2], 1ull);
         } else {
           linear_values(lv, u.r.p, u.r.lr, u.r.log_men, u.r.log_den);
         }
@@ -412,23 +448,39 @@ trio_calls_finish_kernel(const Tables* __restrict__ tab, const FastConsts k, uns
       }
     }
   }
+  if (threadIdx.x == 0) ktrace_stamp(ch.ktrace, ch.ktrace_seq, 2, true);
 }
 
+// tail CTAs (four 128-register warps, one per sub-partition) that fit on an SM beside the resident screen CTAs:
+// (16384 - screen warps per sub-partition * 32 * 64) / (32 * 128)
+inline int tail_ctas_beside_screen() {
+  const int screen_warps = screen_config().per_sm * kScreenWarps / 4;
+  return std::max(1, (16384 - screen_warps * 2048) / 4096);
+}
+
+// Launches the list kernel (after the previous chain-extending kernel: ctx->ev_chain) and the finish kernel on
+// stream `st`, reading lane `ln`'s list and staging its records in the lane's scratch.
 template <bool kU8, bool kMap>
-static int launch_trio_list(dnv_ctx* ctx, const void* d_counts, int64_t n, int64_t site_base, int screen_grid_size,
-                            int in_slot, int out_slot, dnv_call* d_calls, int64_t cap) {
+static int launch_trio_list(dnv_ctx* ctx, TrioLane& ln, cudaStream_t st, const void* d_counts, int64_t n, int64_t site_base,
+                            int screen_grid_size, const CallChain& ch, dnv_call* d_calls, int64_t cap, bool beside_screen) {
   const int sms = ctx->sms;
   const size_t smem = sizeof(ListShared);
   auto kern = trio_list_kernel<kU8, kMap>;
   int& per_sm = ctx->list_per_sm[kU8 ? 1 : 0][kMap ? 1 : 0];
   if (per_sm == 0) {  // first launch on this context
     DNV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // same shared-memory configuration as the screen's, so that both can be resident on one SM (trio_screen.cuh)
+    DNV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    DNV_CUDA(cudaFuncSetAttribute(trio_calls_finish_kernel<kMap>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int q = 1;
     DNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, kListThreads, smem));
     per_sm = std::max(q, 1);
   }
+  // beside_screen: another chunk's screen is (about to be) resident with three CTAs per SM, which leaves room for
+  // exactly one tail CTA per SM — a larger grid would only queue CTAs behind that screen and delay the kernel's
+  // completion.  Alone (last chunk of a synchronous call, serial contexts) the kernel takes the whole machine.
   const int64_t want = (n + kListThreads - 1) / kListThreads;
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sms * per_sm));
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sms * (beside_screen ? tail_ctas_beside_screen() : per_sm)));
   const uint32_t n_tiles = (uint32_t)((n + kScreenSites - 1) / kScreenSites);
   const uint32_t n_warps = (uint32_t)screen_grid_size * kScreenWarps;
   if (reinterpret_cast<uintptr_t>(d_calls) & 15) {
@@ -437,24 +489,29 @@ static int launch_trio_list(dnv_ctx* ctx, const void* d_counts, int64_t n, int64
   }
   // local scratch for the records between the two phases: at most min(cap, n) calls in this chunk
   const int64_t need = std::max<int64_t>(1, std::min(cap, n));
-  if (need > ctx->list_stage_cap) {
-    cudaFree(ctx->d_list_stage);
-    ctx->d_list_stage = nullptr;
-    ctx->list_stage_cap = 0;
-    DNV_CUDA(cudaMalloc(&ctx->d_list_stage, (size_t)need * sizeof(dnv_call)));
-    ctx->list_stage_cap = need;
+  if (need > ln.list_stage_cap) {
+    if (ctx->capturing) { set_error("internal: scratch growth during graph capture"); return DNV_E_INVALID; }
+    cudaFree(ln.d_list_stage);  // (synchronises the device: nothing in flight still uses the old buffer)
+    ln.d_list_stage = nullptr;
+    ln.list_stage_cap = 0;
+    DNV_CUDA(cudaMalloc(&ln.d_list_stage, (size_t)need * sizeof(dnv_call)));
+    ln.list_stage_cap = need;
   }
   const FastConsts fk = make_fast_consts(ctx->h_tab);
-  unsigned long long tag = 0;
-  { const int erc = next_epoch(ctx, &tag); if (erc) return erc; }
-  kern<<<grid, kListThreads, smem, ctx->stream>>>(ctx->d_tab, fk, (const unsigned char*)d_counts, n, site_base, ctx->d_list,
-                                                  ctx->d_wcount, n_warps, n_tiles / n_warps, n_tiles % n_warps,
-                                                  ctx->d_tile_status, tag, ctx->d_counters, in_slot, out_slot, cap,
-                                                  ctx->count_out, ctx->d_list_stage);
+  static const int dbg_skip = [] { const char* e = getenv("DNV_DEBUG_SKIP"); return e ? atoi(e) : 0; }();  // 1: no tail, 2: no finish
+  if (dbg_skip == 1) return DNV_OK;
+  // chunks of one batch: this chunk's records start where the previous chunk's end (tickets and look-back status
+  // are private to the lane, so lists of different batches need no ordering)
+  if (parallel(ctx) && ch.before) DNV_CUDA(cudaStreamWaitEvent(st, ctx->ev_chain, 0));
+  kern<<<grid, kListThreads, smem, st>>>(ctx->d_tab, fk, (const unsigned char*)d_counts, n, site_base, ln.d_list,
+                                        ln.d_wcount, n_warps, n_tiles / n_warps, n_tiles % n_warps,
+                                        ln.d_tile_status, ch, cap, ln.d_list_stage);
+  if (parallel(ctx) && !ch.last) DNV_CUDA(cudaEventRecord(ctx->ev_chain, st));
   // one thread per call; CTAs beyond the number of calls leave at once
-  const int fgrid = (int)std::max<int64_t>(1, std::min<int64_t>((need + kListThreads - 1) / kListThreads, (int64_t)sms * 2));
-  trio_calls_finish_kernel<kMap><<<fgrid, kListThreads, 0, ctx->stream>>>(ctx->d_tab, fk, ctx->d_counters, in_slot, out_slot,
-                                                                          ctx->d_list_stage, d_calls, cap);
+  const int fgrid = (int)std::max<int64_t>(1, std::min<int64_t>((need + kFinishThreads - 1) / kFinishThreads,
+                                                                (int64_t)sms * (beside_screen ? tail_ctas_beside_screen() : 4)));
+  if (dbg_skip != 2)
+    trio_calls_finish_kernel<kMap><<<fgrid, kFinishThreads, 0, st>>>(ctx->d_tab, fk, ch, ln.d_list_stage, d_calls, cap);
   DNV_CUDA(cudaGetLastError());
   return DNV_OK;
 }

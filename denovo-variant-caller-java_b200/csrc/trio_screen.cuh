@@ -39,12 +39,13 @@ namespace dnv {
 
 constexpr int kScreenThreads = 256;
 constexpr int kScreenWarps = kScreenThreads / 32;
-constexpr int kScreenBufs = 2;  // tile buffers per warp, refilled as soon as their tile sits in registers
 
 struct ScreenConsts {
   uint32_t c_hom, c_het;  // log2(r_hom), log2(r_het) in 16.16 fixed point
   uint32_t w[4];          // level 1 weights per candidate allele (Tables::scr_w)
   uint32_t shift32;       // 32 (a run-time value the assembler cannot fold: x >> 32 == 0 orders the tile refill)
+  unsigned long long* ktrace;  // DNV_KTRACE time line of the lane, or null
+  const unsigned int* ktrace_seq;
 };
 
 // One person: keys are (count << 2) | allele, so integer max/min order counts and carry the
@@ -138,14 +139,15 @@ __device__ __forceinline__ bool screen_level1(const uint32_t* w, const ScreenCon
 constexpr int kScreenSites = 128;
 constexpr int kScreenPerLane = kScreenSites / 32;
 constexpr int kScreenRing = 64;       // ring entries (site indices): at most 31 + 32 waiting
-constexpr int kScreenMaxWarps = 8192; // upper bound of gridDim.x * kScreenWarps (sizes wcount and its scan)
+constexpr int kScreenMaxWarps = 4096; // upper bound of gridDim.x * kScreenWarps (sizes wcount and its scan: 16 KB of ListShared)
 
 // tiles [lo, hi) of warp g when n_tiles tiles are dealt to W warps in contiguous, balanced ranges
 __host__ __device__ __forceinline__ uint32_t screen_range_lo(uint32_t g, uint32_t base, uint32_t rem) {
   return g * base + (g < rem ? g : rem);
 }
 
-template <bool kU8>
+// kScreenBufs: tile buffers per warp, refilled as soon as their tile sits in registers
+template <bool kU8, int kScreenBufs>
 __global__ void __launch_bounds__(kScreenThreads, 4)
 trio_screen_kernel(const unsigned char* __restrict__ counts, int64_t n, const ScreenConsts k,
                    uint32_t* __restrict__ list, uint32_t* __restrict__ wcount) {
@@ -158,6 +160,7 @@ trio_screen_kernel(const unsigned char* __restrict__ counts, int64_t n, const Sc
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw + kScreenWarps * kScreenBufs * kTile);
   uint32_t* rings = reinterpret_cast<uint32_t*>(bars + kScreenWarps * kScreenBufs);  // [kScreenWarps][parked | undecided]
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) ktrace_stamp(k.ktrace, k.ktrace_seq, 0, false);
   const uint32_t lt_mask = (1u << lane) - 1u;
   unsigned char* my_tiles = tiles + (size_t)warp * kScreenBufs * kTile;
   unsigned long long* my_bars = bars + warp * kScreenBufs;
@@ -284,22 +287,51 @@ trio_screen_kernel(const unsigned char* __restrict__ counts, int64_t n, const Sc
   }
   if (fcount > 0) flush(fcount);
   if (lane == 0) wcount[g] = written;
+  if (lane == 0) ktrace_stamp(k.ktrace, k.ktrace_seq, 0, true);
+}
+
+// launch configuration of the screen: resident CTAs per SM and tile buffers per warp.
+// Default: THREE CTAs per SM, and room for one CTA of the tail kernels (trio_list.cuh) beside them: registers
+// work out by themselves (3 * 256 * 64 of 65536), shared memory is padded so that a FOURTH screen CTA — of the
+// next chunk, launched on another lane while this one is still running — cannot take that room
+// (4 * (57 KB + 1 KB) > 228 KB per SM; 3 * 58 KB leave 54 KB: ListShared is 42 KB).
+// DNV_SCREEN_CTAS = 2 | 3 | 4 and DNV_SCREEN_BUFS = 2 | 3 are A/B knobs (4 = the round-1 configuration: four CTAs
+// per SM and no room for the tail).
+struct ScreenConfig { int per_sm, bufs; };
+inline ScreenConfig screen_config() {
+  static const ScreenConfig c = [] {
+    const char* e = getenv("DNV_SCREEN_CTAS");
+    const char* b = getenv("DNV_SCREEN_BUFS");
+    ScreenConfig r;
+    r.per_sm = e ? atoi(e) : 2;
+    if (r.per_sm < 1 || r.per_sm > 4) r.per_sm = 2;
+    r.bufs = b ? atoi(b) : 2;
+    if (r.bufs < 2 || r.bufs > 4) r.bufs = 2;
+    return r;
+  }();
+  return c;
 }
 
 // grid of the screen (and so the warp -> tile-range map the list kernel has to reproduce)
-template <bool kU8>
+template <bool kU8, int kBufs>
 static int screen_grid(dnv_ctx* ctx, int64_t n, size_t* smem_out) {
   const int sms = ctx->sms;
   constexpr int kTile = kScreenSites * (kU8 ? 12 : 24);
-  const size_t smem = (size_t)kScreenWarps * kScreenBufs * kTile + kScreenWarps * kScreenBufs * 8 +
-                      (size_t)kScreenWarps * 2 * kScreenRing * 4;
-  auto kern = trio_screen_kernel<kU8>;
+  size_t smem = (size_t)kScreenWarps * kBufs * kTile + kScreenWarps * kBufs * 8 + (size_t)kScreenWarps * 2 * kScreenRing * 4;
+  const int want_per_sm = screen_config().per_sm;
+  if (want_per_sm == 3) smem = std::max<size_t>(smem, 57 * 1024);
+  if (want_per_sm == 2) smem = std::max<size_t>(smem, 76 * 1024);
+  if (want_per_sm == 1) smem = std::max<size_t>(smem, 114 * 1024);
+  auto kern = trio_screen_kernel<kU8, kBufs>;
   int& per_sm = ctx->screen_per_sm[kU8 ? 1 : 0];
   if (per_sm == 0) {  // first launch on this context
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    // the SM keeps its largest shared-memory configuration while the screen is resident: a smaller carve-out (just
+    // enough for the screen's own CTAs) would have to be re-made, on a drained SM, before a tail CTA could join
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess) return -1;
     int q = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, kScreenThreads, smem) != cudaSuccess) return -1;
-    per_sm = std::max(q, 1);
+    per_sm = std::max(std::min(q, want_per_sm), 1);
   }
   const int64_t want = ((n + kScreenSites - 1) / kScreenSites + kScreenWarps - 1) / kScreenWarps;
   int64_t grid = std::min<int64_t>(std::max<int64_t>(want, 1), (int64_t)sms * std::max(per_sm, 1));
@@ -308,16 +340,24 @@ static int screen_grid(dnv_ctx* ctx, int64_t n, size_t* smem_out) {
   return (int)grid;
 }
 
-template <bool kU8>
-static int launch_screen(dnv_ctx* ctx, const void* d_counts, int64_t n, const ScreenConsts& sk, int* grid_out) {
+template <bool kU8, int kBufs>
+static int launch_screen_bufs(dnv_ctx* ctx, TrioLane& ln, cudaStream_t st, const void* d_counts, int64_t n, const ScreenConsts& sk,
+                              int* grid_out) {
   size_t smem = 0;
-  const int grid = screen_grid<kU8>(ctx, n, &smem);
+  const int grid = screen_grid<kU8, kBufs>(ctx, n, &smem);
   if (grid < 1) { set_error("trio_screen_kernel: launch configuration failed"); return DNV_E_CUDA; }
-  trio_screen_kernel<kU8><<<grid, kScreenThreads, smem, ctx->stream>>>((const unsigned char*)d_counts, n, sk, ctx->d_list,
-                                                                      ctx->d_wcount);
+  trio_screen_kernel<kU8, kBufs><<<grid, kScreenThreads, smem, st>>>((const unsigned char*)d_counts, n, sk, ln.d_list, ln.d_wcount);
   DNV_CUDA(cudaGetLastError());
   *grid_out = grid;
   return DNV_OK;
+}
+
+template <bool kU8>
+static int launch_screen(dnv_ctx* ctx, TrioLane& ln, cudaStream_t st, const void* d_counts, int64_t n, const ScreenConsts& sk,
+                         int* grid_out) {
+  if (screen_config().bufs == 4) return launch_screen_bufs<kU8, 4>(ctx, ln, st, d_counts, n, sk, grid_out);
+  if (screen_config().bufs == 3) return launch_screen_bufs<kU8, 3>(ctx, ln, st, d_counts, n, sk, grid_out);
+  return launch_screen_bufs<kU8, 2>(ctx, ln, st, d_counts, n, sk, grid_out);
 }
 
 }  // namespace dnv

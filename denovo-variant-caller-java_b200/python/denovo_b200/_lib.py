@@ -23,7 +23,9 @@ F_NO_SCREEN = 4
 EXPORTS = ["dnv_create", "dnv_destroy", "dnv_last_error", "dnv_abi_version", "dnv_get_tables", "dnv_get_stats",
            "dnv_set_stream",
            "dnv_infer_counts", "dnv_infer_counts_device", "dnv_infer_counts8", "dnv_infer_counts8_device",
-           "dnv_infer_counts_device_async", "dnv_infer_counts8_device_async", "dnv_sync", "dnv_pileup", "dnv_pileup_device",
+           "dnv_infer_counts_device_async", "dnv_infer_counts8_device_async",
+           "dnv_infer_counts_device_async_at", "dnv_infer_counts8_device_async_at", "dnv_flush", "dnv_sync",
+           "dnv_alloc_pinned", "dnv_free_pinned", "dnv_pileup", "dnv_pileup_device",
            "dnv_mendel_filter", "dnv_mendel_filter_device", "dnv_synth_counts_device", "dnv_synth_counts_at_device",
            "dnv_synth_counts_at", "dnv_measure_fp64_peak"]
 
@@ -88,7 +90,12 @@ def load():
     L.dnv_infer_counts8_device.argtypes = [vp, vp, i64, vp, vp, i64, C.POINTER(i64)]
     L.dnv_infer_counts_device_async.argtypes = [vp, vp, i64, vp, i64, vp]
     L.dnv_infer_counts8_device_async.argtypes = [vp, vp, i64, vp, i64, vp]
+    L.dnv_infer_counts_device_async_at.argtypes = [vp, vp, i64, i64, vp, i64, vp]
+    L.dnv_infer_counts8_device_async_at.argtypes = [vp, vp, i64, i64, vp, i64, vp]
+    L.dnv_flush.argtypes = [vp]
     L.dnv_sync.argtypes = [vp]
+    L.dnv_alloc_pinned.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.dnv_free_pinned.argtypes = [vp]
     L.dnv_pileup.argtypes = [vp, vp, vp, vp, vp, i64, vp, i64, vp]
     L.dnv_pileup_device.argtypes = [vp, vp, vp, vp, vp, i64, vp, i64, vp]
     L.dnv_mendel_filter.argtypes = [vp, vp, i64, vp, i64, C.POINTER(i64)]

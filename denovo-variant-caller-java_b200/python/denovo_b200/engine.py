@@ -60,6 +60,11 @@ class BatchPipeline:
         self.engines[self.k % len(self.engines)].infer_device_async(d_counts, n, d_calls, cap, n_calls_out, u8=u8)
         self.k += 1
 
+    def flush(self):
+        """Device-side join of every context (each context's stream waits for its batches; no host wait)."""
+        for e in self.engines:
+            e.flush()
+
     def sync(self):
         """Wait for every submitted batch; returns the stats summed over the contexts."""
         tot = None
@@ -156,11 +161,16 @@ class TrioEngine:
         L.check(fn(self._h, L.ptr(d_counts), n, L.ptr(d_dense), L.ptr(d_calls), cap, C.byref(nc)))
         return nc.value
 
-    def infer_device_async(self, d_counts, n, d_calls, cap, h_n_calls, u8=False):
+    def infer_device_async(self, d_counts, n, d_calls, cap, h_n_calls, u8=False, site_base=0):
         """Enqueue one batch without waiting; h_n_calls = pinned host int64 slot (tensor / array / address)
-        that receives the batch's call count in stream order.  Pair with sync()."""
-        fn = self.lib.dnv_infer_counts8_device_async if u8 else self.lib.dnv_infer_counts_device_async
-        L.check(fn(self._h, L.ptr(d_counts), n, L.ptr(d_calls), cap, L.ptr(h_n_calls)))
+        that receives the batch's call count in stream order.  site_base is added to the records' site
+        indices (interval shards).  Pair with flush() / sync()."""
+        fn = self.lib.dnv_infer_counts8_device_async_at if u8 else self.lib.dnv_infer_counts_device_async_at
+        L.check(fn(self._h, L.ptr(d_counts), n, site_base, L.ptr(d_calls), cap, L.ptr(h_n_calls)))
+
+    def flush(self):
+        """Device-side join: the context's stream waits for every enqueued batch (no host wait)."""
+        L.check(self.lib.dnv_flush(self._h))
 
     def sync(self):
         """Wait for every enqueued batch; stats() then holds the sums over those batches."""

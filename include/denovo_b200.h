@@ -23,8 +23,9 @@
  *    a negative DNV_E_* code; dnv_last_error() gives the thread-local message.
  *  - the caller owns every buffer it passes; the library never retains caller
  *    pointers after return and never frees them.  Device scratch lives in dnv_ctx.
- *  - a dnv_ctx is bound to one CUDA device and is NOT re-entrant (one call in
- *    flight per ctx); different ctxs may be driven from different host threads.
+ *  - a dnv_ctx is bound to one CUDA device and is NOT re-entrant (one host call at a
+ *    time per ctx; internally it is multi-stream); different ctxs may be driven from
+ *    different host threads.
  *  - results are returned in INPUT ORDER (deterministic), unlike the reference's
  *    thread-race-ordered output file (M/ReadCaller.java:122-129).
  *  - there is no CPU fallback: without a CUDA device dnv_create fails with
@@ -40,13 +41,14 @@
 #ifndef DENOVO_B200_H
 #define DENOVO_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define DNV_ABI_VERSION 1
+#define DNV_ABI_VERSION 2
 
 enum {
   DNV_OK = 0,
@@ -189,8 +191,11 @@ int dnv_infer_counts_device(dnv_ctx *ctx, const uint16_t *d_counts, int64_t n,
                             int64_t cap, int64_t *n_calls);
 
 /* Asynchronous form for streams of batches (a genome walked chunk by chunk, a candidate
- * file read block by block): enqueues the whole pipeline on the ctx's stream and returns
- * without waiting.  The number of calls of this batch is STORED BY THE LAST KERNEL into
+ * file read block by block): enqueues the whole pipeline and returns without waiting.  The batch
+ * starts when the work already enqueued on the ctx's stream has finished (so inputs produced there are
+ * ready) and runs on one of the ctx's internal lanes (streams): the bandwidth-bound screen of one batch
+ * overlaps the short latency-bound kernels of the previous ones.  Inputs and outputs of a batch must stay
+ * untouched until dnv_flush / dnv_sync.  The number of calls of this batch is STORED BY THE LAST KERNEL into
  * *n_calls_out, which must be device-writable: pinned host memory (cudaHostAlloc /
  * cudaHostRegister, mapped under UVA), this GPU's memory, or a peer GPU's memory mapped
  * here (the multi-GPU gather puts it next to the records in rank 0's HBM); call
@@ -198,12 +203,22 @@ int dnv_infer_counts_device(dnv_ctx *ctx, const uint16_t *d_counts, int64_t n,
  * are not written (compare *n_calls_out with cap).  Scratch inside the ctx is reused in
  * stream order, so batches may be enqueued back to back; each batch needs its own d_calls
  * and n_calls_out if the results are to outlive the next batch.  dnv_get_stats after
- * dnv_sync reports the sums over the batches enqueued since the previous dnv_sync
- * (at most 64 batches between two dnv_sync calls). */
+ * dnv_sync reports the sums over the batches enqueued since the previous dnv_sync. */
 int dnv_infer_counts_device_async(dnv_ctx *ctx, const uint16_t *d_counts, int64_t n,
                                   dnv_call *d_calls, int64_t cap, int64_t *n_calls_out);
 int dnv_infer_counts8_device_async(dnv_ctx *ctx, const uint8_t *d_counts8, int64_t n,
                                    dnv_call *d_calls, int64_t cap, int64_t *n_calls_out);
+/* Same, with site_base added to dnv_call.site: the batch is one interval shard [site_base, site_base + n)
+ * of a larger axis and its records carry GLOBAL site indices (what the gather of section "multi-GPU" and a
+ * chunked genome walk want). */
+int dnv_infer_counts_device_async_at(dnv_ctx *ctx, const uint16_t *d_counts, int64_t n, int64_t site_base,
+                                     dnv_call *d_calls, int64_t cap, int64_t *n_calls_out);
+int dnv_infer_counts8_device_async_at(dnv_ctx *ctx, const uint8_t *d_counts8, int64_t n, int64_t site_base,
+                                      dnv_call *d_calls, int64_t cap, int64_t *n_calls_out);
+/* Device-side join: the ctx's stream (see dnv_set_stream) waits for every batch enqueued so far, the host does
+ * not.  Work enqueued on that stream afterwards (the caller's own kernels, copies, timing events) sees the
+ * results.  dnv_sync = dnv_flush + host wait + statistics. */
+int dnv_flush(dnv_ctx *ctx);
 int dnv_sync(dnv_ctx *ctx);
 
 /* Compact input variants: counts as uint8 [n][3][4] (12 bytes per site) for pileups whose
@@ -259,6 +274,80 @@ int dnv_synth_counts_at_device(dnv_ctx *ctx, uint64_t seed, const int64_t *d_ind
 /* Host-buffer convenience wrapper of the above (index and counts on the host). */
 int dnv_synth_counts_at(dnv_ctx *ctx, uint64_t seed, const int64_t *index, int64_t n,
                         const uint64_t *thr, int32_t n_thr, uint32_t err_thr, uint16_t *counts);
+
+/* ---- multi-GPU: interval shards and the gather of call records ---------------- */
+/* Sites shard by genomic interval: rank r infers the r-th contiguous range of the axis, so rank order =
+ * genomic order and the ranks never exchange data while they compute.  The one exchange is the final gather
+ * of the call records to one rank — the reference's shared PrintWriter behind `synchronized writeCalls`
+ * (M/DenovoCaller.java:56-59, M/ReadCaller.java:122-129) fed by independent per-site tasks
+ * (M/ReadCaller.java:91-95) and per-thread position shards (M/VariantCaller.java:86-103).  It is fused into
+ * the producing kernels: every rank's kernels store their records and counts straight into the destination
+ * rank's HBM over NVLink; one flag per rank and round tells the destination that everything has landed.
+ *
+ * One process per GPU (torchrun, MPI):            One process, N GPUs:
+ *   every rank   dnv_gather_create                  dnv_group_create / dnv_group_infer_counts (below), or
+ *   dst          dnv_gather_export -> 64 bytes      dnv_gather_create per device + dnv_gather_attach
+ *   launcher     broadcasts the 64 bytes
+ *   others       dnv_gather_import
+ * then, per round:  dnv_infer_counts[8]_device_gather (any number of batches, generation = batch % gens)
+ *                   dnv_gather_arrive on every rank;  dst: dnv_gather_wait, [dnv_sync,] dnv_gather_fetch.
+ * A generation's slots may be rewritten once the destination has fetched them (the caller orders that:
+ * program order in one process, its launcher's barrier between processes). */
+typedef struct dnv_gather dnv_gather;
+#define DNV_GATHER_HANDLE_BYTES 64
+/* This rank's end of a gather of `world` ranks to rank `dst`: up to cap records per rank and generation,
+ * gens generations of slots.  The end of rank dst allocates the destination buffer in its HBM. */
+int dnv_gather_create(dnv_ctx *ctx, int32_t world, int32_t rank, int32_t dst, int64_t cap, int32_t gens,
+                      dnv_gather **out);
+int dnv_gather_destroy(dnv_gather *g);
+/* dst: the 64-byte inter-process handle of the destination buffer; others: map it. */
+int dnv_gather_export(dnv_gather *g, void *handle64);
+int dnv_gather_import(dnv_gather *g, const void *handle64);
+/* Same process: map the destination buffer through peer access (the two ends may share a device). */
+int dnv_gather_attach(dnv_gather *g, dnv_gather *dst_end);
+/* Where rank `rank` writes generation `gen`, as THIS end's device sees it (on dst: where to read it). */
+int dnv_gather_slot(dnv_gather *g, int32_t rank, int32_t gen, dnv_call **records, int64_t **count);
+/* dnv_infer_counts[8]_device_async_at whose records and count land in this rank's slot of generation gen:
+ * the shard [site_base, site_base + n) of the axis, records carrying GLOBAL site indices. */
+int dnv_infer_counts_device_gather(dnv_ctx *ctx, const uint16_t *d_counts, int64_t n, int64_t site_base,
+                                   dnv_gather *g, int32_t gen);
+int dnv_infer_counts8_device_gather(dnv_ctx *ctx, const uint8_t *d_counts8, int64_t n, int64_t site_base,
+                                    dnv_gather *g, int32_t gen);
+/* Every rank, after the batches of a round: dnv_flush + a release flag in the destination (on the device,
+ * no host wait). */
+int dnv_gather_arrive(dnv_gather *g);
+/* dst, after its own dnv_gather_arrive: the ctx's stream waits (on the device) until every rank has arrived
+ * at this round.  Work enqueued on that stream afterwards — timing events, copies — sees all records. */
+int dnv_gather_wait(dnv_gather *g);
+/* dst: waits for the ctx's stream, then copies generation gen to the host in rank order = genomic order.
+ * per_rank (world entries) may be NULL.  DNV_E_CAPACITY if cap (or a rank's slot) was too small, with the
+ * required total in *n_calls; DNV_E_CUDA if a rank never arrived (10 s). */
+int dnv_gather_fetch(dnv_gather *g, int32_t gen, dnv_call *calls, int64_t cap, int64_t *n_calls,
+                     int64_t *per_rank);
+
+/* N devices driven by one process: what a single-process host (the CLI, the Java binding) uses instead of
+ * N processes.  The same device may be listed more than once (tests on a one-GPU box). */
+typedef struct dnv_group dnv_group;
+int dnv_group_create(const dnv_params *params /* .device ignored */, const int32_t *devices,
+                     int32_t n_devices, dnv_group **out);
+int dnv_group_destroy(dnv_group *grp);
+/* Batched BayesInfer.infer over HOST counts, interval-sharded over the group's devices (one host thread per
+ * device for the copies and launches), records gathered through device 0 and returned in input order with
+ * site = index into counts.  Same contract as dnv_infer_counts / dnv_infer_counts8 (calls only). */
+int dnv_group_infer_counts(dnv_group *grp, const uint16_t *counts, int64_t n, dnv_call *calls,
+                           int64_t cap, int64_t *n_calls);
+int dnv_group_infer_counts8(dnv_group *grp, const uint8_t *counts8, int64_t n, dnv_call *calls,
+                            int64_t cap, int64_t *n_calls);
+int dnv_group_size(dnv_group *grp);
+int dnv_group_ctx(dnv_group *grp, int32_t rank, dnv_ctx **out); /* borrowed: owned by the group */
+int dnv_group_get_stats(dnv_group *grp, dnv_stats *out);         /* sums over the devices, last call */
+
+/* ---- host memory ------------------------------------------------------------ */
+/* Page-locked host buffers (cudaHostAlloc, portable across devices): what the host side of a caller plugin
+ * should hand to dnv_infer_counts / dnv_group_infer_counts — pageable memory goes through a staging copy at a
+ * fraction of the PCIe rate.  (Java: MemorySegment.reinterpret over the returned address.) */
+int dnv_alloc_pinned(size_t bytes, void **out);
+int dnv_free_pinned(void *p);
 
 /* ---- calibration ----------------------------------------------------------- */
 /* Dependent-free DFMA chains on every SM: measured FP64 peak in TFLOP/s

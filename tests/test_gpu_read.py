@@ -355,11 +355,8 @@ def test_device_entry_points_reject_bad_arguments():
         assert b"16-byte" in lib.dnv_last_error()
         assert lib.dnv_infer_counts_device_async(eng._h, C.c_void_p(c.data_ptr()), n, C.c_void_p(calls.data_ptr()), n,
                                                  None) == D.DNV_E_INVALID
-        for i in range(64):
+        for i in range(200):  # no limit on the number of batches between two dnv_sync calls
             eng.infer_device_async(c, n, calls, n, h_nc)
-        with pytest.raises(D.DenovoError) as ei:
-            eng.infer_device_async(c, n, calls, n, h_nc)
-        assert ei.value.code == D.DNV_E_INVALID and "dnv_sync" in str(ei.value)
         eng.sync()
-        assert eng.stats()["n_sites"] == 64 * n
+        assert eng.stats()["n_sites"] == 200 * n and eng.stats()["n_calls"] == 0
         assert eng.infer_device(c, n, calls, n) == 0  # all-zero pileups: nothing is called
