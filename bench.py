@@ -6,8 +6,10 @@
                                                             (C restatement, no JVM in this image) on host cores
 
 One "step" = one pass of the hot path over one batch: packed pileup counts resident in HBM
--> compacted call records in HBM (+ for N>1 the NCCL gather of calls to rank 0).
-Prints ONE JSON line on rank 0.
+-> compacted call records in HBM on rank 0 (N>1: stored there by every rank's kernels over NVLink, the
+gather of include/denovo_b200.h: dnv_gather; the gathered records are verified against single-context
+inference after the timed region).  Everything timed goes through the C ABI; Python only owns buffers.
+Prints ONE JSON line on rank 0; `aux` in that line holds the other BASELINE configs (driver-run).
 """
 import argparse
 import json
@@ -24,14 +26,15 @@ METRIC = "trio candidate sites/sec (READ-mode BAYES, 30x)"
 SITES_PER_GPU = 10_000_000
 SEED = 0x5EED0003
 DEPTH, EPS, MU, LRT = 30, 1e-2, 1e-8, 1.0
-GROUP = 64  # asynchronous steps per host synchronisation (and per inter-GPU barrier); <= 64 per context
+GROUP = 64  # asynchronous steps per host synchronisation (and per gather round)
+NBUF = 4    # distinct input buffers (distinct shards of the axis) the steps cycle through; also gather generations
 # ALGORITHMIC work per site:
 #   integer screen (dominant kernel, HBM-bound): 24 B of counts in + 1 bit of decision out
 #   list kernel (only the sites the screen cannot decide): sparse factored FP64 form, FMA = 2
 BYTES_PER_SITE = 24.125
 FLOP_PER_SITE = 451.0
-# DRAM traffic of one screen launch over 10M sites from the ncu --set full capture committed as
-# profiles/r01_read_pipeline_ncu.md (dram__bytes_read.sum + dram__bytes_write.sum), per site
+# DRAM traffic of one screen launch over 10M sites from the ncu --set full capture committed under profiles/
+# (dram__bytes_read.sum + dram__bytes_write.sum), per site
 NCU_TRAFFIC_BYTES_PER_SITE = 26.05
 
 
@@ -145,6 +148,256 @@ def reference_arm(args):
     return 0
 
 
+def timed_sync_calls(fn, reps, warm=3):
+    for _ in range(warm):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    return (time.perf_counter() - t0) / reps
+
+
+def aux_read_config(D, torch, local, method, depth, eps, mu, lrt, n, seed, steps=12):
+    """One BASELINE READ configuration on this GPU: asynchronous batches over NBUF distinct buffers (device
+    resident), CUDA events on the context's stream."""
+    stream = torch.cuda.Stream(device=local)
+    with D.TrioEngine(eps, mu, lrt, method, device=local) as eng:
+        eng.set_stream(stream.cuda_stream)
+        bufs = []
+        for b in range(2):
+            c = torch.empty((n, 12), dtype=torch.int16, device="cuda")
+            eng.synth_counts_device(seed, b * n, n, c, depth=depth, seq_err=eps)
+            bufs.append(c)
+        cap = max(n // 20, 1024)
+        calls = [torch.zeros((cap, D.CALL_DT.itemsize), dtype=torch.uint8, device="cuda") for _ in range(2)]
+        h = torch.zeros(2, dtype=torch.int64).pin_memory()
+
+        def run(k):
+            for i in range(k):
+                eng.infer_device_async(bufs[i % 2], n, calls[i % 2], cap, h.data_ptr() + 8 * (i % 2))
+            eng.flush()
+        with torch.cuda.stream(stream):
+            run(4)
+            eng.sync()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            run(steps)
+            e1.record(stream)
+            eng.sync()
+        st = eng.stats()
+        ms = e0.elapsed_time(e1) / steps
+    return {"method": method, "depth": depth, "eps": eps, "mu": mu, "lrt": lrt, "sites": n, "ms_per_step": ms,
+            "sites_per_s": n / ms * 1e3, "calls_per_step": st["n_calls"] // steps, "hard_sites_per_step": st["n_hard"] // steps,
+            "undecided_per_step": (st["n_sites"] - st["n_screened_out"]) // steps}
+
+
+def aux_undecided(D, torch, np, local, fractions, n=10_000_000, steps=8):
+    """The screen-hostile case: a fraction of the sites replaced by adversarial de-novo-pattern pileups
+    (parents homozygous, child heterozygous, Poisson depths) that the integer screen cannot decide, so they all
+    reach the FP64 list kernel.  Parity: a 100k-site sample of every mix against the CPU oracle."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    out = []
+    stream = torch.cuda.Stream(device=local)
+    with D.TrioEngine(EPS, MU, LRT, "BAYES", device=local) as eng:
+        eng.set_stream(stream.cuda_stream)
+        base = torch.empty((n, 12), dtype=torch.int16, device="cuda")
+        eng.synth_counts_device(SEED, 0, n, base, depth=DEPTH)
+        g = torch.Generator(device="cuda")
+        g.manual_seed(1234)
+        # de novo pattern: parents n_X ~ Poisson(30) of allele X, child split between X and Y
+        x = torch.randint(0, 4, (n,), device="cuda", generator=g)
+        y = (x + torch.randint(1, 4, (n,), device="cuda", generator=g)) % 4
+        dep = torch.poisson(torch.full((n, 3), float(DEPTH), device="cuda"), generator=g).to(torch.int16)
+        alt = (dep[:, 2].float() * (0.25 + 0.5 * torch.rand(n, device="cuda", generator=g))).to(torch.int16)
+        hostile = torch.zeros((n, 3, 4), dtype=torch.int16, device="cuda")
+        idx = torch.arange(n, device="cuda")
+        hostile[idx, 0, x] = dep[:, 0]
+        hostile[idx, 1, x] = dep[:, 1]
+        hostile[idx, 2, x] = dep[:, 2] - alt
+        hostile[idx, 2, y] += alt
+        hostile = hostile.reshape(n, 12)
+        u = torch.rand(n, device="cuda", generator=g)
+        cap = n
+        calls = torch.zeros((cap, D.CALL_DT.itemsize), dtype=torch.uint8, device="cuda")
+        h = torch.zeros(1, dtype=torch.int64).pin_memory()
+        for f in fractions:
+            mix = torch.where((u < f)[:, None], hostile, base).contiguous()
+            with torch.cuda.stream(stream):
+                for _ in range(2):
+                    eng.infer_device_async(mix, n, calls, cap, h)
+                eng.sync()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(steps):
+                    eng.infer_device_async(mix, n, calls, cap, h)
+                eng.flush()
+                e1.record(stream)
+                eng.sync()
+            st = eng.stats()
+            ms = e0.elapsed_time(e1) / steps
+            m = 100_000
+            sample = mix[:m].cpu().numpy().view(np.uint16).reshape(m, 3, 4)
+            ref = O.infer(O.params(EPS, MU, LRT), sample, threads=os.cpu_count() or 1)
+            got = calls[:int(h[0])].cpu().numpy().view(D.CALL_DT).reshape(-1)
+            ok = bool(np.array_equal(got["site"][got["site"] < m], np.nonzero(ref["denovo_bayes"])[0]))
+            out.append({"hostile_fraction": f, "undecided_fraction": (st["n_sites"] - st["n_screened_out"]) / st["n_sites"],
+                        "ms_per_step": ms, "sites_per_s": n / ms * 1e3, "calls_per_step": st["n_calls"] // steps,
+                        "parity_100k_sample_vs_oracle": ok})
+            if not ok:
+                raise SystemExit("undecided sweep: parity FAILED at hostile fraction %g" % f)
+    return out
+
+
+def aux_mendel(D, torch, np, local):
+    """BASELINE config 2: VARIANT-mode Mendelian filter over ~11.8 M (variant, call) records (~2.3 M child SNPs,
+    ~4.7 M records per parent), device resident; bit-exact check of one 200k-variant block against the oracle."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    import synth_inputs as S
+    block = S.make_callset(31, 200_000)
+    span = int(block["end"].max()) + 100
+    reps = 30
+    parts = []
+    for r in range(reps):
+        b = block.copy()
+        b["start"] += r * span
+        b["end"] += r * span
+        b["variant_id"] += r * 200_000
+        parts.append(b)
+    calls = np.concatenate(parts)
+    n = len(calls)
+    stream = torch.cuda.Stream(device=local)
+    with D.TrioEngine(device=local) as eng:
+        eng.set_stream(stream.cuda_stream)
+        d_calls = torch.from_numpy(calls.view(np.uint8).reshape(n, 32)).cuda()
+        n_child = int((calls["person"] == 0).sum())
+        d_out = torch.zeros((n_child + 1, 24), dtype=torch.uint8, device="cuda")
+        res = {}
+
+        def step():
+            res["n"] = eng.mendel_filter_device(d_calls, n, d_out, n_child + 1)
+        with torch.cuda.stream(stream):
+            for _ in range(3):
+                step()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record(stream)
+            for _ in range(5):
+                step()
+            e1.record(stream)
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        got = d_out[:res["n"]].cpu().numpy().view(D.PCALL_DT).reshape(-1)
+    n_ref, want = O.mendel_stream(block)
+    ok = bool(res["n"] == reps * n_ref and all(np.array_equal(got[:n_ref][f], want[f]) for f in ("position", "child", "mom", "dad", "is_denovo")))
+    hbm, _ = load_peaks()
+    return {"records": n, "ms_per_pass": ms, "records_per_s": n / ms * 1e3, "algorithmic_GBps": n * 32 / ms / 1e6,
+            "frac_of_hbm": n * 32 / ms / 1e6 / hbm, "position_calls": int(res["n"]), "denovo_calls": int(got["is_denovo"].sum()),
+            "bit_exact_vs_oracle_block": ok}
+
+
+def aux_pileup(D, torch, np, local, n_sites=2_000_000):
+    """Secondary metric of SURVEY.md 8(d): reads -> counts (pileup kernel) and reads -> counts -> calls chained on
+    the device, every-position layout, 30x, read length 100."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    import synth_inputs as S
+    rs, bo, ba, pe = S.make_reads(41, 1, n_sites, depth=DEPTH)
+    pos = np.arange(1, n_sites + 1, dtype=np.int64)
+    stream = torch.cuda.Stream(device=local)
+    with D.TrioEngine(device=local) as eng:
+        eng.set_stream(stream.cuda_stream)
+        d = [torch.from_numpy(x).cuda() for x in (rs, bo, ba, pe, pos)]
+        d_counts = torch.zeros((n_sites, 12), dtype=torch.int16, device="cuda")
+        cap = max(n_sites // 20, 1024)
+        d_calls = torch.zeros((cap, D.CALL_DT.itemsize), dtype=torch.uint8, device="cuda")
+        chain = {}
+
+        def pile():
+            eng.pileup_device(d[0], d[1], d[2], d[3], len(rs), d[4], n_sites, d_counts)
+
+        def both():
+            eng.pileup_device(d[0], d[1], d[2], d[3], len(rs), d[4], n_sites, d_counts)
+            chain["calls"] = eng.infer_device(d_counts, n_sites, d_calls, cap)
+        times = []
+        for fn in (pile, both):
+            with torch.cuda.stream(stream):
+                for _ in range(3):
+                    fn()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                e0.record(stream)
+                for _ in range(5):
+                    fn()
+                e1.record(stream)
+                torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1) / 5)
+        got = d_counts.cpu().numpy().view(np.uint16).reshape(n_sites, 3, 4)
+    m = 20000
+    sel = slice(n_sites // 2, n_sites // 2 + m)
+    keep = (rs >= pos[sel][0] - 200) & (rs <= pos[sel][-1] + 1)
+    idx = np.nonzero(keep)[0]
+    bo2 = np.zeros(len(idx) + 1, np.int64)
+    np.cumsum(np.diff(bo)[idx], out=bo2[1:])
+    ba2 = np.concatenate([ba[bo[i]:bo[i + 1]] for i in idx])
+    rc, want = O.pileup(rs[idx], bo2, ba2, pe[idx], pos[sel])
+    alg = len(ba) + len(rs) * 17 + n_sites * (8 + 24)
+    hbm, _ = load_peaks()
+    return {"sites": n_sites, "reads": len(rs), "bases": int(len(ba)), "pileup_ms": times[0], "pileup_sites_per_s": n_sites / times[0] * 1e3,
+            "algorithmic_bytes_per_site": alg / n_sites, "algorithmic_GBps": alg / times[0] / 1e6, "frac_of_hbm": alg / times[0] / 1e6 / hbm,
+            "bit_exact_vs_oracle_window": bool(rc == 0 and np.array_equal(got[sel], want)),
+            "reads_to_calls_ms": times[1], "reads_to_calls_sites_per_s": n_sites / times[1] * 1e3, "reads_to_calls_calls": int(chain["calls"])}
+
+
+def genome_walk(D, torch, np, dist, eng, stream, gather, rank, world, local, chunk=1 << 25, seed=0x5EED0004):
+    """BASELINE config 4: every position of an hg19-sized axis (3,095,693,983 sites, 30x), interval-sharded over the
+    ranks (STRONG scaling: the genome is fixed), counts generated procedurally per chunk on the device (the 74 GB
+    of counts are never materialised), call records gathered on rank 0.  Generation is excluded from the timed
+    inference (separate events); returns per-rank numbers, max-reduced by the caller."""
+    from denovo_b200 import sharding
+    total = 3_095_693_983
+    lo, hi = sharding.shard_range(total, world, rank)
+    bufs = [torch.empty((chunk, 12), dtype=torch.int16, device="cuda") for _ in range(2)]
+    cap = chunk // 50
+    calls = [torch.zeros((cap, D.CALL_DT.itemsize), dtype=torch.uint8, device="cuda") for _ in range(2)] if gather is None else None
+    h = torch.zeros(2, dtype=torch.int64).pin_memory()
+    infer_ms = gen_ms = 0.0
+    n_calls = 0
+    per_gen = []
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    k = 0
+    with torch.cuda.stream(stream):
+        for first in range(lo, hi, chunk):
+            m = min(chunk, hi - first)
+            b = k % 2
+            evs[0].record(stream)
+            eng.synth_counts_device(seed, first, m, bufs[b], depth=DEPTH)
+            evs[1].record(stream)
+            if gather is None:
+                eng.infer_device_async(bufs[b], m, calls[b], cap, h.data_ptr() + 8 * b, site_base=first)
+                eng.flush()
+            else:
+                gather.submit(bufs[b], m, first, b)
+                gather.arrive()
+                if rank == 0:
+                    gather.wait()
+            evs[2].record(stream)
+            eng.sync()
+            if gather is not None:
+                dist.barrier()  # rank 0 has every rank's records of this chunk round
+                if rank == 0:
+                    got, per = gather.fetch(b, cap=world * gather.cap)
+                    n_calls += len(got)
+                dist.barrier()
+            else:
+                n_calls += int(h[b])
+            gen_ms += evs[0].elapsed_time(evs[1])
+            infer_ms += evs[1].elapsed_time(evs[2])
+            k += 1
+    return {"sites": hi - lo, "infer_ms": infer_ms, "gen_ms": gen_ms, "calls": n_calls, "chunks": k}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -154,13 +407,15 @@ def main():
     ap.add_argument("--sites", type=int, default=SITES_PER_GPU)
     ap.add_argument("--method", default="BAYES")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-aux", action="store_true", help="skip the other BASELINE configs (aux object of the line)")
     ap.add_argument("--no-screen", action="store_true", help="evaluate every site with the fused FP64 kernel")
-    ap.add_argument("--contexts", type=int, default=4, help="contexts (each on its own stream) the batches are fed to in turn")
-    ap.add_argument("--single-context", action="store_true", help="same as --contexts 1")
+    ap.add_argument("--undecided", type=float, nargs="*", default=None,
+                    help="screen-hostile sweep: fractions of adversarial de-novo-pattern sites (default in aux: 0.01 0.1 0.5 1.0)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
 
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # one hardware queue per lane stream
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -180,80 +435,69 @@ def main():
     n = args.sites
     K, W = args.steps, max(args.warmup, 3)
 
-    # eng: the context used for generation, kernel timing (event brackets) and the host-API leg;
-    # pipe: `depth` untimed contexts, each on its own stream, fed in turn — the production way to walk a stream
-    # of batches (the latency-bound list / finish kernels of one batch run beside the bandwidth-bound screen of
-    # the next ones)
-    eng = D.TrioEngine(EPS, MU, LRT, args.method, device=local, time_kernels=True, no_screen=args.no_screen)
-    stream = torch.cuda.Stream(device=local)          # main stream: timing events, inter-GPU barrier
+    # eng: the product context (lanes inside: consecutive batches overlap on the GPU); eng_t: a serial context whose
+    # kernels are bracketed by CUDA events one by one (DNV_F_TIME_KERNELS) for the roofline of the dominant kernel
+    stream = torch.cuda.Stream(device=local)
+    eng = D.TrioEngine(EPS, MU, LRT, args.method, device=local, no_screen=args.no_screen)
     eng.set_stream(stream.cuda_stream)
-    depth = 1 if args.single_context else max(1, args.contexts)
-    pstreams = [torch.cuda.Stream(device=local) for _ in range(depth)]
-    pipe = D.BatchPipeline(depth=depth, streams=[st.cuda_stream for st in pstreams], seq_err_rate=EPS,
-                           denovo_mut_rate=MU, lrt_threshold=LRT, method=args.method, device=local,
-                           no_screen=args.no_screen)
+    eng_t = D.TrioEngine(EPS, MU, LRT, args.method, device=local, time_kernels=True, no_screen=args.no_screen)
+    eng_t.set_stream(stream.cuda_stream)
 
-    # ---- synthetic shard of this rank (interval sharding: rank r owns sites [r*n, (r+1)*n))
-    d_counts = torch.empty((n, 12), dtype=torch.int16, device="cuda")
-    eng.synth_counts_device(SEED, rank * n, n, d_counts, depth=DEPTH)
+    # ---- synthetic shard of this rank: NBUF distinct buffers = NBUF consecutive intervals of the axis
+    # (interval sharding: rank r owns sites [r * NBUF * n, (r + 1) * NBUF * n)); step i reads buffer i % NBUF
+    def shard_first(r, b):
+        return (r * NBUF + b) * n
+    d_counts = []
+    for b in range(NBUF):
+        c = torch.empty((n, 12), dtype=torch.int16, device="cuda")
+        eng.synth_counts_device(SEED, shard_first(rank, b), n, c, depth=DEPTH)
+        d_counts.append(c)
     cap = max(n // 100, 1024)
-    d_calls = [torch.zeros((cap, D.CALL_DT.itemsize), dtype=torch.uint8, device="cuda") for _ in range(depth)]
     torch.cuda.synchronize()
 
-    from denovo_b200 import sharding
-
-    # N>1: the list kernel of every rank writes its call records and their count straight into rank 0's
-    # HBM over NVLink (symmetric memory, one generation of slots per step of a group); no data
-    # collective, one signal-pad barrier per group of GROUP steps.
-    peer = None
+    # N>1: every rank's kernels store records + counts straight into rank 0's HBM (dnv_gather over IPC-mapped peer
+    # memory; the 64-byte handle is the only thing torch.distributed carries); generation = buffer index
+    gather = None
     if world > 1:
-        try:
-            peer = sharding.PeerGather(dist, cap, D.CALL_DT.itemsize, slots=GROUP)
-        except Exception as e:  # noqa: BLE001
-            print("symmetric memory unavailable (%r): falling back to the NCCL gather" % (e,), file=sys.stderr)
-
-    # One step = one batch through the asynchronous device entry point (dnv_infer_counts_device_async):
-    # the whole pipeline is enqueued, the batch's call count lands in a pinned host slot (N=1) or straight
-    # in rank 0's HBM next to the records (N>1), and the host only waits once per GROUP steps (dnv_sync).
+        gather = D.Gather(eng, world, rank, cap, gens=NBUF)
+        gather.exchange(dist)
+        d_calls = None
+    else:
+        d_calls = [torch.zeros((cap, D.CALL_DT.itemsize), dtype=torch.uint8, device="cuda") for _ in range(NBUF)]
+    h_nc = torch.zeros(NBUF, dtype=torch.int64).pin_memory()
     torch.cuda.set_stream(stream)
-    h_nc = torch.zeros(64, dtype=torch.int64).pin_memory()
-    counts_ptr = d_counts.data_ptr()
-    calls_ptrs = [t.data_ptr() for t in d_calls]
-    nc_ptrs = [h_nc.data_ptr() + 8 * i for i in range(64)]
-    if peer:  # per-generation destinations in rank 0's HBM, computed once
-        rec_ptrs = [peer.records_ptr(i) for i in range(GROUP)]
-        cnt_ptrs = [peer.count_ptr(i) for i in range(GROUP)]
-
-    def join():
-        """The main stream waits for both pipeline streams (no host synchronisation)."""
-        pipe.flush()
-        for st in pstreams:
-            stream.wait_stream(st)
 
     def run_steps(k_steps):
-        """k_steps pipelined steps; returns summed library stats."""
+        """k_steps pipelined steps; one host synchronisation (and one gather round) per GROUP steps."""
         acc = {"n_launches": 0, "n_screened_out": 0, "n_hard": 0, "n_calls": 0, "n_sites": 0}
         done = 0
         while done < k_steps:
             m = min(GROUP, k_steps - done)
-            if world > 1 and not peer:  # no symmetric memory: NCCL gather, needs the count on the host every step
-                m = 1
-                pipe.submit(counts_ptr, n, calls_ptrs[0], cap, nc_ptrs[0])
-                st = pipe.sync()
-                sharding.gather_records(d_calls[0][:int(h_nc[0])], dist)
+            for i in range(done, done + m):
+                b = i % NBUF
+                if gather is not None:
+                    gather.submit(d_counts[b], n, shard_first(rank, b), b)
+                else:
+                    eng.infer_device_async(d_counts[b], n, d_calls[b], cap, h_nc.data_ptr() + 8 * b, site_base=shard_first(0, b))
+            if gather is not None:
+                gather.arrive()      # device-side: flush + release flag in rank 0's HBM
+                if rank == 0:
+                    gather.wait()    # rank 0's stream waits until every rank's records of the round have landed
             else:
-                for i in range(m):
-                    if peer:
-                        pipe.submit(counts_ptr, n, rec_ptrs[i], cap, cnt_ptrs[i])
-                    else:
-                        pipe.submit(counts_ptr, n, calls_ptrs[i % depth], cap, nc_ptrs[i])
-                if peer:
-                    join()
-                    peer.barrier()  # records + counts of every rank and step of the group now sit in rank 0's HBM
-                st = pipe.sync()
-            for key in acc:
-                acc[key] += st[key]
+                eng.flush()
             done += m
+            if done < k_steps:
+                eng.sync()
+                st = eng.stats()
+                for key in acc:
+                    acc[key] += st[key]
+        return acc
+
+    def finish(acc):
+        eng.sync()
+        st = eng.stats()
+        for key in acc:
+            acc[key] += st[key]
         return acc
 
     def barrier():
@@ -262,61 +506,92 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    run_steps(max(W, 2 * depth))  # every context allocates its scratch on its first batch: all of them warm up
+    finish(run_steps(max(W, 2 * NBUF)))  # scratch of every lane is allocated on its first batch: all of them warm up
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if peer:
-        peer.barrier()  # device-side line-up: every rank's timed region starts when all ranks are ready
     e0.record(stream)
-    for st in pstreams:
-        st.wait_event(e0)
     acc = run_steps(K)
-    join()
-    e1.record(stream)
+    e1.record(stream)     # after flush / wait on the same stream: everything of the K steps is inside the bracket
+    acc = finish(acc)
     barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     launches = acc["n_launches"]
     screened_out = acc["n_screened_out"] // K
     n_hard = acc["n_hard"] // K
-    if peer:
-        total_calls = sum(peer.counts(gen=(K - 1) % GROUP)) if rank == 0 else 0
-    else:
-        total_calls = acc["n_calls"] // K
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    per_rank_ms = [ms]
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+        allt = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank_ms = [float(x.item()) for x in allt]
+    ms_max = max(per_rank_ms)
     value = world * n * K / (ms_max * 1e-3)
 
-    # kernel times (CUDA-event brackets inside the library, DNV_F_TIME_KERNELS) and the same step through
-    # the synchronous entry point (the host reads n_calls after every batch), on the timed context
+    # ---- parity of what the timed region produced: rank 0 regenerates every rank's shard of each generation,
+    # infers it with the serial context and compares the gathered records BYTE FOR BYTE
+    verify = {"verified": None}
+    if rank == 0:
+        tmp_counts = torch.empty((n, 12), dtype=torch.int16, device="cuda")
+        tmp_calls = torch.zeros((cap, D.CALL_DT.itemsize), dtype=torch.uint8, device="cuda")
+        gens = sorted(set((K - 1 - j) % NBUF for j in range(min(K, NBUF))))
+        n_rec = 0
+        for b in gens:
+            want = []
+            for r in range(world):
+                eng_t.synth_counts_device(SEED, shard_first(r, b), n, tmp_counts, depth=DEPTH)
+                k = eng_t.infer_device(tmp_counts, n, tmp_calls, cap)
+                w = tmp_calls[:k].cpu().numpy().view(D.CALL_DT).reshape(-1).copy()
+                w["site"] += shard_first(r, b)
+                want.append(w)
+            want = np.concatenate(want)
+            if gather is not None:
+                got, per = gather.fetch(b, cap=world * cap)
+            else:
+                got = d_calls[b][:int(h_nc[b])].cpu().numpy().view(D.CALL_DT).reshape(-1)
+            if got.tobytes() != want.tobytes():
+                print("GATHER PARITY FAILED: generation %d, %d records gathered, %d expected" % (b, len(got), len(want)), file=sys.stderr)
+                os.dup2(real_stdout, 1)
+                print(json.dumps({"metric": METRIC, "error": "gathered records differ from single-context inference"}), flush=True)
+                return 1
+            n_rec += len(got)
+        total_calls = n_rec // len(gens)
+        verify = {"verified": True, "generations_checked": len(gens), "records_checked": n_rec,
+                  "how": "rank 0 regenerates every rank's shard, infers it on a serial context and compares the "
+                         "records of the last %d step(s) byte for byte" % len(gens)}
+        del tmp_counts, tmp_calls
+    else:
+        total_calls = 0
+    barrier()
+
+    # ---- the same step through the synchronous entry point (one call = submit + wait + count on the host), on the
+    # product context (lanes + graph replay), and the kernel times on the serial, event-bracketed context
+    cptr, clptr = d_counts[0], (d_calls[0] if d_calls is not None else torch.zeros((cap, D.CALL_DT.itemsize), dtype=torch.uint8, device="cuda"))
+    sync_s = timed_sync_calls(lambda: eng.infer_device(cptr, n, clptr, cap), 30)
     Kt = 20
     for _ in range(3):
-        eng.infer_device(counts_ptr, n, calls_ptrs[0], cap)
+        eng_t.infer_device(cptr, n, clptr, cap)
     fused_ms = screen_ms = 0.0
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
     for _ in range(Kt):
-        eng.infer_device(counts_ptr, n, calls_ptrs[0], cap)
-        st = eng.stats()
+        eng_t.infer_device(cptr, n, clptr, cap)
+        st = eng_t.stats()
         fused_ms += st["fused_kernel_ms"]
         screen_ms += st["screen_kernel_ms"]
-    sync_ms = (time.perf_counter() - t0) * 1e3 / Kt
-    fused_ms, screen_ms = fused_ms * K / Kt, screen_ms * K / Kt  # the roofline code below divides by K
+    k_ms, s_ms = fused_ms / Kt, screen_ms / Kt
 
     # ---- end to end through the host API: pinned host counts -> calls in pinned host memory
-    # the host packs counts as uint8 (12 B/site) when every per-allele depth is below 256, else uint16
-    u8 = bool(int(d_counts.max().item()) < 256)
+    # the host packs counts as uint8 (12 B/site) when every per-allele depth is below 256, else uint16: an INPUT
+    # FORMAT of the ABI (dnv_infer_counts8), packed once outside the timed region like any other input preparation
+    u8 = bool(int(d_counts[0].max().item()) < 256)
     if u8:
         h_counts = torch.empty((n, 12), dtype=torch.uint8).pin_memory()
-        h_counts.copy_(d_counts.to(torch.uint8))
+        h_counts.copy_(d_counts[0].to(torch.uint8))
     else:
         h_counts = torch.empty((n, 12), dtype=torch.int16).pin_memory()
-        h_counts.copy_(d_counts)
+        h_counts.copy_(d_counts[0])
     h_calls = torch.zeros((cap, D.CALL_DT.itemsize), dtype=torch.uint8).pin_memory()
     eng.set_stream(None)
     for _ in range(2):
@@ -332,6 +607,47 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * n * Ke / float(te.item())
+    eng.set_stream(stream.cuda_stream)
+
+    # ---- aux: the other BASELINE configs, driver-run in the same line
+    aux = None
+    if not args.no_aux:
+        aux = {}
+        if world > 1:
+            # config 4 (strong scaling over the ranks) with its gather
+            gw = D.Gather(eng, world, rank, (1 << 25) // 50, gens=2)
+            gw.exchange(dist)
+            g = genome_walk(D, torch, np, dist, eng, stream, gw, rank, world, local)
+            tt = torch.tensor([g["infer_ms"], g["gen_ms"]], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            gw.close()
+            if rank == 0:
+                aux["config4_genome_every_position"] = {"sites": 3_095_693_983, "n_gpus": world, "scaling": "strong",
+                                                        "infer_ms_max_over_ranks": float(tt[0]), "sites_per_s": 3_095_693_983 / float(tt[0]) * 1e3,
+                                                        "generator_ms_max_over_ranks": float(tt[1]), "calls_gathered_on_rank0": g["calls"],
+                                                        "chunk_sites": 1 << 25}
+        elif rank == 0:
+            g = genome_walk(D, torch, np, dist, eng, stream, None, 0, 1, local)
+            aux["config4_genome_every_position"] = {"sites": g["sites"], "n_gpus": 1, "scaling": "strong", "infer_ms_max_over_ranks": g["infer_ms"],
+                                                    "sites_per_s": g["sites"] / g["infer_ms"] * 1e3, "generator_ms_max_over_ranks": g["gen_ms"],
+                                                    "calls_gathered_on_rank0": g["calls"], "chunk_sites": 1 << 25}
+        # config 5 on every rank (weak: 10 M sites per GPU), config 3 variants / config 2 / pileup on rank 0
+        c5 = [aux_read_config(D, torch, local, "BAYES", 200, 1e-3, mu, 1.0, n, 0x5EED0005) for mu in (1e-10, 1e-6)]
+        if world > 1:
+            for c in c5:
+                tt = torch.tensor([c["ms_per_step"]], dtype=torch.float64, device="cuda")
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                c["ms_per_step"] = float(tt[0])
+                c["sites_per_s"] = world * n / float(tt[0]) * 1e3
+                c["n_gpus"] = world
+        if rank == 0:
+            aux["config5_200x_eps1e-3"] = c5
+            aux["config3_MAP"] = aux_read_config(D, torch, local, "MAP", DEPTH, EPS, MU, 1.0, n, SEED)
+            aux["config3_LRT_T10"] = aux_read_config(D, torch, local, "LRT", DEPTH, EPS, MU, 10.0, n, SEED)
+            aux["config2_mendel_filter"] = aux_mendel(D, torch, np, local)
+            aux["pileup_and_reads_to_calls"] = aux_pileup(D, torch, np, local)
+            aux["undecided_sweep"] = aux_undecided(D, torch, np, local, args.undecided if args.undecided else [0.01, 0.1, 0.5, 1.0])
+        barrier()
 
     if rank != 0:
         if world > 1:
@@ -339,30 +655,29 @@ def main():
         return 0
 
     # ---- roofline of the dominant kernel
-    fp64_peak, _ = eng.measure_fp64_peak()
+    fp64_peak, _ = eng_t.measure_fp64_peak()
     hbm_peak, peak_src = load_peaks()
-    k_ms = fused_ms / K          # the kernels of a step: integer screen + list kernel + finish kernel
-    s_ms = screen_ms / K         # the screen alone
     if s_ms > 0:
         # BAYES/LRT: the integer screen streams every site's counts and is the dominant kernel (HBM-bound)
         n_fp64 = n - screened_out
         ach_gbs = BYTES_PER_SITE * n / (s_ms * 1e-3) / 1e9
         f_ms = max(k_ms - s_ms, 1e-9)
         ach_tf = FLOP_PER_SITE * n_fp64 / (f_ms * 1e-3) / 1e12
+        step_gbs = BYTES_PER_SITE * n / (ms_max / K * 1e-3) / 1e9
         roofline = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                     "traffic": NCU_TRAFFIC_BYTES_PER_SITE * n, "kernel": "trio_screen_kernel", "kernel_ms": s_ms,
-                    # share of the step's kernel time (screen + list + finish kernel, timed alone on the timed
-                    # context: comparable with the serialised ncu launch list); the value loop overlaps the
-                    # list kernel of one batch with the screen of the next, so ms_per_step < their sum
+                    # kernel times from the serial context (each kernel alone, comparable with the serialised ncu launch
+                    # list); in the value loop the list / finish kernels of one batch run BESIDE the screen of the
+                    # next, so ms_per_step is below their sum
                     "kernel_share_of_step": s_ms / k_ms, "step_kernels_ms": k_ms, "bytes_per_site": BYTES_PER_SITE,
-                    "peak_source": peak_src,
+                    "peak_source": peak_src, "whole_step_GBps": step_gbs, "whole_step_frac": step_gbs / hbm_peak,
                     "sites_decided_by_screen": int(screened_out), "sites_to_fp64_kernel": int(n_fp64),
                     "fp64_kernel": {"kernel": "trio_list_kernel + trio_calls_finish_kernel (fused FP64 posterior, ordered compaction, call records)", "kernel_ms": f_ms, "sites": int(n_fp64),
                                     "flop_per_site": FLOP_PER_SITE, "achieved_tflops": ach_tf,
                                     "fp64_peak_tflops": fp64_peak,
                                     "peak_source": "dependent-free DFMA chains on all SMs, measured in this run"}}
     else:
-        # MAP (or screen disabled): the fused FP64 kernel sees every site (FP64-pipe-bound)
+        # screen disabled: the fused FP64 kernel sees every site (FP64-pipe-bound)
         ach_tf = FLOP_PER_SITE * n / (k_ms * 1e-3) / 1e12
         roofline = {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                     "frac": ach_tf / fp64_peak if fp64_peak else None, "traffic": None,
@@ -387,18 +702,20 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "READ-mode %s inference, %d synthetic trio candidate sites per GPU at 30x, eps 1e-2, "
                                    "mu 1e-8 (BASELINE configs[2]); interval-sharded; calls gathered to rank 0 %s"
-                                   % (args.method, n, "by peer stores over NVLink from the list kernel + one signal-pad "
-                                      "barrier per group of steps (no data collective)" if peer else ("with NCCL" if world > 1 else "(single GPU)")),
-                       "sites_per_gpu": n, "l2": "input 240 MB per pass > 126 MB L2 (no flush needed)",
+                                   % (args.method, n, "by the kernels' peer stores over NVLink into rank 0's HBM + one release flag per "
+                                      "rank and round (dnv_gather; no data collective)" if world > 1 else "(single GPU)"),
+                       "sites_per_gpu": n, "l2": "input 240 MB per pass > 126 MB L2, and %d distinct input buffers in rotation (no flush needed)" % NBUF,
                        "calls_per_step": int(total_calls), "hard_sites_per_step": int(n_hard),
-                       "step": "asynchronous batches (dnv_infer_counts_device_async) fed alternately to %d contexts on %d streams, one dnv_sync per %d steps; kernel times from a separate timed context" % (depth, depth, GROUP),
-                       "ms_per_step_synchronous_api": sync_ms, "contexts": depth,
-                       "warmup_steps_run": max(W, 2 * depth)},
+                       "step": "asynchronous batches (dnv_infer_counts_device_async / _gather) on ONE context: %s lanes inside the library, one dnv_sync per %d steps; kernel times from a serial, event-bracketed context" % (os.environ.get("DNV_LANES", "3"), GROUP),
+                       "ms_per_step_synchronous_api": sync_s * 1e3, "per_rank_ms_per_step": [x / K for x in per_rank_ms],
+                       "gather_verified": verify["verified"], "gather_verification": verify,
+                       "warmup_steps_run": max(W, 2 * NBUF), "same_config_as_reference_arm": "the reference arm times a bounded 200k-site sample of this workload per step (CPU throughput per site does not depend on the batch size)"},
             "e2e": {"value": e2e_value, "unit": "sites/s", "h2d_bytes_per_step": n * (12 if u8 else 24),
-                    "input_format": "uint8 counts, 12 B/site (dnv_infer_counts8)" if u8 else "uint16 counts, 24 B/site",
+                    "input_format": "uint8 counts, 12 B/site (dnv_infer_counts8; packed once outside the timed region — it is the caller's input format)" if u8 else "uint16 counts, 24 B/site",
                     "d2h_bytes_per_step": int(e2e_calls) * D.CALL_DT.itemsize + 64, "steps": Ke,
-                    "timer": "host wall clock around dnv_infer_counts (pinned host buffers), max over ranks"},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}
+                    "timer": "host wall clock around dnv_infer_counts8 (pinned host buffers), max over ranks",
+                    "limiter": "PCIe: one x16 Gen5 link per GPU; at N>1 every rank pulls its pinned buffer through the same host NUMA node"},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "aux": aux}
     sys.stdout.flush()
     os.dup2(real_stdout, 1)
     print(json.dumps(line), flush=True)

@@ -25,7 +25,11 @@ EXPORTS = ["dnv_create", "dnv_destroy", "dnv_last_error", "dnv_abi_version", "dn
            "dnv_infer_counts", "dnv_infer_counts_device", "dnv_infer_counts8", "dnv_infer_counts8_device",
            "dnv_infer_counts_device_async", "dnv_infer_counts8_device_async",
            "dnv_infer_counts_device_async_at", "dnv_infer_counts8_device_async_at", "dnv_flush", "dnv_sync",
-           "dnv_alloc_pinned", "dnv_free_pinned", "dnv_pileup", "dnv_pileup_device",
+           "dnv_alloc_pinned", "dnv_free_pinned",
+           "dnv_gather_create", "dnv_gather_destroy", "dnv_gather_export", "dnv_gather_import", "dnv_gather_attach",
+           "dnv_gather_slot", "dnv_infer_counts_device_gather", "dnv_infer_counts8_device_gather", "dnv_gather_arrive",
+           "dnv_gather_wait", "dnv_gather_fetch", "dnv_group_create", "dnv_group_destroy", "dnv_group_infer_counts",
+           "dnv_group_infer_counts8", "dnv_group_size", "dnv_group_ctx", "dnv_group_get_stats", "dnv_pileup", "dnv_pileup_device",
            "dnv_mendel_filter", "dnv_mendel_filter_device", "dnv_synth_counts_device", "dnv_synth_counts_at_device",
            "dnv_synth_counts_at", "dnv_measure_fp64_peak"]
 
@@ -94,6 +98,24 @@ def load():
     L.dnv_infer_counts8_device_async_at.argtypes = [vp, vp, i64, i64, vp, i64, vp]
     L.dnv_flush.argtypes = [vp]
     L.dnv_sync.argtypes = [vp]
+    L.dnv_gather_create.argtypes = [vp, i32, i32, i32, i64, i32, C.POINTER(vp)]
+    L.dnv_gather_destroy.argtypes = [vp]
+    L.dnv_gather_export.argtypes = [vp, vp]
+    L.dnv_gather_import.argtypes = [vp, vp]
+    L.dnv_gather_attach.argtypes = [vp, vp]
+    L.dnv_gather_slot.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(vp)]
+    L.dnv_infer_counts_device_gather.argtypes = [vp, vp, i64, i64, vp, i32]
+    L.dnv_infer_counts8_device_gather.argtypes = [vp, vp, i64, i64, vp, i32]
+    L.dnv_gather_arrive.argtypes = [vp]
+    L.dnv_gather_wait.argtypes = [vp]
+    L.dnv_gather_fetch.argtypes = [vp, i32, vp, i64, C.POINTER(i64), vp]
+    L.dnv_group_create.argtypes = [C.POINTER(Params), vp, i32, C.POINTER(vp)]
+    L.dnv_group_destroy.argtypes = [vp]
+    L.dnv_group_infer_counts.argtypes = [vp, vp, i64, vp, i64, C.POINTER(i64)]
+    L.dnv_group_infer_counts8.argtypes = [vp, vp, i64, vp, i64, C.POINTER(i64)]
+    L.dnv_group_size.argtypes = [vp]
+    L.dnv_group_ctx.argtypes = [vp, i32, C.POINTER(vp)]
+    L.dnv_group_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.dnv_alloc_pinned.argtypes = [C.c_size_t, C.POINTER(vp)]
     L.dnv_free_pinned.argtypes = [vp]
     L.dnv_pileup.argtypes = [vp, vp, vp, vp, vp, i64, vp, i64, vp]

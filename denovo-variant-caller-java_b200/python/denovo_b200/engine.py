@@ -7,8 +7,12 @@
   new ReadSummary(reads, pos) (M/ReadSummary.java)  TrioEngine.pileup(...)
   VariantsBuffer + PositionCall (M/VariantsBuffer)  TrioEngine.mendel_filter(calls)
 
+  shared PrintWriter of N per-site tasks            Gather (one process per GPU) / DeviceGroup (one process)
+    (M/ReadCaller.java:91-95,122-129)
+
 Every method goes through the C ABI (include/denovo_b200.h); host arrays are numpy,
-device arrays are torch CUDA tensors (torch is used only to own device memory).
+device arrays are torch CUDA tensors (torch is used only to own device memory).  Batching — the overlap of
+consecutive batches, the interval shards, the gather — lives below the ABI; this file only forwards.
 """
 import ctypes as C
 import math
@@ -36,53 +40,6 @@ def poisson_thresholds(depth, kmax=None):
         thr.append((1 << 64) - 1 if x >= 18446744073709551616.0 else int(x))
         term = term * depth / (k + 1)
     return np.array(thr, np.uint64)
-
-
-class BatchPipeline:
-    """Host-side batching layer for streams of device-resident batches (a genome walked chunk by chunk).
-
-    A batch is kernels with opposite characters: a bandwidth-bound integer screen over every site, then
-    two short latency-bound kernels for the ~1 % it cannot decide.  Several contexts, each on its own
-    CUDA stream and fed in turn, let the short kernels of one batch run beside the screens of the next
-    ones (measured on B200, 10 M-site batches: 87 us with one context, 68 with two, 61 with four).  Batches are independent, so nothing else
-    changes: every batch writes its own records and call count (dnv_infer_counts_device_async), and
-    `sync()` waits for all of them."""
-
-    def __init__(self, depth=4, streams=None, **engine_kwargs):
-        self.engines = [TrioEngine(**engine_kwargs) for _ in range(depth)]
-        if streams is not None:  # raw cudaStream_t handles, one per context (else each context's own stream)
-            for e, st in zip(self.engines, streams):
-                e.set_stream(st)
-        self.k = 0
-
-    def submit(self, d_counts, n, d_calls, cap, n_calls_out, u8=False):
-        """Enqueue one batch on the next context; arguments as TrioEngine.infer_device_async."""
-        self.engines[self.k % len(self.engines)].infer_device_async(d_counts, n, d_calls, cap, n_calls_out, u8=u8)
-        self.k += 1
-
-    def flush(self):
-        """Device-side join of every context (each context's stream waits for its batches; no host wait)."""
-        for e in self.engines:
-            e.flush()
-
-    def sync(self):
-        """Wait for every submitted batch; returns the stats summed over the contexts."""
-        tot = None
-        for e in self.engines:
-            e.sync()
-            st = e.stats()
-            tot = st if tot is None else {k: tot[k] + st[k] for k in st}
-        return tot
-
-    def close(self):
-        for e in self.engines:
-            e.close()
-
-    def __enter__(self):
-        return self
-
-    def __exit__(self, *a):
-        self.close()
 
 
 class TrioEngine:
@@ -228,3 +185,119 @@ class TrioEngine:
         tf, ms = C.c_double(0), C.c_double(0)
         L.check(self.lib.dnv_measure_fp64_peak(self._h, C.byref(tf), C.byref(ms)))
         return tf.value, ms.value
+
+
+class Gather:
+    """One rank's end of the gather of call records to rank `dst` (include/denovo_b200.h: dnv_gather).
+    The records and counts are stored by the producing kernels straight into the destination's HBM; this class
+    only owns the handle.  Between processes the destination's 64-byte handle has to reach the other ranks:
+    `exchange(dist)` does that with one torch.distributed broadcast (plumbing, any backend)."""
+
+    def __init__(self, engine, world, rank, cap, gens=1, dst=0):
+        self.eng, self.lib = engine, engine.lib
+        self.world, self.rank, self.dst, self.cap, self.gens = world, rank, dst, int(cap), int(gens)
+        h = C.c_void_p()
+        L.check(self.lib.dnv_gather_create(engine._h, world, rank, dst, self.cap, self.gens, C.byref(h)))
+        self._h = h
+
+    def export_handle(self):
+        buf = (C.c_ubyte * 64)()
+        L.check(self.lib.dnv_gather_export(self._h, buf))
+        return bytes(buf)
+
+    def import_handle(self, handle):
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        L.check(self.lib.dnv_gather_import(self._h, buf))
+
+    def attach(self, dst_end):
+        L.check(self.lib.dnv_gather_attach(self._h, dst_end._h))
+
+    def exchange(self, dist):
+        """One process per GPU: broadcast the destination's handle and map it on the other ranks."""
+        import torch
+        t = torch.zeros(64, dtype=torch.uint8)
+        if self.rank == self.dst:
+            t = torch.frombuffer(bytearray(self.export_handle()), dtype=torch.uint8).clone()
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        t = t.to(dev)
+        dist.broadcast(t, src=self.dst)
+        if self.rank != self.dst:
+            self.import_handle(bytes(t.cpu().numpy().tobytes()))
+
+    def submit(self, d_counts, n, site_base, gen, u8=False):
+        """Enqueue one batch whose records (global site indices) and count land in this rank's slot of `gen`."""
+        fn = self.lib.dnv_infer_counts8_device_gather if u8 else self.lib.dnv_infer_counts_device_gather
+        L.check(fn(self.eng._h, L.ptr(d_counts), n, site_base, self._h, gen))
+
+    def arrive(self):
+        L.check(self.lib.dnv_gather_arrive(self._h))
+
+    def wait(self):
+        L.check(self.lib.dnv_gather_wait(self._h))
+
+    def fetch(self, gen=0, cap=None):
+        """Destination: the gathered records of one generation (rank order = genomic order) and per-rank counts."""
+        cap = self.world * self.cap if cap is None else cap
+        out = np.zeros(max(cap, 1), L.CALL_DT)
+        per = np.zeros(self.world, np.int64)
+        n = C.c_int64(0)
+        L.check(self.lib.dnv_gather_fetch(self._h, gen, L.ptr(out), cap, C.byref(n), L.ptr(per)))
+        return out[:n.value], per
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.dnv_gather_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+class DeviceGroup:
+    """N devices driven by this one process (dnv_group): host batches are split by interval, every device infers
+    its shard, the records come back gathered in input order.  What the single-process hosts (CLI, Java) use."""
+
+    def __init__(self, devices, seq_err_rate=1e-2, denovo_mut_rate=1e-8, lrt_threshold=1.0, method="BAYES"):
+        self.lib = L.load()
+        m = L.METHODS[method.upper()] if isinstance(method, str) else int(method)
+        prm = L.Params(seq_err_rate, denovo_mut_rate, lrt_threshold, m, 0, 0, 0)
+        dev = np.ascontiguousarray(devices, np.int32)
+        h = C.c_void_p()
+        L.check(self.lib.dnv_group_create(C.byref(prm), L.ptr(dev), len(dev), C.byref(h)))
+        self._h = h
+
+    def infer(self, counts, cap=None):
+        u8 = isinstance(counts, np.ndarray) and counts.dtype == np.uint8
+        counts = np.ascontiguousarray(counts, np.uint8 if u8 else np.uint16).reshape(-1, 12)
+        n = counts.shape[0]
+        cap = n if cap is None else cap
+        calls = np.zeros(max(cap, 1), L.CALL_DT)
+        nc = C.c_int64(0)
+        fn = self.lib.dnv_group_infer_counts8 if u8 else self.lib.dnv_group_infer_counts
+        L.check(fn(self._h, L.ptr(counts), n, L.ptr(calls) if cap > 0 else None, cap, C.byref(nc)))
+        return calls[:nc.value]
+
+    def infer_into(self, counts_ptr, n, calls_ptr, cap, u8=False):
+        """Zero-allocation call over caller-owned (pinned) buffers; returns n_calls."""
+        nc = C.c_int64(0)
+        fn = self.lib.dnv_group_infer_counts8 if u8 else self.lib.dnv_group_infer_counts
+        L.check(fn(self._h, L.ptr(counts_ptr), n, L.ptr(calls_ptr), cap, C.byref(nc)))
+        return nc.value
+
+    def stats(self):
+        s = L.Stats()
+        L.check(self.lib.dnv_group_get_stats(self._h, C.byref(s)))
+        return {"n_sites": s.n_sites, "n_calls": s.n_calls, "n_hard": s.n_hard, "n_launches": s.n_launches,
+                "n_screened_out": s.n_screened_out}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.dnv_group_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()

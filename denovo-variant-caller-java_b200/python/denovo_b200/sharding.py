@@ -7,8 +7,10 @@ depends only on its own 12 counts, the reference already runs one task per site
 concatenated genomic axis, so rank order = genomic order, and there is NO
 data-path collective: the only exchange is the final gather of call records and
 counters to rank 0, which replaces the shared PrintWriter + synchronized
-writeCalls (M/DenovoCaller.java:56-59).  Works on any torch.distributed backend
-(NCCL with CUDA tensors on the GPU box, gloo with CPU tensors in the tests).
+writeCalls (M/DenovoCaller.java:56-59).  The product gather is below the C ABI (dnv_gather: the
+kernels store their records straight into rank 0's HBM; denovo_b200.Gather); `gather_records` here is the
+collective fallback for launchers without peer access, on any torch.distributed backend (NCCL with CUDA
+tensors, gloo with CPU tensors in the tests).
 """
 import numpy as np
 
@@ -72,64 +74,3 @@ def globalize_sites(records_np, site_offset):
     out = records_np.copy()
     out["site"] += np.int64(site_offset)
     return out
-
-
-class PeerGather:
-    """Gather of call records to `dst` WITHOUT a data collective: every rank's kernels store their
-    dnv_call records and the record count straight into rank dst's HBM over NVLink (peer stores
-    through a torch symmetric-memory mapping).  The destination holds `slots` generations of
-    world x [64-byte header (int64 count) | cap records]: batch k of a pipelined run writes
-    generation k % slots, so ranks never wait for each other per batch — ONE signal-pad barrier per
-    group of <= slots batches (`barrier()`) tells dst that everything has landed.
-    Rank order = genomic order, so the regions of one generation read in rank order are the
-    gathered result.  `gather_records` (NCCL) is the fallback when symmetric memory is unavailable."""
-
-    HEADER = 64
-
-    def __init__(self, dist, cap_records, itemsize=80, dst=0, slots=1):
-        import torch
-        import torch.distributed._symmetric_memory as symm_mem
-        self.torch, self.dist, self.dst = torch, dist, dst
-        self.world, self.rank = dist.get_world_size(), dist.get_rank()
-        self.cap, self.itemsize, self.slots = int(cap_records), int(itemsize), int(slots)
-        self.slot = (self.HEADER + self.cap * self.itemsize + 255) // 256 * 256
-        self.total = self.slots * self.world * self.slot
-        self.buf = symm_mem.empty((self.total,), dtype=torch.uint8, device="cuda")
-        self.hdl = symm_mem.rendezvous(self.buf, dist.group.WORLD)
-        self.dst_view = self.hdl.get_buffer(dst, (self.total,), torch.uint8)  # rank dst's buffer
-        self.dst_base = int(self.hdl.buffer_ptrs[dst])
-
-    def _off(self, rank, gen):
-        return ((gen % self.slots) * self.world + rank) * self.slot
-
-    def records_ptr(self, gen=0):
-        """Device pointer (in rank dst's memory) where this rank's kernels write their dnv_call records."""
-        return self.dst_base + self._off(self.rank, gen) + self.HEADER
-
-    def count_ptr(self, gen=0):
-        """Device pointer (in rank dst's memory) of this rank's int64 record count."""
-        return self.dst_base + self._off(self.rank, gen)
-
-    def barrier(self):
-        """Signal-pad barrier on the current stream: after it, every rank's stores have landed in dst."""
-        self.hdl.barrier()
-
-    def publish(self, n_calls, gen=0):
-        """Host-known count: write it next to the records, then barrier (synchronous callers)."""
-        lo = self._off(self.rank, gen)
-        self.dst_view[lo:lo + 8].view(self.torch.int64).fill_(int(n_calls))
-        self.hdl.barrier()
-
-    def counts(self, gen=0):
-        """On dst (after barrier): per-rank record counts of one generation."""
-        lo = self._off(0, gen)
-        heads = self.buf[lo:lo + self.world * self.slot].view(self.world, self.slot)[:, :8].contiguous()
-        return heads.view(self.torch.int64).view(-1).tolist()
-
-    def records(self, counts=None, gen=0):
-        """On dst: the gathered records of one generation as one contiguous uint8 [total, itemsize] tensor."""
-        counts = self.counts(gen) if counts is None else counts
-        lo = self._off(0, gen)
-        rows = self.buf[lo:lo + self.world * self.slot].view(self.world, self.slot)
-        rows = rows[:, self.HEADER:self.HEADER + self.cap * self.itemsize].reshape(self.world, self.cap, self.itemsize)
-        return self.torch.cat([rows[r, :counts[r]] for r in range(self.world)], dim=0)

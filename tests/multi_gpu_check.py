@@ -1,6 +1,12 @@
-"""torchrun worker (N >= 2 GPUs): interval-sharded inference with the peer-store gather must equal
-single-GPU inference over the whole range, record for record, in genomic order.
-Run:  python -m torch.distributed.run --nproc-per-node 2 tests/multi_gpu_check.py"""
+"""Worker of the multi-rank gather check (launched with torch.distributed.run, world >= 2): interval-sharded
+inference with the gather of include/denovo_b200.h (dnv_gather: the kernels store records and counts straight
+into rank 0's HBM; the 64-byte IPC handle of that buffer is the only thing the launcher broadcasts) must equal
+single-context inference over the whole range, record for record, in genomic order — for several generations
+in flight and for the NCCL / gloo collective fallback.
+
+  real GPUs :  python -m torch.distributed.run --nproc-per-node 2 tests/multi_gpu_check.py
+  one GPU   :  DNV_TEST_SAME_DEVICE=1 ... (every rank uses cuda:0, gloo carries the handle): the inter-process path
+               (cudaIpcOpenMemHandle, release flags, the destination's wait) is the same."""
 import os
 import sys
 
@@ -16,61 +22,60 @@ from denovo_b200 import sharding  # noqa: E402
 
 def main():
     rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    same = os.environ.get("DNV_TEST_SAME_DEVICE") == "1"
+    dev = 0 if same else local
+    torch.cuda.set_device(dev)
+    if same:
+        dist.init_process_group("gloo")
+    else:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
     total, seed = 3_000_001, 0x5EED0003
     lo, hi = sharding.shard_range(total, world, rank)
     n = hi - lo
     cap = 20000
-    eng = D.TrioEngine(device=local)
+    eng = D.TrioEngine(device=dev)
     counts = torch.empty((n, 12), dtype=torch.int16, device="cuda")
     eng.synth_counts_device(seed, lo, n, counts)
-    for use_peer in ("async", True, False):
-        if use_peer == "async":
-            # pipelined batches: three generations in flight, the kernels store records AND counts into
-            # rank 0's HBM, one barrier for the group; every generation must hold the same gathered result
-            pg = sharding.PeerGather(dist, cap, D.CALL_DT.itemsize, slots=3)
-            torch.cuda.set_stream(torch.cuda.Stream())
-            eng.set_stream(torch.cuda.current_stream().cuda_stream)
-            for g in range(3):
-                eng.infer_device_async(counts, n, pg.records_ptr(g), cap, pg.count_ptr(g))
-            pg.barrier()
-            eng.sync()
-            torch.cuda.synchronize()
-            if rank == 0:
-                gens = [pg.records(gen=g).cpu().numpy().tobytes() for g in range(3)]
-                assert gens[0] == gens[1] == gens[2], "generations differ"
-            got = pg.records(gen=2).cpu().numpy().reshape(-1).view(D.CALL_DT) if rank == 0 else None
-            offs = np.cumsum([0] + pg.counts(gen=2))[:-1] if rank == 0 else None
-            eng.set_stream(None)
-            torch.cuda.set_stream(torch.cuda.default_stream())
-        elif use_peer:
-            pg = sharding.PeerGather(dist, cap, D.CALL_DT.itemsize)
-            nc = eng.infer_device(counts, n, pg.records_ptr(), cap)
-            pg.publish(nc)
-            torch.cuda.synchronize()
-            got = pg.records().cpu().numpy().reshape(-1).view(D.CALL_DT) if rank == 0 else None
-            offs = np.cumsum([0] + pg.counts())[:-1] if rank == 0 else None
-        else:
-            local_calls = torch.zeros((cap, D.CALL_DT.itemsize), dtype=torch.uint8, device="cuda")
-            nc = eng.infer_device(counts, n, local_calls, cap)
-            rec, cnts = sharding.gather_records(local_calls[:nc], dist)
-            got = rec.cpu().numpy().reshape(-1).view(D.CALL_DT) if rank == 0 else None
-            offs = np.cumsum([0] + cnts)[:-1] if rank == 0 else None
+    torch.cuda.synchronize()
+    want = None
+    if rank == 0:
+        whole = torch.empty((total, 12), dtype=torch.int16, device="cuda")
+        eng.synth_counts_device(seed, 0, total, whole)
+        ref_calls = torch.zeros((4 * cap, D.CALL_DT.itemsize), dtype=torch.uint8, device="cuda")
+        nref = eng.infer_device(whole, total, ref_calls, 4 * cap)
+        want = ref_calls[:nref].cpu().numpy().reshape(-1).view(D.CALL_DT).copy()
+        del whole
+    # ---- the C-ABI gather: three generations in flight, two rounds (the slots are reused)
+    g = D.Gather(eng, world, rank, cap, gens=3)
+    g.exchange(dist)
+    for rnd in range(2):
+        for gen in range(3):
+            g.submit(counts, n, lo, gen)
+        g.arrive()
         if rank == 0:
-            got = got.copy()
-            bounds = [sharding.shard_range(total, world, r)[0] for r in range(world)]
-            ends = list(offs[1:]) + [len(got)]
-            for r in range(world):  # shard-relative -> global site index
-                got["site"][offs[r]:ends[r]] += bounds[r]
-            whole = torch.empty((total, 12), dtype=torch.int16, device="cuda")
-            eng.synth_counts_device(seed, 0, total, whole)
-            ref_calls = torch.zeros((4 * cap, D.CALL_DT.itemsize), dtype=torch.uint8, device="cuda")
-            nref = eng.infer_device(whole, total, ref_calls, 4 * cap)
-            want = ref_calls[:nref].cpu().numpy().reshape(-1).view(D.CALL_DT)
-            assert len(got) == len(want) and got.tobytes() == want.tobytes(), ("mismatch", use_peer, len(got), len(want))
-            print("multi_gpu_check OK: world %d, %s gather, %d calls" % (world, {"async": "pipelined peer-store", True: "peer-store", False: "NCCL"}[use_peer], len(got)))
-        dist.barrier()
+            g.wait()
+            for gen in range(3):
+                got, per = g.fetch(gen)
+                assert int(per.sum()) == len(got) and len(per) == world
+                assert len(got) == len(want) and got.tobytes() == want.tobytes(), ("gather mismatch", rnd, gen, len(got), len(want))
+        eng.sync()
+        dist.barrier()  # the slots may be rewritten once rank 0 has fetched them
+        if rank == 0:
+            print("multi_gpu_check OK: world %d, peer-store gather round %d, %d calls" % (world, rnd, len(want)))
+    g.close()
+    # ---- collective fallback (NCCL on GPUs, gloo on CPU tensors)
+    local_calls = torch.zeros((cap, D.CALL_DT.itemsize), dtype=torch.uint8, device="cuda")
+    nc = eng.infer_device(counts, n, local_calls, cap)
+    send = local_calls[:nc] if not same else local_calls[:nc].cpu()
+    rec, cnts = sharding.gather_records(send, dist)
+    if rank == 0:
+        got = rec.cpu().numpy().reshape(-1).view(D.CALL_DT).copy()
+        offs = np.cumsum([0] + cnts)
+        for r in range(world):  # shard-relative -> global site index
+            got["site"][offs[r]:offs[r + 1]] += sharding.shard_range(total, world, r)[0]
+        assert got.tobytes() == want.tobytes(), "collective gather mismatch"
+        print("multi_gpu_check OK: world %d, collective gather, %d calls" % (world, len(got)))
+    dist.barrier()
     dist.destroy_process_group()
 
 

@@ -39,16 +39,14 @@ def main():
         buf = torch.empty((5003, 12), dtype=torch.int16, device="cuda")
         eng.synth_counts_device(7, 11, 5003, buf)
         eng.synth_counts_at(7, np.arange(0, 999, 3))
-        # asynchronous batches on one context and on the two-context pipeline
+        # asynchronous batches over the context's lanes, and a two-rank device group (peer-store gather)
         out = torch.zeros((5003, D.CALL_DT.itemsize), dtype=torch.uint8, device="cuda")
         h_nc = torch.zeros(4, dtype=torch.int64).pin_memory()
         for i in range(3):
             eng.infer_device_async(buf, 5003 - 100 * i, out, 5003, h_nc.data_ptr() + 8 * i)
         eng.sync()
-        with D.BatchPipeline(depth=2) as pipe:
-            for i in range(4):
-                pipe.submit(buf, 5003, out, 5003, h_nc.data_ptr() + 8 * i)
-            pipe.sync()
+        with D.DeviceGroup([0, 0]) as grp:
+            grp.infer(buf.cpu().numpy().view(np.uint16).reshape(-1, 3, 4))
     print("sanitize_smoke OK")
 
 

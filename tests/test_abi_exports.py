@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(L.EXPORTS) == names
-    assert lib.dnv_abi_version() == 1
+    assert lib.dnv_abi_version() == 2
 
 
 def test_struct_sizes_match_header():

@@ -87,16 +87,100 @@ def test_10m_sites_every_site_against_the_oracle(method, lrt):
         assert np.allclose(e["p"], sel["p"], rtol=1e-9, atol=0)
 
 
-def test_two_gpu_sharded_gather_equals_single_gpu():
-    """Needs >= 2 GPUs (skipped on a 1-GPU box): torchrun tests/multi_gpu_check.py."""
+def _run_gather_workers(world, same_device):
+    import os
     import subprocess
     import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    if same_device:
+        env["DNV_TEST_SAME_DEVICE"] = "1"
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                        "--master-addr", "127.0.0.1", "--master-port", "29533" if same_device else "29534",
+                        "tests/multi_gpu_check.py"], cwd=root, capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.stdout.count("multi_gpu_check OK") == 3  # two gather rounds + the collective fallback
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_interprocess_gather_equals_single_context(world):
+    """One process per rank, every rank on cuda:0 (runs on a one-GPU box): the interval shards, the IPC-mapped
+    destination buffer, the kernels' remote stores, the release flags and the destination's wait must reproduce
+    single-context inference over the whole range record for record."""
+    _run_gather_workers(world, same_device=True)
+
+
+def test_multi_gpu_gather_equals_single_gpu():
+    """The same over NVLink on real devices (skipped on a 1-GPU box)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    root = __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29533", "tests/multi_gpu_check.py"],
-                       cwd=root, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert r.stdout.count("multi_gpu_check OK") == 3  # pipelined peer-store, peer-store, NCCL
+    _run_gather_workers(min(torch.cuda.device_count(), 8), same_device=False)
+
+
+def test_gather_ends_in_one_process_and_slot_layout():
+    """dnv_gather inside one process (peer access; both ends on cuda:0): slots are disjoint, 256-byte aligned,
+    generation-major, records 16-byte aligned; two ranks' shards gathered = the whole range."""
+    import ctypes as C
+    import torch
+    total, cap, gens, world = 700_001, 8000, 4, 2
+    with D.TrioEngine() as e0, D.TrioEngine() as e1:
+        ends = [D.Gather(e0, world, 0, cap, gens), D.Gather(e1, world, 1, cap, gens)]
+        ends[1].attach(ends[0])
+        seen = {}
+        for gen in range(2 * gens):
+            for r in range(world):
+                rec, cnt = C.c_void_p(), C.c_void_p()
+                assert e0.lib.dnv_gather_slot(ends[0]._h, r, gen, C.byref(rec), C.byref(cnt)) == 0
+                assert cnt.value % 256 == 0 and rec.value == cnt.value + 64 and rec.value % 16 == 0
+                if gen < gens:
+                    assert all(abs(cnt.value - o) >= 64 + cap * 80 for o in seen.values())
+                    seen[(r, gen)] = cnt.value
+                else:
+                    assert cnt.value == seen[(r, gen - gens)]  # generations wrap
+        whole = torch.empty((total, 12), dtype=torch.int16, device="cuda")
+        e0.synth_counts_device(0x5EED0003, 0, total, whole)
+        ref = torch.zeros((2 * cap, 80), dtype=torch.uint8, device="cuda")
+        k = e0.infer_device(whole, total, ref, 2 * cap)
+        want = ref[:k].cpu().numpy().tobytes()
+        half = total // 2
+        for gen in (0, 1, 5):
+            ends[0].submit(whole[:half], half, 0, gen)
+            ends[1].submit(whole[half:], total - half, half, gen)
+        ends[1].arrive()
+        ends[0].arrive()
+        ends[0].wait()
+        for gen in (0, 1, 5):
+            got, per = ends[0].fetch(gen)
+            assert got.tobytes() == want and per.sum() == k
+        e1.sync()
+        with pytest.raises(D.DenovoError) as ei:   # too small a host buffer: the needed total is reported
+            ends[0].fetch(0, cap=3)
+        assert ei.value.code == D.DNV_E_CAPACITY and str(k) in str(ei.value)
+        for g in ends:
+            g.close()
+
+
+@pytest.mark.parametrize("devices", [[0], [0, 0], [0, 0, 0, 0, 0]])
+def test_device_group_equals_single_context(devices):
+    """dnv_group (one process, N devices; here N contexts on cuda:0): host counts are split by interval, one host
+    thread per device, records gathered through device 0 — equal to one context over the whole batch."""
+    n = 1_000_003
+    counts = O.synth_counts(0x5EED0001, 0, n, depth=30, seq_err=1e-2)
+    with D.TrioEngine() as eng:
+        want, _ = eng.infer(counts)
+    with D.DeviceGroup(devices) as grp:
+        got = grp.infer(counts)
+        assert got.tobytes() == want.tobytes()
+        st = grp.stats()
+        assert st["n_sites"] == n and st["n_calls"] == len(want)
+        got8 = grp.infer(counts.astype(np.uint8))
+        assert got8.tobytes() == want.tobytes()
+        # fewer sites than devices, no sites, too small a capacity
+        few = grp.infer(counts[:3])
+        assert len(few) == int((want["site"] < 3).sum())
+        assert len(grp.infer(counts[:0])) == 0
+        with pytest.raises(D.DenovoError) as ei:
+            grp.infer(counts, cap=5)
+        assert ei.value.code == D.DNV_E_CAPACITY and str(len(want)) in str(ei.value)
+        assert grp.infer(counts).tobytes() == want.tobytes()   # still usable

@@ -81,26 +81,3 @@ def test_reference_stride_shards():
     """M/VariantCaller.java:89-98 with start 1, end 1000, 4 threads."""
     assert sharding.stride_shards(1, 1000, 4) == [(1, 249), (250, 498), (499, 747), (748, 1000)]
     assert sharding.stride_shards(1, 10, 1) == [(1, 10)]
-
-
-def test_peer_gather_slot_layout():
-    """PeerGather's destination layout (pure arithmetic, no GPU): world x slots regions of
-    [64-byte header | cap records], 256-byte aligned, disjoint, generation-major."""
-    from denovo_b200.sharding import PeerGather
-    pg = object.__new__(PeerGather)
-    pg.world, pg.rank, pg.cap, pg.itemsize, pg.slots, pg.dst = 8, 3, 1000, 80, 5, 0
-    pg.slot = (PeerGather.HEADER + pg.cap * pg.itemsize + 255) // 256 * 256
-    pg.dst_base = 1 << 20
-    seen = set()
-    for gen in range(2 * pg.slots):
-        for r in range(pg.world):
-            off = pg._off(r, gen)
-            assert off % 256 == 0 and off + pg.slot <= pg.slots * pg.world * pg.slot
-            if gen < pg.slots:
-                assert off not in seen
-                seen.add(off)
-            else:
-                assert off == pg._off(r, gen - pg.slots)  # generations wrap
-    assert len(seen) == pg.slots * pg.world
-    assert pg.count_ptr(2) == pg.dst_base + pg._off(3, 2)
-    assert pg.records_ptr(2) == pg.count_ptr(2) + PeerGather.HEADER and pg.records_ptr(2) % 16 == 0
