@@ -224,7 +224,7 @@ def aux_undecided(D, torch, np, local, fractions, n=10_000_000, steps=8):
         for f in fractions:
             mix = torch.where((u < f)[:, None], hostile, base).contiguous()
             with torch.cuda.stream(stream):
-                for _ in range(2):
+                for _ in range(4):  # every lane allocates its scratch on its first batch
                     eng.infer_device_async(mix, n, calls, cap, h)
                 eng.sync()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -350,7 +350,7 @@ def aux_pileup(D, torch, np, local, n_sites=2_000_000):
             "reads_to_calls_ms": times[1], "reads_to_calls_sites_per_s": n_sites / times[1] * 1e3, "reads_to_calls_calls": int(chain["calls"])}
 
 
-def genome_walk(D, torch, np, dist, eng, stream, gather, rank, world, local, chunk=1 << 25, seed=0x5EED0004):
+def genome_walk(D, torch, np, dist, eng, stream, gather, rank, world, local, chunk=1 << 26, seed=0x5EED0004):
     """BASELINE config 4: every position of an hg19-sized axis (3,095,693,983 sites, 30x), interval-sharded over the
     ranks (STRONG scaling: the genome is fixed), counts generated procedurally per chunk on the device (the 74 GB
     of counts are never materialised), call records gathered on rank 0.  Generation is excluded from the timed
@@ -615,7 +615,7 @@ def main():
         aux = {}
         if world > 1:
             # config 4 (strong scaling over the ranks) with its gather
-            gw = D.Gather(eng, world, rank, (1 << 25) // 50, gens=2)
+            gw = D.Gather(eng, world, rank, (1 << 26) // 50, gens=2)
             gw.exchange(dist)
             g = genome_walk(D, torch, np, dist, eng, stream, gw, rank, world, local)
             tt = torch.tensor([g["infer_ms"], g["gen_ms"]], dtype=torch.float64, device="cuda")
@@ -625,12 +625,12 @@ def main():
                 aux["config4_genome_every_position"] = {"sites": 3_095_693_983, "n_gpus": world, "scaling": "strong",
                                                         "infer_ms_max_over_ranks": float(tt[0]), "sites_per_s": 3_095_693_983 / float(tt[0]) * 1e3,
                                                         "generator_ms_max_over_ranks": float(tt[1]), "calls_gathered_on_rank0": g["calls"],
-                                                        "chunk_sites": 1 << 25}
+                                                        "chunk_sites": 1 << 26}
         elif rank == 0:
             g = genome_walk(D, torch, np, dist, eng, stream, None, 0, 1, local)
             aux["config4_genome_every_position"] = {"sites": g["sites"], "n_gpus": 1, "scaling": "strong", "infer_ms_max_over_ranks": g["infer_ms"],
                                                     "sites_per_s": g["sites"] / g["infer_ms"] * 1e3, "generator_ms_max_over_ranks": g["gen_ms"],
-                                                    "calls_gathered_on_rank0": g["calls"], "chunk_sites": 1 << 25}
+                                                    "calls_gathered_on_rank0": g["calls"], "chunk_sites": 1 << 26}
         # config 5 on every rank (weak: 10 M sites per GPU), config 3 variants / config 2 / pileup on rank 0
         c5 = [aux_read_config(D, torch, local, "BAYES", 200, 1e-3, mu, 1.0, n, 0x5EED0005) for mu in (1e-10, 1e-6)]
         if world > 1:

@@ -22,10 +22,19 @@ cap = n // 100
 calls = [torch.zeros((cap, 80), dtype=torch.uint8, device="cuda") for _ in range(4)]
 h = torch.zeros(4, dtype=torch.int64).pin_memory()
 ROUNDS = 4  # the first rounds warm up (allocations, graph capture)
+MODE = sys.argv[3] if len(sys.argv) > 3 else "async"
+import time
 for rep in range(ROUNDS):
+    t0 = time.perf_counter()
     for i in range(K):
-        eng.infer_device_async(counts, n, calls[i % 4], cap, h[i % 4:i % 4 + 1])
+        if MODE == "sync":   # one synchronous call per batch: chunks over the lanes, graph replay
+            eng.infer_device(counts, n, calls[0], cap)
+        else:
+            eng.infer_device_async(counts, n, calls[i % 4], cap, h[i % 4:i % 4 + 1])
     eng.sync()
+    print("round %d: %.1f us per batch (host clock)" % (rep, (time.perf_counter() - t0) / K * 1e6))
+if MODE == "sync":
+    K *= 3
 SLOTS = 1024
 buf = np.zeros((4, SLOTS, 6), np.uint64)
 seq = np.zeros(4, np.uint32)
