@@ -180,6 +180,19 @@ bool will_screen(const dnv_ctx* ctx, bool dense) {
   return !direct && (map ? ctx->h_tab.map_screen_ok : ctx->h_tab.early_ok) && !dense && !(ctx->prm.flags & DNV_F_NO_SCREEN);
 }
 
+// Per chunk: the screen, unless recent batches were screen-hostile.  The screen pays when it decides most sites
+// (99 % of a genome-wide or candidate-file pileup); on inputs that are mostly de-novo-pattern sites — e.g. the
+// Mendelian-inconsistent candidates FULL mode passes from the VARIANT filter to READ mode
+// (M/DenovoRunner.java:173-182) — everything it leaves goes through the list kernel at ~175 ns per site, and above
+// ~15 % undecided the all-sites fused kernel (trio_fast.cuh, ~34 ns per site) wins.  Both paths return identical
+// records; while in dense mode every 32nd chunk is screened again to re-measure the mix.
+bool pick_screen(dnv_ctx* ctx, bool dense) {
+  if (!will_screen(ctx, dense)) return false;
+  if (!ctx->dense_mode) return true;
+  if (++ctx->dense_probe >= 32) { ctx->dense_probe = 0; return true; }
+  return false;
+}
+
 // entry of `key` in a graph cache: the existing one, else the least recently used slot recycled for it
 static GraphEntry* graph_slot(dnv_ctx* ctx, GraphEntry* tab, const GraphKey& key) {
   GraphEntry* lru = &tab[0];
@@ -420,18 +433,21 @@ static void collect_kernel_times(dnv_ctx* ctx) {
 }
 
 // statistics of everything enqueued since the previous collect (h_acc holds the accumulators)
-static int finish_stats(dnv_ctx* ctx, int64_t n_sites) {
+int dnvi_finish_stats(dnv_ctx* ctx, int64_t n_sites) {
   collect_kernel_times(ctx);
   ctx->stats.n_sites = n_sites;
   ctx->stats.n_calls = (int64_t)ctx->h_acc[0];
   ctx->stats.n_hard = (int64_t)ctx->h_acc[2];
-  ctx->stats.n_screened_out = ctx->screened ? n_sites - (int64_t)ctx->h_acc[1] : 0;
+  ctx->stats.n_screened_out = ctx->sites_screened - (int64_t)ctx->h_acc[1];
+  if (ctx->sites_screened >= 4096 && !getenv("DNV_NO_DENSE_MODE"))
+    ctx->dense_mode = (double)ctx->h_acc[1] > 0.15 * (double)ctx->sites_screened;
+  ctx->sites_screened = 0;
   return DNV_OK;
 }
 // host wait + statistics
 static int finish_all(dnv_ctx* ctx, int64_t n_sites) {
   const int rc = collect(ctx);
-  return rc ? rc : finish_stats(ctx, n_sites);
+  return rc ? rc : dnvi_finish_stats(ctx, n_sites);
 }
 
 // batches enqueued by the async entry points must be collected before a synchronous call reuses the ctx
@@ -481,7 +497,7 @@ static int infer_device_async_impl(dnv_ctx* ctx, const void* d_counts, int bps, 
   }
   // A batch of one chunk on the calls-only path is replayable: the second time its arguments are seen it is
   // captured on its lane's stream, from then on it costs the host one wait + one graph launch.
-  const bool graphable = ctx->use_graphs_async && n > 0 && n <= device_chunk() && will_screen(ctx, false) && true;
+  const bool graphable = ctx->use_graphs_async && !ctx->dense_mode && n > 0 && n <= device_chunk() && will_screen(ctx, false) && true;
   if (graphable) {
     TrioLane& ln = ctx->lane[ctx->lane_next];
     const GraphKey key{d_counts, d_calls, n_calls_out, nullptr, n, site_base, cap, bps};
@@ -504,6 +520,7 @@ static int infer_device_async_impl(dnv_ctx* ctx, const void* d_counts, int bps, 
       ln.used = true;
       ctx->lane_next = (ctx->lane_next + 1) % ctx->n_lanes;
       ctx->screened = true;
+      ctx->sites_screened += n;
       ctx->stats.n_launches += 3;
       ctx->n_async++;
       ctx->async_sites += n;
@@ -531,7 +548,7 @@ static int infer_device_impl(dnv_ctx* ctx, const void* d_counts, int bps, int64_
   reset_call_state(ctx);
   // the whole call — chunks over the lanes, join, statistics to the host — is replayable when its arguments repeat
   bool launched = false;
-  if (ctx->use_graphs && n > 0 && will_screen(ctx, d_dense != nullptr)) {
+  if (ctx->use_graphs && !ctx->dense_mode && n > 0 && will_screen(ctx, d_dense != nullptr)) {
     const GraphKey key{d_counts, d_calls, nullptr, d_dense, n, 0, cap, bps};
     GraphEntry* ge = graph_slot(ctx, ctx->sync_graphs, key);
     ge->seen++;
@@ -554,6 +571,7 @@ static int infer_device_impl(dnv_ctx* ctx, const void* d_counts, int bps, int64_
       const int64_t chunk = chunk_for(ctx, n, true);
       ctx->stats.n_launches += 3 * ((n + chunk - 1) / chunk);
       ctx->screened = true;
+      ctx->sites_screened += n;
       launched = true;
     }
   }
@@ -565,7 +583,7 @@ static int infer_device_impl(dnv_ctx* ctx, const void* d_counts, int bps, int64_
     rc = collect(ctx);
     if (rc) return rc;
   }
-  rc = finish_stats(ctx, n);
+  rc = dnvi_finish_stats(ctx, n);
   if (rc) return rc;
   *n_calls = ctx->stats.n_calls;
   if (*n_calls > cap) {

@@ -131,6 +131,9 @@ struct dnv_ctx {
   size_t cstatus_bytes;
   unsigned long long epoch;           // launch tag of the compaction kernel's status words
   bool screened;           // the last call used the screen
+  int64_t sites_screened;  // sites that went through the screen since the statistics were last collected
+  bool dense_mode;         // recent batches left > 15 % of their sites undecided: the all-sites fused kernel is faster
+  int dense_probe;         // chunks since dense_mode last sent one through the screen to re-measure
   bool capturing;          // a CUDA graph of the current submission is being captured (no allocation allowed)
   bool use_graphs;         // DNV_GRAPHS=0 turns graph replay off
   bool use_graphs_async;   // DNV_GRAPHS_ASYNC=1: also replay asynchronous batches
@@ -175,6 +178,9 @@ struct dnv_ctx {
     }                                                                         \
   } while (0)
 
+// statistics (and the dense-mode decision) of everything enqueued since the previous collect; internal, C linkage
+extern "C" int dnvi_finish_stats(dnv_ctx* ctx, int64_t n_sites);
+
 namespace dnv {
 constexpr int kCtrAcc = 16, kCtrZero = 23, kCtrWork = 24, kCtrWords = 32;
 
@@ -217,6 +223,7 @@ int ensure_stage_calls(dnv_ctx* ctx, int64_t calls_cap);
 int enqueue_device_batch(dnv_ctx* ctx, const void* d_counts, int bps, int64_t n, int64_t site_base, dnv_site_result* d_dense,
                          dnv_call* d_calls, int64_t cap, int64_t* count_out, bool split, bool no_sub_wait);
 bool will_screen(const dnv_ctx* ctx, bool dense);
+bool pick_screen(dnv_ctx* ctx, bool dense);
 int enqueue_host_batch(dnv_ctx* ctx, const void* counts, int bps, int64_t n, int64_t site_base, dnv_site_result* dense,
                        dnv_call* d_calls, int64_t cap, int64_t* count_out);
 inline bool parallel(const dnv_ctx* ctx) { return ctx->n_lanes > 1; }

@@ -333,10 +333,11 @@ static int group_infer(dnv_group* grp, const void* counts, int bps, int64_t n, d
     rc = cudaSetDevice(ctx->device) == cudaSuccess ? collect(ctx) : DNV_E_CUDA;
     if (rc) return rc;
     const int64_t m = lo_of(r + 1) - lo_of(r);
+    dnvi_finish_stats(ctx, m);
     grp->stats.n_sites += m;
-    grp->stats.n_calls += (int64_t)ctx->h_acc[0];
-    grp->stats.n_hard += (int64_t)ctx->h_acc[2];
-    grp->stats.n_screened_out += ctx->screened ? m - (int64_t)ctx->h_acc[1] : 0;
+    grp->stats.n_calls += ctx->stats.n_calls;
+    grp->stats.n_hard += ctx->stats.n_hard;
+    grp->stats.n_screened_out += ctx->stats.n_screened_out;
     grp->stats.n_launches += ctx->stats.n_launches;
   }
   return frc;

@@ -287,7 +287,7 @@ int launch_trio_chunk(dnv_ctx* ctx, const ChunkArgs& a) {
   const bool direct = (ctx->prm.flags & DNV_F_FORCE_DIRECT) != 0;
   const bool timed = (ctx->prm.flags & DNV_F_TIME_KERNELS) != 0 && ctx->n_timed < 64;
   const bool map = ctx->prm.method == DNV_METHOD_MAP;
-  const bool screen = will_screen(ctx, a.d_dense != nullptr);
+  const bool screen = ctx->capturing ? will_screen(ctx, a.d_dense != nullptr) : pick_screen(ctx, a.d_dense != nullptr);
   // the unscreened path keeps its decision bits in shared scratch: always lane 0 (its chunks serialise)
   const int li = screen ? ctx->lane_next : 0;
   if (screen) ctx->lane_next = (ctx->lane_next + 1) % ctx->n_lanes;
@@ -346,6 +346,7 @@ int launch_trio_chunk(dnv_ctx* ctx, const ChunkArgs& a) {
     if (rc) return rc;
     if (timed) DNV_CUDA(cudaEventRecord(ctx->ev_k1[ctx->n_timed++], tl));
     ctx->screened = true;
+    if (!ctx->capturing) ctx->sites_screened += n;
   } else {
     rc = ensure_call_idx(ctx, a.cap);
     if (rc) return rc;

@@ -28,6 +28,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "denovo_b200.h"
@@ -101,7 +102,9 @@ struct CommandLine {
   uint64_t syntheticSeed = 0x5EED0001ULL;
   double syntheticDepth = 30.0;
   std::string syntheticCallset;  // binary dnv_vcall stream, see VariantFileSource
-  int device = 0;
+  std::string syntheticSource = "reads";  // reads: synthetic reads -> pileup kernel -> inference; counts: pileup counts directly
+  int syntheticReadLength = 100;
+  std::vector<int32_t> devices = {0};  // CUDA devices of the READ caller (interval-sharded, records gathered through the first)
   bool help = false;
 
   static std::string usage() {
@@ -129,7 +132,41 @@ struct CommandLine {
            " --synthetic_seed <u64>            : seed of the synthetic trio (default 0x5EED0001)\n"
            " --synthetic_depth <x>             : mean read depth per individual (default 30)\n"
            " --synthetic_callset <file>        : binary (variant, call) stream for the VARIANT caller\n"
-           " --device <n>                      : CUDA device ordinal (default 0)\n";
+           " --synthetic_source <reads|counts> : reads (default): aligned reads at the candidates -> pileup kernel -> inference;\n"
+           "                                     counts: pileup counts straight from the generator\n"
+           " --synthetic_read_length <n>       : length of the synthetic reads (default 100)\n"
+           " --device <n>                      : CUDA device ordinal (default 0)\n"
+           " --devices <list>                  : CUDA devices, e.g. 0-7 or 0,2,3: candidate sites are sharded by interval over\n"
+           "                                     them, the call records gathered through the first\n";
+  }
+
+  // "0-7", "0,2,3", "1"
+  static std::vector<int32_t> parseDevices(const std::string& v) {
+    std::vector<int32_t> out;
+    size_t a = 0;
+    while (a <= v.size()) {
+      size_t b = v.find(',', a);
+      if (b == std::string::npos) b = v.size();
+      const std::string part = v.substr(a, b - a);
+      const size_t dash = part.find('-');
+      char* end = nullptr;
+      if (part.empty()) throw CmdLineException("\"" + v + "\" is not a valid value for \"--devices\"");
+      if (dash == std::string::npos) {
+        const long x = std::strtol(part.c_str(), &end, 10);
+        if (*end || x < 0) throw CmdLineException("\"" + v + "\" is not a valid value for \"--devices\"");
+        out.push_back((int32_t)x);
+      } else {
+        const long lo = std::strtol(part.substr(0, dash).c_str(), &end, 10);
+        const bool bad_lo = *end != 0 || dash == 0;
+        const std::string hs = part.substr(dash + 1);
+        const long hi = std::strtol(hs.c_str(), &end, 10);
+        if (bad_lo || *end || hs.empty() || lo < 0 || hi < lo) throw CmdLineException("\"" + v + "\" is not a valid value for \"--devices\"");
+        for (long x = lo; x <= hi; x++) out.push_back((int32_t)x);
+      }
+      a = b + 1;
+    }
+    if (out.empty() || out.size() > 64) throw CmdLineException("\"--devices\" takes 1 to 64 devices");
+    return out;
   }
 
   void setArgs(int argc, char** argv) {
@@ -191,7 +228,18 @@ struct CommandLine {
       else if (f == "--synthetic_seed") syntheticSeed = (uint64_t)integer(f, need(i));
       else if (f == "--synthetic_depth") syntheticDepth = num(f, need(i));
       else if (f == "--synthetic_callset") syntheticCallset = need(i);
-      else if (f == "--device") device = (int)integer(f, need(i));
+      else if (f == "--synthetic_source") {
+        syntheticSource = need(i);
+        for (auto& c : syntheticSource) c = (char)std::tolower((unsigned char)c);
+        if (syntheticSource != "reads" && syntheticSource != "counts")
+          throw CmdLineException("\"" + syntheticSource + "\" is not a valid value for \"--synthetic_source\"");
+      }
+      else if (f == "--synthetic_read_length") {
+        syntheticReadLength = (int)integer(f, need(i));
+        if (syntheticReadLength < 1 || syntheticReadLength > 1000) throw CmdLineException("\"--synthetic_read_length\" must lie in 1..1000");
+      }
+      else if (f == "--device") devices = {(int32_t)integer(f, need(i))};
+      else if (f == "--devices") devices = parseDevices(need(i));
       else throw CmdLineException("\"" + f + "\" is not a valid option");
     }
     if (help) return;
@@ -284,14 +332,15 @@ struct DenovoShared {
   CommandLine cmd;
   std::set<int> chromosomes;  // EnumSet<Chromosome>, ALL when no --chromosome (M/DenovoRunner.java:85-94)
   std::shared_ptr<Logger> logger;
-  dnv_ctx* ctx = nullptr;
+  dnv_ctx* ctx = nullptr;      // single-device engine (VARIANT filter, pileup)
+  dnv_group* grp = nullptr;    // the READ caller's devices
 
   explicit DenovoShared(const CommandLine& c) : cmd(c) {
     if (c.chromosomes.empty()) for (int i = 0; i < 25; i++) chromosomes.insert(i);
     else for (const auto& s : c.chromosomes) chromosomes.insert(chromosome_from_string(s));
     logger = std::make_shared<Logger>(c.logLevel, c.logFile);
   }
-  ~DenovoShared() { if (ctx) dnv_destroy(ctx); }
+  ~DenovoShared() { if (grp) dnv_group_destroy(grp); if (ctx) dnv_destroy(ctx); }
   DenovoShared(const DenovoShared&) = delete;
 
   // new BayesInfer(shared) -> dnv_create (tables built once, M/ReadCaller.java:49-52)
@@ -302,12 +351,132 @@ struct DenovoShared {
       p.denovo_mut_rate = cmd.denovoMutationRate;
       p.lrt_threshold = cmd.lrtThreshold;
       p.method = cmd.inferMethod;
-      p.device = cmd.device;
+      p.device = cmd.devices[0];
       if (dnv_create(&p, &ctx) != DNV_OK) throw std::runtime_error(std::string("dnv_create: ") + dnv_last_error());
     }
     return ctx;
   }
+  dnv_params params() const {
+    dnv_params p{};
+    p.seq_err_rate = cmd.sequenceErrorRate;
+    p.denovo_mut_rate = cmd.denovoMutationRate;
+    p.lrt_threshold = cmd.lrtThreshold;
+    p.method = cmd.inferMethod;
+    p.device = cmd.devices[0];
+    return p;
+  }
+  // the reference's one shared BayesInfer, used by every task of the pool (M/ReadCaller.java:49-52,91-95): here one
+  // device group — a context per device, shards by interval, records gathered through the first device
+  dnv_group* group() {
+    if (!grp) {
+      const dnv_params p = params();
+      if (dnv_group_create(&p, cmd.devices.data(), (int32_t)cmd.devices.size(), &grp) != DNV_OK)
+        throw std::runtime_error(std::string("dnv_group_create: ") + dnv_last_error());
+    }
+    return grp;
+  }
 };
+
+// page-locked host buffer (dnv_alloc_pinned): what crosses the ABI in bulk lives in pinned memory, so that the
+// host-to-device copies run at the PCIe rate and the devices of a group copy concurrently
+template <typename T>
+struct Pinned {
+  T* p = nullptr;
+  size_t n = 0;
+  explicit Pinned(size_t count) : n(count) {
+    void* v = nullptr;
+    if (dnv_alloc_pinned(std::max<size_t>(count, 1) * sizeof(T), &v) != DNV_OK)
+      throw std::runtime_error(std::string("dnv_alloc_pinned: ") + dnv_last_error());
+    p = (T*)v;
+  }
+  ~Pinned() { dnv_free_pinned(p); }
+  Pinned(const Pinned&) = delete;
+  Pinned& operator=(const Pinned&) = delete;
+  T* data() { return p; }
+  T& operator[](size_t i) { return p[i]; }
+};
+
+// ---- synthetic read source (bit-for-bit specification: the test oracle's
+// synth_ref_reads_at) — stands in for the three reads().search() calls per candidate (M/ReadCaller.java:155-186).
+// For every candidate site (global position i) and person, the reads of the synthetic pileup become aligned reads
+// of length L that cover the site; everything else in a read is the synthetic reference genome at its own
+// position, with '-' gaps.  Output in the layout dnv_pileup takes: sorted by (person, start).
+struct SyntheticReads {
+  std::vector<int64_t> read_start, base_off;
+  std::vector<char> bases;
+  std::vector<uint8_t> person;
+};
+namespace synth {
+constexpr uint64_t PHI = 0x9E3779B97F4A7C15ULL;
+inline uint64_t splitmix64(uint64_t x) {
+  uint64_t z = x + PHI;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  return z ^ (z >> 31);
+}
+inline uint64_t key(uint64_t seed, uint64_t stream) { return splitmix64(seed ^ (stream * PHI)); }
+}  // namespace synth
+
+inline SyntheticReads synthetic_reads_at(uint64_t seed, const std::vector<int64_t>& index, const std::vector<uint64_t>& thr,
+                                         uint32_t err_thr, int L, uint32_t gap_thr) {
+  using namespace synth;
+  struct R { int64_t start, site; int32_t j; uint8_t person, base; };
+  std::vector<R> rd;
+  const uint64_t k_class = key(seed, 0), k_ref = key(seed, 1), k_alt = key(seed, 2), k_par = key(seed, 3), k_fill = key(seed, 16);
+  for (const int64_t site : index) {
+    const uint64_t i = (uint64_t)site;
+    const uint32_t c100 = (uint32_t)(((splitmix64(k_class ^ i) >> 32) * 100ULL) >> 32);
+    const int cls = c100 < 90 ? 0 : (c100 < 99 ? 1 : 2);
+    const int ref = (int)(splitmix64(k_ref ^ i) & 3);
+    const int alt = (ref + 1 + (int)(splitmix64(k_alt ^ i) % 3)) & 3;
+    const uint64_t pb = splitmix64(k_par ^ i);
+    int g[3][2] = {{ref, ref}, {ref, ref}, {ref, ref}};
+    if (cls == 1) { g[(int)(pb & 1)][1] = alt; if ((pb >> 1) & 1) g[2][1] = alt; }
+    else if (cls == 2) g[2][1] = alt;
+    for (int p = 0; p < 3; p++) {
+      const uint64_t ud = splitmix64(key(seed, 4 + (uint64_t)p) ^ i);
+      const int depth = (int)(std::upper_bound(thr.begin(), thr.end(), ud) - thr.begin());  // #{k : thr[k] <= ud}
+      const uint64_t k_read = key(seed, 8 + (uint64_t)p), k_off = key(seed, 12 + (uint64_t)p);
+      for (int j = 0; j < depth; j++) {
+        const uint64_t rid = (i << 16) | (uint64_t)j;
+        const uint64_t u = splitmix64(k_read ^ rid);
+        int b = g[p][u & 1];
+        if ((uint32_t)(u >> 32) < err_thr) b = (b + 1 + (int)(((u >> 8) & 0xFFFF) % 3)) & 3;
+        const int64_t off = (int64_t)(splitmix64(k_off ^ rid) % (uint64_t)L);
+        rd.push_back(R{site - off, site, j, (uint8_t)p, (uint8_t)b});
+      }
+    }
+  }
+  std::sort(rd.begin(), rd.end(), [](const R& a, const R& b) {
+    if (a.person != b.person) return a.person < b.person;
+    if (a.start != b.start) return a.start < b.start;
+    if (a.site != b.site) return a.site < b.site;
+    return a.j < b.j;
+  });
+  SyntheticReads out;
+  const size_t n = rd.size();
+  out.read_start.resize(n); out.base_off.resize(n + 1); out.person.resize(n); out.bases.resize(n * (size_t)L);
+  const unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  auto fill = [&](size_t lo, size_t hi) {
+    for (size_t r = lo; r < hi; r++) {
+      out.read_start[r] = rd[r].start; out.person[r] = rd[r].person; out.base_off[r] = (int64_t)(r * (size_t)L);
+      const uint64_t rid = ((uint64_t)rd[r].site << 16) | (uint64_t)rd[r].j;
+      const uint64_t k_gap = key(seed, 17 + 32 * (uint64_t)rd[r].person);
+      char* dst = out.bases.data() + r * (size_t)L;
+      for (int t = 0; t < L; t++) {
+        const int64_t q = rd[r].start + t;
+        if (q == rd[r].site) dst[t] = "ACGT"[rd[r].base];
+        else if ((uint32_t)(splitmix64(k_gap ^ (rid * 1024 + (uint64_t)t)) >> 32) < gap_thr) dst[t] = '-';
+        else dst[t] = "ACGT"[splitmix64(k_fill ^ (uint64_t)q) & 3];
+      }
+    }
+  };
+  std::vector<std::thread> th;
+  for (unsigned w = 0; w < nt; w++) th.emplace_back(fill, n * w / nt, n * (w + 1) / nt);
+  for (auto& t : th) t.join();
+  out.base_off[n] = (int64_t)(n * (size_t)L);
+  return out;
+}
 
 // ---- DenovoCaller (M/DenovoCaller.java:24-78) ----------------------------------------------
 class DenovoCaller {
@@ -393,17 +562,37 @@ class GpuReadCaller : public DenovoCaller {
     const int64_t n = (int64_t)sites.size();
     if (n > 0) {
       dnv_ctx* ctx = shared_.engine();
-      // synthetic pileup source in place of reads.search x3 (M/ReadCaller.java:155-186)
       const auto thr = poisson_thresholds(shared_.cmd.syntheticDepth);
       const uint32_t err_thr = (uint32_t)(shared_.cmd.sequenceErrorRate * 4294967296.0);
-      std::vector<uint16_t> counts((size_t)n * 12);
-      if (dnv_synth_counts_at(ctx, shared_.cmd.syntheticSeed, index.data(), n, thr.data(), (int32_t)thr.size(), err_thr,
-                              counts.data()) != DNV_OK)
-        throw std::runtime_error(std::string("synthetic pileup source: ") + dnv_last_error());
-      std::vector<dnv_call> calls((size_t)n);
+      Pinned<uint16_t> counts((size_t)n * 12);
+      if (shared_.cmd.syntheticSource == "counts") {
+        // pileup counts straight from the generator (no reads)
+        if (dnv_synth_counts_at(ctx, shared_.cmd.syntheticSeed, index.data(), n, thr.data(), (int32_t)thr.size(), err_thr,
+                                counts.data()) != DNV_OK)
+          throw std::runtime_error(std::string("synthetic pileup source: ") + dnv_last_error());
+      } else {
+        // getReadMap + getReadSummaryMap (M/ReadCaller.java:113-116,138-186): the reads at every candidate, then
+        // `new ReadSummary(reads, position)` x3 for ALL candidates in one dnv_pileup call.  The pileup wants its
+        // positions ascending: candidates are looked up through their sorted, de-duplicated positions.
+        std::vector<int64_t> uniq(index);
+        std::sort(uniq.begin(), uniq.end());
+        uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+        const SyntheticReads reads = synthetic_reads_at(shared_.cmd.syntheticSeed, uniq, thr, err_thr,
+                                                        shared_.cmd.syntheticReadLength, (uint32_t)(1e-3 * 4294967296.0));
+        std::vector<uint16_t> ucounts(uniq.size() * 12);
+        if (dnv_pileup(ctx, reads.read_start.data(), reads.base_off.data(), reads.bases.data(), reads.person.data(),
+                       (int64_t)reads.read_start.size(), uniq.data(), (int64_t)uniq.size(), ucounts.data()) != DNV_OK)
+          throw std::runtime_error(std::string("dnv_pileup: ") + dnv_last_error());
+        for (int64_t i = 0; i < n; i++) {
+          const size_t u = (size_t)(std::lower_bound(uniq.begin(), uniq.end(), index[(size_t)i]) - uniq.begin());
+          std::memcpy(counts.data() + (size_t)i * 12, ucounts.data() + u * 12, 12 * sizeof(uint16_t));
+        }
+      }
+      // BayesInfer.infer for every candidate (M/ReadCaller.java:119-120): ONE call, interval-sharded over --devices
+      Pinned<dnv_call> calls((size_t)n);
       int64_t n_calls = 0;
-      if (dnv_infer_counts(ctx, counts.data(), n, nullptr, calls.data(), n, &n_calls) != DNV_OK)
-        throw std::runtime_error(std::string("dnv_infer_counts: ") + dnv_last_error());
+      if (dnv_group_infer_counts(shared_.group(), counts.data(), n, calls.data(), n, &n_calls) != DNV_OK)
+        throw std::runtime_error(std::string("dnv_group_infer_counts: ") + dnv_last_error());
       std::string buf;
       for (int64_t i = 0; i < n_calls; i++) {
         const dnv_call& c = calls[(size_t)i];

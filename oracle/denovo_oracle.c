@@ -283,6 +283,47 @@ int64_t orc_pileup(const int64_t *read_start, const int64_t *base_off,
   return 0;
 }
 
+/* The same rule for reads SORTED by (person, start) — what the product's dnv_pileup takes — with the window of
+ * reads that can reach a position found by binary search instead of a scan over all reads: for big test
+ * inputs.  tests/test_oracle_paths.py checks it against orc_pileup above. */
+int64_t orc_pileup_sorted(const int64_t *read_start, const int64_t *base_off,
+                          const char *bases, const uint8_t *person, int64_t n_reads,
+                          const int64_t *site_pos, int64_t n_sites,
+                          uint16_t *counts_out) {
+  memset(counts_out, 0, (size_t)n_sites * 12 * sizeof(uint16_t));
+  int64_t first[4] = {0, n_reads, n_reads, n_reads}, lmax = 0;
+  for (int64_t r = 0; r < n_reads; r++) {
+    int64_t len = base_off[r + 1] - base_off[r];
+    if (len > lmax) lmax = len;
+    if (person[r] > 2) return -(r + 1);
+    if (r > 0 && (person[r - 1] > person[r] || (person[r - 1] == person[r] && read_start[r - 1] > read_start[r]))) return -(r + 1);
+  }
+  for (int p = 1; p <= 2; p++) {
+    int64_t r = 0;
+    while (r < n_reads && person[r] < p) r++;
+    first[p] = r;
+  }
+  first[3] = n_reads;
+  for (int64_t s = 0; s < n_sites; s++) {
+    int64_t pos = site_pos[s];
+    for (int p = 0; p < 3; p++) {
+      int64_t lo = first[p], hi = first[p + 1];
+      while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (read_start[mid] <= pos - lmax) lo = mid + 1; else hi = mid; }
+      for (int64_t r = lo; r < first[p + 1] && read_start[r] <= pos; r++) {
+        int64_t len = base_off[r + 1] - base_off[r];
+        int64_t off = pos - read_start[r];
+        if (off >= len) continue;
+        char b = bases[base_off[r] + off];
+        if (b == '-') continue;
+        int a = allele_index(b);
+        if (a < 0) return -(r + 1);
+        counts_out[s * 12 + p * 4 + a]++;
+      }
+    }
+  }
+  return 0;
+}
+
 /* ------------------------------------------------------------------ */
 /* VARIANT mode                                                        */
 /* ------------------------------------------------------------------ */

@@ -115,6 +115,12 @@ int64_t orc_pileup(const int64_t *read_start, const int64_t *base_off,
                    const int64_t *site_pos, int64_t n_sites,
                    uint16_t *counts_out);
 
+/* Same rule, reads sorted by (person, start): binary-searched windows (big test inputs). */
+int64_t orc_pileup_sorted(const int64_t *read_start, const int64_t *base_off,
+                          const char *bases, const uint8_t *person, int64_t n_reads,
+                          const int64_t *site_pos, int64_t n_sites,
+                          uint16_t *counts_out);
+
 /* ---- VARIANT mode (M/VariantsBuffer.java + M/VariantCaller.java:120-210) ---- */
 /* Streaming simulation of one shard: admission, trigger, eviction, interval
  * match, genotype decode.  Emits one orc_pcall per child SNP that found both

@@ -32,12 +32,22 @@ def read_line(chrom, pos, counts, dad, mom, child, is_denovo=True):
         "true" if is_denovo else "false")
 
 
-def expected_read_lines(cands, seed, depth=30, eps=1e-2, mu=1e-8, lrt=1.0, method="BAYES", chromosomes=None):
+def expected_read_lines(cands, seed, depth=30, eps=1e-2, mu=1e-8, lrt=1.0, method="BAYES", chromosomes=None,
+                        source="reads", read_len=100):
+    """source="reads" (the CLI's default): the oracle's synthetic reads at the candidates -> oracle pileup
+    (ReadSummary rule) -> oracle inference; source="counts": pileup counts straight from the generator."""
     cands = [(c, p) for c, p in cands if chromosomes is None or c.upper() in chromosomes]
     if not cands:
         return []
     idx = np.array([global_index(c, p) for c, p in cands], np.int64)
-    counts = O.synth_counts_at(seed, idx, depth=depth, seq_err=eps)
+    if source == "counts":
+        counts = O.synth_counts_at(seed, idx, depth=depth, seq_err=eps)
+    else:
+        uniq = np.unique(idx)
+        rs, bo, ba, pe = O.synth_reads_at(seed, uniq, depth=depth, seq_err=eps, read_len=read_len)
+        rc, ucounts = O.pileup_sorted(rs, bo, ba, pe, uniq)
+        assert rc == 0
+        counts = ucounts[np.searchsorted(uniq, idx)]
     ref = O.infer(O.params(eps, mu, lrt), counts)
     field = {"MAP": "denovo_map", "BAYES": "denovo_bayes", "LRT": "denovo_lrt"}[method]
     return [read_line(c, p, counts[i], ref["dad"][i], ref["mom"][i], ref["child"][i])

@@ -48,6 +48,8 @@ def lib():
         _lib.orc_infer.restype = C.c_int
         _lib.orc_pileup.restype = C.c_int64
         _lib.orc_mendel_stream.restype = C.c_int64
+        _lib.orc_pileup_sorted.restype = C.c_int64
+        _lib.synth_ref_reads_at.restype = C.c_int64
     return _lib
 
 
@@ -102,6 +104,35 @@ def pileup(read_start, base_off, bases, person, site_pos):
                           C.c_int64(read_start.shape[0]), _p(site_pos),
                           C.c_int64(site_pos.shape[0]), _p(out))
     return rc, out
+
+
+def pileup_sorted(read_start, base_off, bases, person, site_pos):
+    """orc_pileup for reads sorted by (person, start): binary-searched windows, for big inputs."""
+    read_start = np.ascontiguousarray(read_start, np.int64)
+    base_off = np.ascontiguousarray(base_off, np.int64)
+    bases = np.ascontiguousarray(bases, np.uint8)
+    person = np.ascontiguousarray(person, np.uint8)
+    site_pos = np.ascontiguousarray(site_pos, np.int64)
+    out = np.zeros((site_pos.shape[0], 3, 4), np.uint16)
+    rc = lib().orc_pileup_sorted(_p(read_start), _p(base_off), _p(bases), _p(person), C.c_int64(read_start.shape[0]),
+                                 _p(site_pos), C.c_int64(site_pos.shape[0]), _p(out))
+    return rc, out
+
+
+def synth_reads_at(seed, index, depth=30, seq_err=1e-2, read_len=100, gap_rate=1e-3, thr=None):
+    """Synthetic reads covering the candidate sites `index` (global positions): the specification of the host's
+    read source.  Returns read_start, base_off, bases (uint8 ASCII), person, sorted by (person, start)."""
+    if thr is None:
+        thr = poisson_thresholds(depth)
+    index = np.ascontiguousarray(index, np.int64)
+    err_thr, gap_thr = int(seq_err * (1 << 32)), int(gap_rate * (1 << 32))
+    args = (C.c_uint64(seed), _p(index), C.c_int64(index.shape[0]), _p(thr), C.c_int32(thr.shape[0]), C.c_uint32(err_thr),
+            C.c_int32(read_len), C.c_uint32(gap_thr))
+    n = lib().synth_ref_reads_at(*args, None, None, None, None)
+    rs, bo = np.zeros(n, np.int64), np.zeros(n + 1, np.int64)
+    ba, pe = np.zeros(n * read_len, np.uint8), np.zeros(n, np.uint8)
+    lib().synth_ref_reads_at(*args, _p(rs), _p(bo), _p(ba), _p(pe))
+    return rs, bo, ba, pe
 
 
 def mendel_stream(calls):

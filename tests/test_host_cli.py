@@ -68,20 +68,30 @@ def test_fails_loudly_without_gpu(tmp_path):
 
 
 def candidates(n, seed=0):
+    """Candidate sites, some of them closer together than a read is long (their synthetic reads then contribute to
+    each other's pileups, as real reads would), one of them listed twice."""
     rng = np.random.default_rng(seed)
     chroms = ["chr1", "chr2", "chrX", "CHR7", "chr21"]
-    return [(chroms[int(rng.integers(0, len(chroms)))], int(rng.integers(1, 40_000_000))) for _ in range(n)]
+    out = [(chroms[int(rng.integers(0, len(chroms)))], int(rng.integers(200, 40_000_000))) for _ in range(n)]
+    for k in range(0, n - 1, 97):
+        out[k + 1] = (out[k][0], out[k][1] + int(rng.integers(1, 60)))
+    out[n // 2] = out[n // 3]
+    return out
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("method", ["bayes", "map", "lrt"])
 def test_read_mode_output_file(tmp_path, method):
-    cands = candidates(30000)
+    """READ mode end to end on its default source: candidate file -> synthetic reads -> dnv_pileup (the pileup kernel)
+    -> interval-sharded inference on two contexts (--devices 0,0) -> output file, line for line against the oracle
+    chain (reads spec -> ReadSummary rule -> performInference -> format strings)."""
+    cands = candidates(12000)
     cand = tmp_path / "cands.csv"
     cand.write_text("".join("%s,%d,extra,fields\n" % c for c in cands))
     out = tmp_path / "calls.csv"
     r = run(["--caller", "read", "--inference_method", method, "--output_file", str(out), "--input_calls_file",
-             str(cand), "--synthetic_seed", str(0x5EED0001), "--log_level", "info", "--num_threads", "4"] + REQ)
+             str(cand), "--synthetic_seed", str(0x5EED0001), "--log_level", "info", "--num_threads", "4",
+             "--devices", "0,0"] + REQ)
     assert r.returncode == 0, r.stderr
     got = out.read_text().splitlines()
     want = H.expected_read_lines(cands, 0x5EED0001, method=method.upper())
@@ -89,6 +99,30 @@ def test_read_mode_output_file(tmp_path, method):
     assert got == want
     assert "INFO : ---- Starting Bayesian Read Caller ----" in r.stderr
     assert "INFO : 100 Read candidates processed" in r.stderr
+
+
+@pytest.mark.gpu
+def test_read_mode_counts_source_and_short_reads(tmp_path):
+    """--synthetic_source counts (pileup counts straight from the generator) and a 40-base read source."""
+    cands = candidates(20000, seed=9)
+    cand = tmp_path / "cands.csv"
+    cand.write_text("".join("%s,%d\n" % c for c in cands))
+    out = tmp_path / "calls.csv"
+    r = run(["--caller", "read", "--output_file", str(out), "--input_calls_file", str(cand), "--synthetic_source", "counts",
+             "--synthetic_seed", "11"] + REQ)
+    assert r.returncode == 0, r.stderr
+    want = H.expected_read_lines(cands, 11, source="counts")
+    assert out.read_text().splitlines() == want and len(want) > 10
+    r = run(["--caller", "read", "--output_file", str(out), "--input_calls_file", str(cand), "--synthetic_read_length", "40",
+             "--synthetic_seed", "11", "--devices", "0-0"] + REQ)
+    assert r.returncode == 0, r.stderr
+    want = H.expected_read_lines(cands, 11, read_len=40)
+    assert out.read_text().splitlines() == want and len(want) > 10
+
+
+def test_devices_flag_is_validated():
+    r = run(["--caller", "read", "--output_file", "x", "--devices", "3-1"] + REQ)
+    assert r.returncode == 1 and "--devices" in r.stderr
 
 
 @pytest.mark.gpu

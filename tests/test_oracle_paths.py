@@ -73,3 +73,30 @@ def test_pileup_oracle_matches_numpy():
     ba2[bo[5] + 3] = ord("N")
     rc, _ = O.pileup(rs, bo, ba2, pe, np.array([rs[5] + 3]))
     assert rc == -6
+
+
+def test_sorted_pileup_oracle_equals_the_scan_and_read_source_properties():
+    """orc_pileup_sorted (binary-searched windows, for big inputs) == orc_pileup (the plain ReadSummary scan), on the
+    synthetic read source; an isolated candidate's pileup equals the counts generator's, reads are sorted by
+    (person, start) and every read covers its site."""
+    import numpy as np
+    import oracle_lib as O
+    import synth_inputs as S
+    idx = np.unique(np.concatenate([np.random.default_rng(5).integers(10_000, 50_000_000, 300),
+                                    np.array([777, 800, 801, 850, 10**9, 10**9 + 99])])).astype(np.int64)
+    rs, bo, ba, pe = O.synth_reads_at(0x5EED0001, idx, depth=30, read_len=100)
+    assert np.all(np.diff(pe.astype(int)) >= 0) and all(np.all(np.diff(rs[pe == p]) >= 0) for p in range(3))
+    assert set(np.unique(ba)) <= set(b"ACGT-") and (ba == ord("-")).mean() < 5e-3
+    rc1, c1 = O.pileup(rs, bo, ba, pe, idx)
+    rc2, c2 = O.pileup_sorted(rs, bo, ba, pe, idx)
+    assert rc1 == 0 and rc2 == 0 and np.array_equal(c1, c2)
+    counts = O.synth_counts_at(0x5EED0001, idx, depth=30)
+    near = np.zeros(len(idx), bool)
+    near[1:] |= np.diff(idx) < 100
+    near[:-1] |= np.diff(idx) < 100
+    assert np.array_equal(c1[~near], counts[~near]) and near.sum() >= 5
+    assert np.all(c1.astype(int).sum(axis=2) >= counts.astype(int).sum(axis=2) - 0)   # neighbours only add reads
+    # variable-length reads, unsorted sites
+    rs, bo, ba, pe = S.make_reads(3, 100, 3000, depth=20, var_len=True)
+    pos = np.random.default_rng(1).permutation(np.arange(50, 3200)).astype(np.int64)
+    assert np.array_equal(O.pileup(rs, bo, ba, pe, pos)[1], O.pileup_sorted(rs, bo, ba, pe, pos)[1])
