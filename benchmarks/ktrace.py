@@ -24,15 +24,24 @@ h = torch.zeros(4, dtype=torch.int64).pin_memory()
 ROUNDS = 4  # the first rounds warm up (allocations, graph capture)
 MODE = sys.argv[3] if len(sys.argv) > 3 else "async"
 import time
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+st = torch.cuda.Stream()
+eng.set_stream(st.cuda_stream)
 for rep in range(ROUNDS):
+    torch.cuda.synchronize()
+    e0.record(st)
     t0 = time.perf_counter()
     for i in range(K):
         if MODE == "sync":   # one synchronous call per batch: chunks over the lanes, graph replay
             eng.infer_device(counts, n, calls[0], cap)
         else:
             eng.infer_device_async(counts, n, calls[i % 4], cap, h[i % 4:i % 4 + 1])
+    t1 = time.perf_counter()
+    eng.flush()
+    e1.record(st)
     eng.sync()
-    print("round %d: %.1f us per batch (host clock)" % (rep, (time.perf_counter() - t0) / K * 1e6))
+    print("round %d: %.1f us per batch (host clock), host enqueue %.1f us per batch, CUDA events %.1f us per batch"
+          % (rep, (time.perf_counter() - t0) / K * 1e6, (t1 - t0) / K * 1e6, e0.elapsed_time(e1) * 1e3 / K))
 if MODE == "sync":
     K *= 3
 SLOTS = 1024
@@ -53,4 +62,5 @@ print("batch lane  screen[start end]   list[start end]   finish[start end]")
 for i, r in enumerate(rows):
     v = [(x - t0) / 1e3 for x in r[1:]]
     print("%3d  %3d  %7.1f %7.1f   %7.1f %7.1f   %7.1f %7.1f" % (i, r[0], *v))
-print("steady step: %.1f us" % ((rows[-1][2] - rows[2][2]) / 1e3 / (K - 3)))
+print("steady step: %.1f us; first screen start -> last finish end: %.1f us = %.1f us per batch" % (
+    (rows[-1][2] - rows[2][2]) / 1e3 / (K - 3), (max(r[6] for r in rows) - t0) / 1e3, (max(r[6] for r in rows) - t0) / 1e3 / K))

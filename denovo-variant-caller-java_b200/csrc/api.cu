@@ -341,6 +341,11 @@ int dnv_create(const dnv_params* p, dnv_ctx** out) {
     set_error("dnv_create: seq_err_rate and denovo_mut_rate must lie in (0,1), method in {0,1,2}");
     return DNV_E_INVALID;
   }
+  // One hardware work queue per stream of a context (front, copy, and a screen + a tail stream per lane): with
+  // the default of 8 connections, streams that share a queue serialise against each other (measured: the list
+  // kernel of one lane waits for the screen of the next).  Only effective if CUDA has not been initialised yet in
+  // this process; a host that initialises CUDA first sets the variable itself (bench.py does).
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) {

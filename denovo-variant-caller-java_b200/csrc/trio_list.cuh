@@ -454,6 +454,8 @@ trio_calls_finish_kernel(const Tables* __restrict__ tab, const FastConsts k, con
 // tail CTAs (four 128-register warps, one per sub-partition) that fit on an SM beside the resident screen CTAs:
 // (16384 - screen warps per sub-partition * 32 * 64) / (32 * 128)
 inline int tail_ctas_beside_screen() {
+  static const int forced = [] { const char* e = getenv("DNV_TAIL_GRID"); return e ? atoi(e) : 0; }();  // A/B knob
+  if (forced >= 1 && forced <= 8) return forced;
   const int screen_warps = screen_config().per_sm * kScreenWarps / 4;
   return std::max(1, (16384 - screen_warps * 2048) / 4096);
 }

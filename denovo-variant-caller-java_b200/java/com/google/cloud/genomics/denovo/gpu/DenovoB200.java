@@ -5,7 +5,8 @@
  * here.  It is the binding a maintainer of alenzhao/denovo-variant-caller-java adds next to
  * DenovoCaller; the tested host is the C++ CLI (../../../../../../../host) over the same ABI.
  *
- * One downcall handle per exported entry point; struct layouts mirror the header byte for byte
+ * One downcall handle per entry point the caller plugins use (the context is a dnv_group: one dnv_ctx per
+ * device, the first one also serves dnv_pileup / dnv_mendel_filter); struct layouts mirror the header byte for byte
  * (dnv_params 40 B, dnv_call 80 B, dnv_site_result 48 B, dnv_vcall 32 B, dnv_pcall 24 B).
  */
 package com.google.cloud.genomics.denovo.gpu;
@@ -62,7 +63,9 @@ public final class DenovoB200 implements AutoCloseable {
   private final Arena libArena = Arena.ofShared();
   private final SymbolLookup lib;
   private final MethodHandle create, destroy, lastError, inferCounts, inferCounts8, pileup, mendelFilter, synthCountsAt;
-  private MemorySegment ctx = MemorySegment.NULL;
+  private final MethodHandle groupCreate, groupDestroy, groupInferCounts, groupInferCounts8, groupCtx, allocPinned, freePinned;
+  private MemorySegment ctx = MemorySegment.NULL;    // dnv_ctx of the first device (pileup, Mendelian filter)
+  private MemorySegment group = MemorySegment.NULL;  // dnv_group over all devices (READ-mode inference), owns ctx
 
   private MethodHandle handle(String name, FunctionDescriptor fd) {
     return LINKER.downcallHandle(lib.find(name).orElseThrow(
@@ -75,7 +78,26 @@ public final class DenovoB200 implements AutoCloseable {
    */
   public DenovoB200(String libraryPath, double seqErrRate, double denovoMutRate, double lrtThreshold,
       int method, int device) {
+    this(libraryPath, seqErrRate, denovoMutRate, lrtThreshold, method, new int[] {device});
+  }
+
+  /**
+   * Several devices driven by this one JVM (dnv_group): READ-mode batches are split by genomic interval over
+   * them and the call records come back gathered in input order — the batching and result-gather layer of the
+   * Java host is two downcalls.
+   */
+  public DenovoB200(String libraryPath, double seqErrRate, double denovoMutRate, double lrtThreshold,
+      int method, int[] devices) {
     lib = SymbolLookup.libraryLookup(libraryPath, libArena);
+    groupCreate = handle("dnv_group_create", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS));
+    groupDestroy = handle("dnv_group_destroy", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    groupInferCounts = handle("dnv_group_infer_counts", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG,
+        ADDRESS, JAVA_LONG, ADDRESS));
+    groupInferCounts8 = handle("dnv_group_infer_counts8", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG,
+        ADDRESS, JAVA_LONG, ADDRESS));
+    groupCtx = handle("dnv_group_ctx", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS));
+    allocPinned = handle("dnv_alloc_pinned", FunctionDescriptor.of(JAVA_INT, JAVA_LONG, ADDRESS));
+    freePinned = handle("dnv_free_pinned", FunctionDescriptor.of(JAVA_INT, ADDRESS));
     create = handle("dnv_create", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
     destroy = handle("dnv_destroy", FunctionDescriptor.of(JAVA_INT, ADDRESS));
     lastError = handle("dnv_last_error", FunctionDescriptor.of(ADDRESS));
@@ -95,10 +117,14 @@ public final class DenovoB200 implements AutoCloseable {
       p.set(JAVA_DOUBLE, 8, denovoMutRate);
       p.set(JAVA_DOUBLE, 16, lrtThreshold);
       p.set(JAVA_INT, 24, method);
-      p.set(JAVA_INT, 28, device);
+      p.set(JAVA_INT, 28, devices[0]);
       p.set(JAVA_INT, 32, 0);
+      MemorySegment dev = a.allocate((long) devices.length * 4, 4);
+      for (int i = 0; i < devices.length; i++) dev.setAtIndex(JAVA_INT, i, devices[i]);
       MemorySegment out = a.allocate(ADDRESS);
-      check((int) create.invoke(p, out));
+      check((int) groupCreate.invoke(p, dev, devices.length, out));
+      group = out.get(ADDRESS, 0);
+      check((int) groupCtx.invoke(group, 0, out)); // borrowed: the group owns its contexts
       ctx = out.get(ADDRESS, 0);
     } catch (RuntimeException e) {
       throw e;
@@ -150,6 +176,44 @@ public final class DenovoB200 implements AutoCloseable {
     }
   }
 
+  /**
+   * inferCounts over all devices of the group: counts are split by interval (one host thread per device inside the
+   * library), every device infers its shard, the records are gathered through the first device and returned in
+   * input order.  Pass buffers from allocPinned so that the devices copy concurrently at the PCIe rate.
+   */
+  public long groupInferCounts(MemorySegment counts, long n, MemorySegment calls, long cap) {
+    try (Arena a = Arena.ofConfined()) {
+      MemorySegment nCalls = a.allocate(JAVA_LONG);
+      check((int) groupInferCounts.invoke(group, counts, n, calls, cap, nCalls));
+      return nCalls.get(JAVA_LONG, 0);
+    } catch (RuntimeException e) {
+      throw e;
+    } catch (Throwable t) {
+      throw new IllegalStateException(t);
+    }
+  }
+
+  /** Page-locked host memory (dnv_alloc_pinned); release with freePinned. */
+  public MemorySegment allocPinned(long bytes) {
+    try (Arena a = Arena.ofConfined()) {
+      MemorySegment out = a.allocate(ADDRESS);
+      check((int) allocPinned.invoke(bytes, out));
+      return out.get(ADDRESS, 0).reinterpret(bytes);
+    } catch (RuntimeException e) {
+      throw e;
+    } catch (Throwable t) {
+      throw new IllegalStateException(t);
+    }
+  }
+
+  public void freePinned(MemorySegment p) {
+    try {
+      freePinned.invoke(p);
+    } catch (Throwable ignored) {
+      // nothing useful to do
+    }
+  }
+
   /** Batched new ReadSummary(reads, position) x3 (ReadSummary.java:45-59). */
   public void pileup(MemorySegment readStart, MemorySegment baseOff, MemorySegment bases, MemorySegment person,
       long nReads, MemorySegment sitePos, long nSites, MemorySegment countsOut) {
@@ -190,11 +254,12 @@ public final class DenovoB200 implements AutoCloseable {
   @Override
   public void close() {
     try {
-      if (!ctx.equals(MemorySegment.NULL)) destroy.invoke(ctx);
+      if (!group.equals(MemorySegment.NULL)) groupDestroy.invoke(group); // destroys its contexts
     } catch (Throwable ignored) {
       // nothing useful to do at shutdown
     }
     ctx = MemorySegment.NULL;
+    group = MemorySegment.NULL;
     libArena.close();
   }
 }

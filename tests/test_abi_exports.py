@@ -65,3 +65,27 @@ def test_fails_loudly_without_gpu():
         D.TrioEngine()
     assert ei.value.code == D.DNV_E_CUDA
     assert "no CPU fallback" in str(ei.value)
+
+
+def test_java_binding_only_names_exported_symbols_and_matching_offsets():
+    """The Java (Panama FFM) sources cannot be compiled here (no JDK): at least every downcall they name must be
+    an exported, declared entry point, and the byte offsets they hard-code must be the header's."""
+    jdir = os.path.join(ROOT, "denovo-variant-caller-java_b200", "java")
+    names, srcs = set(), {}
+    for dp, _, fs in os.walk(jdir):
+        for f in fs:
+            if f.endswith(".java"):
+                txt = open(os.path.join(dp, f)).read()
+                srcs[f] = txt
+                names |= set(re.findall(r'handle\("(dnv_[a-z0-9_]+)"', txt))
+    assert {"dnv_group_create", "dnv_group_infer_counts", "dnv_pileup", "dnv_mendel_filter", "dnv_alloc_pinned"} <= names
+    declared = set(header_functions())
+    assert names <= declared, names - declared
+    c, p, v = D.CALL_DT.fields, D.PCALL_DT.fields, D.VCALL_DT.fields
+    assert (c["site"][1], c["counts"][1], c["dad"][1], c["mom"][1], c["child"][1]) == (0, 8, 32, 33, 34)   # GpuReadCaller.details
+    assert (p["position"][1], p["child"][1], p["mom"][1], p["dad"][1], p["is_denovo"][1]) == (0, 16, 17, 18, 19)  # callShard
+    assert (v["start"][1], v["end"][1], v["variant_id"][1], v["gt0"][1], v["gt1"][1], v["ngt"][1], v["person"][1],
+            v["filter_pass"][1], v["ref_len"][1], v["ref_base"][1], v["alt0_len"][1], v["alt0_base"][1],
+            v["alt1_len"][1], v["alt1_base"][1]) == (0, 8, 16, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30)    # pack()
+    assert "extends DenovoCaller" in srcs["GpuReadCaller.java"] and "extends DenovoCaller" in srcs["GpuVariantCaller.java"]
+    assert "public void execute()" in srcs["GpuVariantCaller.java"]
