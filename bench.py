@@ -365,7 +365,7 @@ def genome_walk(D, torch, np, dist, eng, stream, gather, rank, world, local, chu
     infer_ms = gen_ms = 0.0
     n_calls = 0
     per_gen = []
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     k = 0
     with torch.cuda.stream(stream):
         for first in range(lo, hi, chunk):
@@ -374,6 +374,12 @@ def genome_walk(D, torch, np, dist, eng, stream, gather, rank, world, local, chu
             evs[0].record(stream)
             eng.synth_counts_device(seed, first, m, bufs[b], depth=DEPTH)
             evs[1].record(stream)
+            if gather is not None:
+                # every rank has generated its chunk before any rank starts the timed inference: rank 0's wait then
+                # measures the gather, not the other ranks' generators
+                torch.cuda.synchronize()
+                dist.barrier()
+            evs[3].record(stream)
             if gather is None:
                 eng.infer_device_async(bufs[b], m, calls[b], cap, h.data_ptr() + 8 * b, site_base=first)
                 eng.flush()
@@ -393,7 +399,7 @@ def genome_walk(D, torch, np, dist, eng, stream, gather, rank, world, local, chu
             else:
                 n_calls += int(h[b])
             gen_ms += evs[0].elapsed_time(evs[1])
-            infer_ms += evs[1].elapsed_time(evs[2])
+            infer_ms += evs[3].elapsed_time(evs[2])
             k += 1
     return {"sites": hi - lo, "infer_ms": infer_ms, "gen_ms": gen_ms, "calls": n_calls, "chunks": k}
 
