@@ -27,7 +27,7 @@ SITES_PER_GPU = 10_000_000
 SEED = 0x5EED0003
 DEPTH, EPS, MU, LRT = 30, 1e-2, 1e-8, 1.0
 GROUP = 64  # asynchronous steps per host synchronisation (and per gather round)
-NBUF = 4    # distinct input buffers (distinct shards of the axis) the steps cycle through; also gather generations
+NBUF = int(os.environ.get('BENCH_NBUF', '4'))    # distinct input buffers (distinct shards of the axis) the steps cycle through; also gather generations
 # ALGORITHMIC work per site:
 #   integer screen (dominant kernel, HBM-bound): 24 B of counts in + 1 bit of decision out
 #   list kernel (only the sites the screen cannot decide): sparse factored FP64 form, FMA = 2
@@ -72,15 +72,20 @@ class ClockSampler:
             self.err = repr(e)
 
     def _loop(self):
+        # NVML queries go through the same kernel driver as the launches of the timed loop and were measured to
+        # stall them (a 20-step region ran 15 % slower with a query every 0.5 ms): the first sample is taken 0.4 ms
+        # into the region, the following ones every 4 ms — a 20-step region (1.2 ms) sees one, longer ones several
         nv = self.nv
+        time.sleep(0.0004)
         while not self.stop_flag:
             try:
                 self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 self.reasons |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                if len(self.sm) % 4 == 1:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
             except Exception:  # noqa: BLE001
                 break
-            time.sleep(0.0005)
+            time.sleep(0.004)
 
     def start(self):
         if self.ok:
@@ -515,7 +520,7 @@ def main():
     finish(run_steps(max(W, 2 * NBUF)))  # scratch of every lane is allocated on its first batch: all of them warm up
     sampler = ClockSampler(local)
     barrier()
-    if rank == 0:
+    if rank == 0 and not os.environ.get('BENCH_NO_SAMPLER'):
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -524,7 +529,7 @@ def main():
     acc = finish(acc)
     barrier()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = (sampler.stop() if not os.environ.get('BENCH_NO_SAMPLER') else None) if rank == 0 else None
     launches = acc["n_launches"]
     screened_out = acc["n_screened_out"] // K
     n_hard = acc["n_hard"] // K

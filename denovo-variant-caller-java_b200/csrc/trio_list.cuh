@@ -48,9 +48,29 @@ constexpr int kFinishThreads = 128;
 constexpr int kFinishWarps = kFinishThreads / 32;
 constexpr int kTailCtasPerSm = 4;  // launch bound of both tail kernels: 128 registers per thread
 
+// A/B switches (benchmarks/gpu/ab.sh builds the variants): staged power tables, raw sums finished by the finish
+// kernel, programmatic dependent launch of the finish kernel
+#ifndef DNV_LIST_SMEM_POW
+#define DNV_LIST_SMEM_POW 1
+#endif
+#ifndef DNV_RAW_SUMS
+#define DNV_RAW_SUMS 1
+#endif
+#ifndef DNV_FINISH_PDL
+#define DNV_FINISH_PDL 1
+#endif
+constexpr int kListPow = DNV_LIST_SMEM_POW ? 256 : 0;  // power-table entries staged in shared memory (depths below 256; deeper reads L1 / L2)
+
+// BAYES / LRT: the head of the power tables (the dependent table look-ups of person_linear then cost a shared-memory
+// round trip instead of an L2 one: beside the screen the SM's L1 is almost all carved out as shared memory); the
+// exact tables stay in global memory (hard sites are rare).  MAP: the exact tables, no power tables.
+template <bool kMap>
 struct ListShared {
-  double rel[1000];               // exact path: getRelationshipLogLikelihood
-  double rmax[110];               // exact MAP pruning bounds
+  double rel[kMap ? 1000 : 2];    // MAP: getRelationshipLogLikelihood (the decision sweep reads it for every site)
+  double rmax[kMap ? 110 : 2];    // MAP: exact pruning bounds
+  double pw_inv[kMap ? 1 : 2][(kMap || !kListPow) ? 2 : kListPow];
+  double pw_m[kMap ? 1 : 2][(kMap || !kListPow) ? 2 : kListPow];
+  int32_t pw_e[kMap ? 1 : 2][(kMap || !kListPow) ? 4 : kListPow];
   double warp_L[kListWarps][32];  // exact path: per-warp read log-likelihoods
   uint32_t isden[32];             // exact path: isDenovoMap
   uint32_t woff[kScreenMaxWarps + 1];  // exclusive scan of wcount[]
@@ -58,6 +78,16 @@ struct ListShared {
   int warp_sum[kListWarps];
   unsigned int ticket[2];  // next tile, handed from thread 0 to the CTA (double buffered by trip parity)
   unsigned long long excl;
+};
+
+// power-table accessor of the list kernel: shared memory below kListPow, global memory (L1 / L2) above
+template <bool kMap>
+struct ListPow {
+  const ListShared<kMap>& s;
+  const Tables* t;
+  __device__ __forceinline__ double inv(int j, int i) const { return i < kListPow ? s.pw_inv[j][i] : __ldg(&t->pw_inv[j][i]); }
+  __device__ __forceinline__ double mant(int j, int i) const { return i < kListPow ? s.pw_m[j][i] : __ldg(&t->pw_m[j][i]); }
+  __device__ __forceinline__ int expo(int j, int i) const { return i < kListPow ? s.pw_e[j][i] : __ldg(&t->pw_e[j][i]); }
 };
 
 // ch (CallChain, dnv_internal.cuh): *before = calls of this batch before this chunk, *after <- calls up to and
@@ -73,7 +103,7 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
                  uint32_t n_warps, uint32_t range_base, uint32_t range_rem, unsigned long long* status,
                  const CallChain ch, int64_t cap, dnv_call* __restrict__ stage) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  ListShared& s = *reinterpret_cast<ListShared*>(smem_raw);
+  ListShared<kMap>& s = *reinterpret_cast<ListShared<kMap>*>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int kBps = kU8 ? 12 : 24;
 #ifdef DNV_LIST_TRACE
@@ -98,19 +128,44 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
     const uint32_t j = i * kListThreads + threadIdx.x;
     wv[i] = j < n_warps ? __ldg(wcount + j) : 0u;
   }
-  constexpr int kRelLoads = (500 + kListThreads - 1) / kListThreads;  // 500 double2 = rel[1000]
-  constexpr int kRmaxLoads = (110 + kListThreads - 1) / kListThreads;
+  // MAP: rel[1000] as 500 double2 + the pruning bounds; BAYES / LRT: the first kListPow entries of the six power
+  // tables as 16-byte words (2 x kListPow doubles = kListPow double2 per table pair, ints as int4)
+  constexpr int kRelLoads = kMap ? (500 + kListThreads - 1) / kListThreads : 1;
+  constexpr int kRmaxLoads = kMap ? (110 + kListThreads - 1) / kListThreads : 1;
+  constexpr bool kStagePow = !kMap && kListPow > 0;
+  constexpr int kPowD2 = kStagePow ? kListPow / 2 : 1;  // double2 per table row
+  constexpr int kPowE4 = kStagePow ? kListPow / 4 : 1;  // int4 per exponent row
+  constexpr int kPowLoads = kStagePow ? (4 * kPowD2 + kListThreads - 1) / kListThreads : 1;  // inv[0], inv[1], m[0], m[1]
+  constexpr int kPowELoads = kStagePow ? (2 * kPowE4 + kListThreads - 1) / kListThreads : 1;
   double2 relv[kRelLoads];
-#pragma unroll
-  for (int i = 0; i < kRelLoads; i++) {
-    const int j = threadIdx.x + i * kListThreads;
-    relv[i] = j < 500 ? __ldg(reinterpret_cast<const double2*>(tab->rel) + j) : make_double2(0.0, 0.0);
-  }
   double rmaxv[kRmaxLoads];
+  double2 powv[kPowLoads];
+  int4 powe[kPowELoads];
+  if (kMap) {
 #pragma unroll
-  for (int i = 0; i < kRmaxLoads; i++) {
-    const int j = threadIdx.x + i * kListThreads;
-    rmaxv[i] = j < 110 ? (j < 100 ? tab->rmax_dm[j] : tab->rmax_d[j - 100]) : 0.0;
+    for (int i = 0; i < kRelLoads; i++) {
+      const int j = threadIdx.x + i * kListThreads;
+      relv[i] = j < 500 ? __ldg(reinterpret_cast<const double2*>(tab->rel) + j) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int i = 0; i < kRmaxLoads; i++) {
+      const int j = threadIdx.x + i * kListThreads;
+      rmaxv[i] = j < 110 ? (j < 100 ? tab->rmax_dm[j] : tab->rmax_d[j - 100]) : 0.0;
+    }
+  } else if (kStagePow) {
+#pragma unroll
+    for (int i = 0; i < kPowLoads; i++) {
+      const int j = threadIdx.x + i * kListThreads;  // row = j / kPowD2: inv[0], inv[1], m[0], m[1]
+      const int row = j / kPowD2, col = j % kPowD2;
+      const double* src = row < 2 ? tab->pw_inv[row] : tab->pw_m[row & 1];
+      powv[i] = row < 4 ? __ldg(reinterpret_cast<const double2*>(src) + col) : make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int i = 0; i < kPowELoads; i++) {
+      const int j = threadIdx.x + i * kListThreads;
+      const int row = j / kPowE4, col = j % kPowE4;
+      powe[i] = row < 2 ? __ldg(reinterpret_cast<const int4*>(tab->pw_e[row]) + col) : make_int4(0, 0, 0, 0);
+    }
   }
   const uint32_t isdenv = threadIdx.x < 32 ? tab->isden[threadIdx.x] : 0u;
 #pragma unroll
@@ -118,15 +173,30 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
     const uint32_t j = i * kListThreads + threadIdx.x;
     if (j < n_warps) s.woff[j] = wv[i];
   }
+  if (kMap) {
 #pragma unroll
-  for (int i = 0; i < kRelLoads; i++) {
-    const int j = threadIdx.x + i * kListThreads;
-    if (j < 500) reinterpret_cast<double2*>(s.rel)[j] = relv[i];
-  }
+    for (int i = 0; i < kRelLoads; i++) {
+      const int j = threadIdx.x + i * kListThreads;
+      if (j < 500) reinterpret_cast<double2*>(s.rel)[j] = relv[i];
+    }
 #pragma unroll
-  for (int i = 0; i < kRmaxLoads; i++) {
-    const int j = threadIdx.x + i * kListThreads;
-    if (j < 110) s.rmax[j] = rmaxv[i];
+    for (int i = 0; i < kRmaxLoads; i++) {
+      const int j = threadIdx.x + i * kListThreads;
+      if (j < 110) s.rmax[j] = rmaxv[i];
+    }
+  } else if (kStagePow) {
+#pragma unroll
+    for (int i = 0; i < kPowLoads; i++) {
+      const int j = threadIdx.x + i * kListThreads;
+      const int row = j / kPowD2, col = j % kPowD2;
+      if (row < 4) reinterpret_cast<double2*>(row < 2 ? s.pw_inv[row] : s.pw_m[row & 1])[col] = powv[i];
+    }
+#pragma unroll
+    for (int i = 0; i < kPowELoads; i++) {
+      const int j = threadIdx.x + i * kListThreads;
+      const int row = j / kPowE4, col = j % kPowE4;
+      if (row < 2) reinterpret_cast<int4*>(s.pw_e[row])[col] = powe[i];
+    }
   }
   if (threadIdx.x < 32) s.isden[threadIdx.x] = isdenv;
   __syncthreads();
@@ -171,7 +241,7 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
       if (ch.last) atomicAdd(&ch.acc[0], calls_before);
     }
   }
-  const GmemPow pw{tab};
+  const ListPow<kMap> pw{s, tab};
   stamp(1);
 
   // Tiles are handed out by ticket, in increasing order, to CTAs that are running: the look-back below
@@ -247,7 +317,7 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
 #pragma unroll
           for (int q = 0; q < 12; q++) cu[q] = (uint16_t)__shfl_sync(0xffffffffu, c[q], h);
           ExactOut r;
-          exact_site_warp(cu, s.rel, s.isden, s.warp_L[warp], k.hm, k.ht, k.mm, k.method, k.lrt_threshold, &r);
+          exact_site_warp(cu, kMap ? s.rel : tab->rel, s.isden, s.warp_L[warp], k.hm, k.ht, k.mm, k.method, k.lrt_threshold, &r);
           if (lane == h) { ex = r; dn = r.is_denovo; }
         }
       }
@@ -317,11 +387,16 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
           o.dad = (uint8_t)ex.dad; o.mom = (uint8_t)ex.mom; o.child = (uint8_t)ex.child;
           o.max_ll = ex.max_ll; o.p = ex.p; o.lr = ex.lr; o.log_men = ex.log_men; o.log_den = ex.log_den;
           o.flags = 1;
-        } else {  // phase 2 fills in the MAP triple and max_ll
+        } else {  // the finish kernel fills in the MAP triple and max_ll, and turns the raw sums into p / LR / logs
           o.dad = o.mom = o.child = 0;
           o.max_ll = 0.0;
+#if DNV_RAW_SUMS
+          o.p = lo_.den_s; o.lr = lo_.men_s; o.log_men = lo_.s2; o.log_den = 0.0;
+          o.flags = 2u | ((uint32_t)lo_.zd << 8) | ((uint32_t)lo_.zm << 12);
+#else
           linear_values(lo_, o.p, o.lr, o.log_men, o.log_den);
           o.flags = 0;
+#endif
         }
         o.site = site_base + (int64_t)site;
 #pragma unroll
@@ -369,15 +444,19 @@ template <bool kMap>
 __global__ void __launch_bounds__(kFinishThreads, kTailCtasPerSm)
 trio_calls_finish_kernel(const Tables* __restrict__ tab, const FastConsts k, const CallChain ch,
                          const dnv_call* __restrict__ stage, dnv_call* __restrict__ calls, int64_t cap) {
+  // Launched with programmatic stream serialisation: the CTAs of this kernel are scheduled while the list kernel's
+  // last CTAs are still running, stage the site-invariant tables, and only then wait for the list kernel's results
+  // (griddepcontrol.wait) — the launch gap and the prologue disappear from the tail's critical path.
+  __shared__ FinishShared s;
+  stage_exact_tables(tab, s.rel, s.isden);
+  stage_map_bounds(tab, s.rmax);
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (threadIdx.x == 0) ktrace_stamp(ch.ktrace, ch.ktrace_seq, 2, false);
   const unsigned long long calls_before = ch.pair[0];  // written by the list kernel of this chunk
   unsigned long long all = ch.pair[1];
   if (all > (unsigned long long)cap) all = (unsigned long long)cap;
-  if (calls_before + (unsigned long long)blockIdx.x * kFinishThreads >= all) return;  // block-uniform: no call for this CTA
-  __shared__ FinishShared s;
-  stage_exact_tables(tab, s.rel, s.isden);
-  stage_map_bounds(tab, s.rmax);
   __syncthreads();
+  if (calls_before + (unsigned long long)blockIdx.x * kFinishThreads >= all) return;  // block-uniform: no call for this CTA
   const GmemPow pw{tab};
   (void)pw;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -423,6 +502,14 @@ trio_calls_finish_kernel(const Tables* __restrict__ tab, const FastConsts k, con
           linear_values(lv, u.r.p, u.r.lr, u.r.log_men, u.r.log_den);
         }
       } else if (!(u.r.flags & 1u)) {  // hard sites are complete already
+        if (u.r.flags & 2u) {  // raw sums of the list kernel -> p, LR, log-likelihoods (log and divisions run here, one dense thread per call)
+          LinOut lv;
+          lv.den_s = u.r.p; lv.men_s = u.r.lr; lv.s2 = u.r.log_men;
+          lv.zd = (int)((u.r.flags >> 8) & 3u); lv.zm = (int)((u.r.flags >> 12) & 3u);
+          lv.dn = true; lv.hard = false;
+          linear_values(lv, u.r.p, u.r.lr, u.r.log_men, u.r.log_den);
+          u.r.flags = 0;
+        }
         double Ld[10], Lm[10], Lc[10];
         exact_read_loglik(u.r.counts + 0, k.hm, k.ht, k.mm, Ld);
         exact_read_loglik(u.r.counts + 4, k.hm, k.ht, k.mm, Lm);
@@ -466,7 +553,7 @@ template <bool kU8, bool kMap>
 static int launch_trio_list(dnv_ctx* ctx, TrioLane& ln, cudaStream_t st, const void* d_counts, int64_t n, int64_t site_base,
                             int screen_grid_size, const CallChain& ch, dnv_call* d_calls, int64_t cap, bool beside_screen) {
   const int sms = ctx->sms;
-  const size_t smem = sizeof(ListShared);
+  const size_t smem = sizeof(ListShared<kMap>);
   auto kern = trio_list_kernel<kU8, kMap>;
   int& per_sm = ctx->list_per_sm[kU8 ? 1 : 0][kMap ? 1 : 0];
   if (per_sm == 0) {  // first launch on this context
@@ -512,8 +599,20 @@ static int launch_trio_list(dnv_ctx* ctx, TrioLane& ln, cudaStream_t st, const v
   // one thread per call; CTAs beyond the number of calls leave at once
   const int fgrid = (int)std::max<int64_t>(1, std::min<int64_t>((need + kFinishThreads - 1) / kFinishThreads,
                                                                 (int64_t)sms * (beside_screen ? tail_ctas_beside_screen() : 4)));
-  if (dbg_skip != 2)
-    trio_calls_finish_kernel<kMap><<<fgrid, kFinishThreads, 0, st>>>(ctx->d_tab, fk, ch, ln.d_list_stage, d_calls, cap);
+  if (dbg_skip != 2) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)fgrid);
+    cfg.blockDim = dim3(kFinishThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = DNV_FINISH_PDL;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const dnv_call* stage_in = ln.d_list_stage;
+    DNV_CUDA(cudaLaunchKernelEx(&cfg, trio_calls_finish_kernel<kMap>, (const Tables*)ctx->d_tab, fk, ch, stage_in, d_calls, cap));
+  }
   DNV_CUDA(cudaGetLastError());
   return DNV_OK;
 }
