@@ -325,8 +325,11 @@ def aux_pileup(D, torch, np, local, n_sites=2_000_000):
         def both():
             eng.pileup_device(d[0], d[1], d[2], d[3], len(rs), d[4], n_sites, d_counts)
             chain["calls"] = eng.infer_device(d_counts, n_sites, d_calls, cap)
+
+        def fused():
+            chain["fused_calls"] = eng.infer_reads_device(d[0], d[1], d[2], d[3], len(rs), d[4], n_sites, d_calls, cap)
         times = []
-        for fn in (pile, both):
+        for fn in (pile, both, fused):
             with torch.cuda.stream(stream):
                 for _ in range(3):
                     fn()
@@ -352,7 +355,9 @@ def aux_pileup(D, torch, np, local, n_sites=2_000_000):
     return {"sites": n_sites, "reads": len(rs), "bases": int(len(ba)), "pileup_ms": times[0], "pileup_sites_per_s": n_sites / times[0] * 1e3,
             "algorithmic_bytes_per_site": alg / n_sites, "algorithmic_GBps": alg / times[0] / 1e6, "frac_of_hbm": alg / times[0] / 1e6 / hbm,
             "bit_exact_vs_oracle_window": bool(rc == 0 and np.array_equal(got[sel], want)),
-            "reads_to_calls_ms": times[1], "reads_to_calls_sites_per_s": n_sites / times[1] * 1e3, "reads_to_calls_calls": int(chain["calls"])}
+            "reads_to_calls_ms": times[1], "reads_to_calls_sites_per_s": n_sites / times[1] * 1e3, "reads_to_calls_calls": int(chain["calls"]),
+            "fused_reads_to_calls_ms": times[2], "fused_reads_to_calls_sites_per_s": n_sites / times[2] * 1e3,
+            "fused_equals_chained": bool(chain["fused_calls"] == chain["calls"])}
 
 
 def genome_walk(D, torch, np, dist, eng, stream, gather, rank, world, local, chunk=1 << 26, seed=0x5EED0004):

@@ -267,6 +267,7 @@ int enqueue_device_batch(dnv_ctx* ctx, const void* d_counts, int bps, int64_t n,
     a.no_sub_wait = no_sub_wait;
     a.wait_ev = nullptr;
     a.count_out = count_out;
+    a.reads = nullptr;
     a.dense_host = nullptr;
     a.done_ev = nullptr;
     const int rc = launch_trio_chunk(ctx, a);
@@ -307,6 +308,7 @@ int enqueue_host_batch(dnv_ctx* ctx, const void* counts, int bps, int64_t n, int
     a.no_sub_wait = false;
     a.wait_ev = ctx->ev_h2d[k];
     a.count_out = count_out;
+    a.reads = nullptr;
     a.dense_host = dense ? dense + off : nullptr;
     a.done_ev = ctx->ev_done[k];
     rc = launch_trio_chunk(ctx, a);
@@ -376,7 +378,7 @@ int dnv_destroy(dnv_ctx* ctx) {
   cudaDeviceSynchronize();
   for (int g = 0; g < kGraphSlots; g++) if (ctx->sync_graphs[g].exec) cudaGraphExecDestroy(ctx->sync_graphs[g].exec);
   cudaFree(ctx->d_tab); cudaFree(ctx->d_bits); cudaFree(ctx->d_cstatus);
-  cudaFree(ctx->d_ktrace); cudaFree(ctx->d_ktrace_seq);
+  cudaFree(ctx->d_ktrace); cudaFree(ctx->d_ktrace_seq); cudaFree(ctx->d_reads_counts);
   cudaFree(ctx->d_call_idx); cudaFree(ctx->d_counters); cudaFree(ctx->d_stage_calls); cudaFree(ctx->d_scratch);
   for (int l = 0; l < kMaxLanes; l++) {
     TrioLane& ln = ctx->lane[l];

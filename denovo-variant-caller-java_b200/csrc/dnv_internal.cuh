@@ -161,6 +161,10 @@ struct dnv_ctx {
   int sms;                  // multiprocessors of the device
   int screen_per_sm[2];     // resident CTAs per SM of trio_screen_kernel<u16 / u8>, 0 = not queried yet
   int list_per_sm[2][2];    // ... of trio_list_kernel<u16 / u8><BAYES-LRT / MAP>
+  int scatter_per_sm;       // ... of pileup_screen_kernel
+  int scatter_plain_per_sm; // ... of pileup_scatter_kernel
+  uint16_t* d_reads_counts; // fused reads -> calls: per-site counts (only the undecided sites' rows are written)
+  int64_t reads_counts_cap;
   // DNV_KTRACE=1: device-side time line, 6 words per chunk (screen, list, finish: first CTA start / last CTA end)
   unsigned long long* d_ktrace;   // [lane][kKtraceSlots][6]
   unsigned int* d_ktrace_seq;     // [lane]
@@ -184,6 +188,12 @@ extern "C" int dnvi_finish_stats(dnv_ctx* ctx, int64_t n_sites);
 namespace dnv {
 constexpr int kCtrAcc = 16, kCtrZero = 23, kCtrWork = 24, kCtrWords = 32;
 
+// reads of a chunk whose sites are given as positions (fused reads -> calls path; device pointers)
+struct ReadsArgs {
+  const int64_t* read_start; const int64_t* base_off; const char* bases; int64_t n_reads;
+  const int64_t* site_pos; long long* meta;  // meta: person offsets, max read length, error word (pileup_prep_kernel)
+};
+
 // one chunk of sites resident in HBM through the READ pipeline (trio.cu)
 struct ChunkArgs {
   const void* d_counts;
@@ -197,6 +207,8 @@ struct ChunkArgs {
   bool tail_alone;         // no other chunk's screen will run beside this chunk's list / finish kernels
   cudaEvent_t wait_ev;     // the chunk's input is ready (null: the context's ev_sub)
   int64_t* count_out;
+  const struct ReadsArgs* reads; // non-null: d_counts is scratch, the counts of the chunk's sites come from these reads through the
+                           // fused pileup-screen kernel (pileup_scatter.cuh) instead of the screen kernel
   dnv_site_result* dense_host;  // host API: where the chunk's dense records go (copied on the chunk's stream), or null
   cudaEvent_t done_ev;     // recorded when the chunk no longer needs its input (staging ring of the host API), or null
 };
@@ -213,6 +225,9 @@ __device__ __forceinline__ void ktrace_stamp(unsigned long long* base, const uns
 constexpr int kWcountWords = 8192;  // >= kScreenMaxWarps (trio_screen.cuh)
 // Enqueues the chunk on the next lane.
 int launch_trio_chunk(dnv_ctx* ctx, const ChunkArgs& a);
+// reads -> counts with the read-major scatter kernel (pileup_scatter.cuh, compiled in trio.cu)
+int launch_pileup_scatter(dnv_ctx* ctx, cudaStream_t st, const int64_t* d_read_start, const int64_t* d_base_off, const char* d_bases,
+                          long long* meta, const int64_t* d_site_pos, int64_t n_sites, int64_t n_reads, uint16_t* d_counts);
 int ensure_scratch(dnv_ctx* ctx, size_t bytes);
 // the pipeline as the entry points see it (api.cu)
 int begin_submit(dnv_ctx* ctx);

@@ -54,6 +54,8 @@ using namespace dnv;
 
 extern "C" {
 
+static int pileup_status(long long* h);
+
 int dnv_pileup_device(dnv_ctx* ctx, const int64_t* d_read_start, const int64_t* d_base_off, const char* d_bases,
                       const uint8_t* d_person, int64_t n_reads, const int64_t* d_site_pos, int64_t n_sites,
                       uint16_t* d_counts_out) {
@@ -79,14 +81,27 @@ int dnv_pileup_device(dnv_ctx* ctx, const int64_t* d_read_start, const int64_t* 
     const int grid = (int)std::min<int64_t>((n_reads + 255) / 256, (int64_t)sms * 8);
     pileup_prep_kernel<<<grid, 256, 0, ctx->stream>>>(d_read_start, d_base_off, d_person, n_reads, meta);
   }
-  // dense tiles: bases staged in shared memory, eight sites per thread (pileup_stage.cuh); sparse tiles:
-  // one site at a time inside the same kernel
-  DNV_CUDA(launch_pileup_stage<8>(ctx->stream, sms, d_read_start, d_base_off, d_bases, meta, d_site_pos, n_sites, n_reads,
-                                  d_counts_out));
+  // dense tiles: position-major gather (pileup_stage.cuh; 6.9 G sites/s at 30x); DNV_PILEUP_KERNEL=scatter selects the
+  // read-major formulation with shared-memory atomics (pileup_scatter.cuh; 6.3 G sites/s — its tile routine is what the
+  // fused reads -> calls kernel builds on); sparse tiles: one site at a time in either
+  static const bool use_stage = [] { const char* e = getenv("DNV_PILEUP_KERNEL"); return !(e && std::string(e) == "scatter"); }();
+  if (use_stage) {
+    DNV_CUDA(launch_pileup_stage<8>(ctx->stream, sms, d_read_start, d_base_off, d_bases, meta, d_site_pos, n_sites, n_reads,
+                                    d_counts_out));
+  } else {
+    const int rc2 = launch_pileup_scatter(ctx, ctx->stream, d_read_start, d_base_off, d_bases, meta, d_site_pos, n_sites, n_reads,
+                                          d_counts_out);
+    if (rc2) return rc2;
+  }
   DNV_CUDA(cudaGetLastError());
   long long h[8];
   DNV_CUDA(cudaMemcpyAsync(h, meta, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
   DNV_CUDA(cudaStreamSynchronize(ctx->stream));
+  return pileup_status(h);
+}
+
+// decodes the error word the pileup kernels leave in meta[5]
+static int pileup_status(long long* h) {
   if (h[5] != 0) {
     const unsigned long long w = (unsigned long long)h[5];
     const int kind = (w & 7) == kPileErrBadBase ? DNV_E_BADBASE : (w & 7) == kPileErrUnsorted ? DNV_E_UNSORTED : DNV_E_INVALID;
@@ -138,6 +153,145 @@ int dnv_pileup(dnv_ctx* ctx, const int64_t* read_start, const int64_t* base_off,
   PL_TRY(cudaStreamSynchronize(ctx->stream));
 #undef PL_TRY
   cudaFree(d_start); cudaFree(d_off); cudaFree(d_bases); cudaFree(d_person); cudaFree(d_pos); cudaFree(d_counts);
+  return rc;
+}
+
+// ---- reads -> calls, fused -------------------------------------------------------------
+// ReadCaller.runBayesDenovoInference for a whole batch of candidate sites (M/ReadCaller.java:111-130):
+// getReadSummaryMap (`new ReadSummary(reads, position)` x3, :138-146) and BayesInfer.infer (:119-120) in ONE pass —
+// the pileup of a tile of positions is accumulated in shared memory, screened there by the exact integer screen, and
+// only the ~1 % undecided sites leave the SM (counts + sorted site list) for the fused FP64 list kernel.
+int dnv_infer_reads_device(dnv_ctx* ctx, const int64_t* d_read_start, const int64_t* d_base_off, const char* d_bases,
+                           const uint8_t* d_person, int64_t n_reads, const int64_t* d_site_pos, int64_t n_sites,
+                           dnv_call* d_calls, int64_t cap, int64_t* n_calls) {
+  if (!ctx || !n_calls || n_reads < 0 || n_sites < 0 || cap < 0 || (n_sites > 0 && !d_site_pos) || (cap > 0 && !d_calls) ||
+      (n_reads > 0 && (!d_read_start || !d_base_off || !d_bases || !d_person))) {
+    set_error("dnv_infer_reads_device: invalid argument");
+    return DNV_E_INVALID;
+  }
+  *n_calls = 0;
+  if (n_sites == 0) return DNV_OK;
+  if ((reinterpret_cast<uintptr_t>(d_read_start) & 7) || (reinterpret_cast<uintptr_t>(d_base_off) & 7) ||
+      (reinterpret_cast<uintptr_t>(d_site_pos) & 7)) {
+    set_error("dnv_infer_reads_device: read_start, base_off and site_pos must be 8-byte aligned");
+    return DNV_E_INVALID;
+  }
+  DNV_CUDA(cudaSetDevice(ctx->device));
+  { const int rc = dnv_sync(ctx); if (rc) return rc; }  // batches of the asynchronous entry points are collected first
+  // the per-site counts: only the rows of undecided sites are ever written (fused path)
+  if (n_sites > ctx->reads_counts_cap) {
+    cudaFree(ctx->d_reads_counts);
+    ctx->d_reads_counts = nullptr;
+    ctx->reads_counts_cap = 0;
+    DNV_CUDA(cudaMalloc(&ctx->d_reads_counts, (size_t)n_sites * 24));
+    ctx->reads_counts_cap = n_sites;
+  }
+  if (!will_screen(ctx, false) || ctx->dense_mode) {
+    // parameters outside the screen's validity, or screen-hostile input: pileup, then the all-sites path
+    int rc = dnv_pileup_device(ctx, d_read_start, d_base_off, d_bases, d_person, n_reads, d_site_pos, n_sites, ctx->d_reads_counts);
+    if (rc) return rc;
+    return dnv_infer_counts_device(ctx, ctx->d_reads_counts, n_sites, nullptr, d_calls, cap, n_calls);
+  }
+  int rc = ensure_scratch(ctx, 64);
+  if (rc) return rc;
+  long long* meta = (long long*)ctx->d_scratch;
+  DNV_CUDA(cudaMemsetAsync(meta, 0, 64, ctx->stream));
+  if (n_reads > 0) {
+    const int grid = (int)std::min<int64_t>((n_reads + 255) / 256, (int64_t)ctx->sms * 8);
+    pileup_prep_kernel<<<grid, 256, 0, ctx->stream>>>(d_read_start, d_base_off, d_person, n_reads, meta);
+  }
+  reset_call_state(ctx);
+  rc = begin_submit(ctx);  // the lanes start after the validation / metadata pass
+  if (rc) return rc;
+  ctx->count_bytes = 24;
+  ReadsArgs ra{d_read_start, d_base_off, d_bases, n_reads, d_site_pos, meta};
+  const int64_t chunk = 1ll << 27;  // a multiple of the fused kernel's tile
+  for (int64_t off = 0; off < n_sites; off += chunk) {
+    ReadsArgs rc_args = ra;
+    rc_args.site_pos = d_site_pos + off;
+    ChunkArgs a;
+    a.d_counts = ctx->d_reads_counts + off * 12;
+    a.site_base = off;
+    a.n = std::min(chunk, n_sites - off);
+    a.d_dense = nullptr;
+    a.d_calls = d_calls;
+    a.cap = cap;
+    a.first = off == 0;
+    a.last = off + chunk >= n_sites;
+    a.no_sub_wait = false;
+    a.tail_alone = a.last;
+    a.wait_ev = nullptr;
+    a.count_out = nullptr;
+    a.reads = &rc_args;
+    a.dense_host = nullptr;
+    a.done_ev = nullptr;
+    rc = launch_trio_chunk(ctx, a);
+    if (rc) return rc;
+  }
+  rc = collect(ctx);
+  if (rc) return rc;
+  dnvi_finish_stats(ctx, n_sites);
+  long long h[8];
+  DNV_CUDA(cudaMemcpyAsync(h, meta, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  DNV_CUDA(cudaStreamSynchronize(ctx->stream));
+  rc = pileup_status(h);
+  if (rc) return rc;
+  *n_calls = ctx->stats.n_calls;
+  if (*n_calls > cap) {
+    set_error("call capacity too small: need " + std::to_string(*n_calls) + ", have " + std::to_string(cap));
+    return DNV_E_CAPACITY;
+  }
+  return DNV_OK;
+}
+
+int dnv_infer_reads(dnv_ctx* ctx, const int64_t* read_start, const int64_t* base_off, const char* bases,
+                    const uint8_t* person, int64_t n_reads, const int64_t* site_pos, int64_t n_sites, dnv_call* calls,
+                    int64_t cap, int64_t* n_calls) {
+  if (!ctx || !n_calls || n_reads < 0 || n_sites < 0 || cap < 0 || (n_sites > 0 && !site_pos) || (cap > 0 && !calls) ||
+      (n_reads > 0 && (!read_start || !base_off || !bases || !person))) {
+    set_error("dnv_infer_reads: invalid argument");
+    return DNV_E_INVALID;
+  }
+  *n_calls = 0;
+  if (n_sites == 0) return DNV_OK;
+  DNV_CUDA(cudaSetDevice(ctx->device));
+  const int64_t n_bases = n_reads > 0 ? base_off[n_reads] : 0;
+  const int64_t dev_cap = std::min(cap, n_sites);
+  int64_t *d_start = nullptr, *d_off = nullptr, *d_pos = nullptr;
+  char* d_bases = nullptr;
+  uint8_t* d_person = nullptr;
+  dnv_call* d_calls = nullptr;
+  int rc = DNV_OK;
+#define RD_TRY(x) do { if (rc == DNV_OK && (x) != cudaSuccess) { set_error(std::string("dnv_infer_reads: ") + cudaGetErrorString(cudaGetLastError())); rc = DNV_E_CUDA; } } while (0)
+  RD_TRY(cudaMalloc(&d_start, (size_t)std::max<int64_t>(n_reads, 1) * 8));
+  RD_TRY(cudaMalloc(&d_off, (size_t)(n_reads + 1) * 8));
+  RD_TRY(cudaMalloc(&d_bases, (size_t)std::max<int64_t>(n_bases, 1)));
+  RD_TRY(cudaMalloc(&d_person, (size_t)std::max<int64_t>(n_reads, 1)));
+  RD_TRY(cudaMalloc(&d_pos, (size_t)n_sites * 8));
+  RD_TRY(cudaMalloc(&d_calls, (size_t)std::max<int64_t>(dev_cap, 1) * sizeof(dnv_call)));
+  if (n_reads > 0) {
+    RD_TRY(cudaMemcpyAsync(d_start, read_start, (size_t)n_reads * 8, cudaMemcpyHostToDevice, ctx->stream));
+    RD_TRY(cudaMemcpyAsync(d_off, base_off, (size_t)(n_reads + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    RD_TRY(cudaMemcpyAsync(d_bases, bases, (size_t)n_bases, cudaMemcpyHostToDevice, ctx->stream));
+    RD_TRY(cudaMemcpyAsync(d_person, person, (size_t)n_reads, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  RD_TRY(cudaMemcpyAsync(d_pos, site_pos, (size_t)n_sites * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (rc == DNV_OK) rc = dnv_infer_reads_device(ctx, d_start, d_off, d_bases, d_person, n_reads, d_pos, n_sites, d_calls, dev_cap, n_calls);
+  const int64_t got = std::min<int64_t>(*n_calls, dev_cap);
+  if ((rc == DNV_OK || rc == DNV_E_CAPACITY) && got > 0) {
+    const int keep = rc;
+    rc = DNV_OK;
+    RD_TRY(cudaMemcpyAsync(calls, d_calls, (size_t)got * sizeof(dnv_call), cudaMemcpyDeviceToHost, ctx->stream));
+    RD_TRY(cudaStreamSynchronize(ctx->stream));
+    if (rc == DNV_OK) rc = keep;
+  }
+  if (rc == DNV_OK && *n_calls > cap) {
+    set_error("call capacity too small: need " + std::to_string(*n_calls) + ", have " + std::to_string(cap));
+    rc = DNV_E_CAPACITY;
+  }
+  cudaStreamSynchronize(ctx->stream);
+#undef RD_TRY
+  cudaFree(d_start); cudaFree(d_off); cudaFree(d_bases); cudaFree(d_person); cudaFree(d_pos); cudaFree(d_calls);
   return rc;
 }
 

@@ -28,6 +28,7 @@
 #include "trio_fast.cuh"
 #include "trio_list.cuh"
 #include "trio_screen.cuh"
+#include "pileup_scatter.cuh"
 
 namespace dnv {
 
@@ -264,7 +265,7 @@ static int ensure_lane_list(dnv_ctx* ctx, TrioLane& ln, int64_t n) {
   cudaFree(ln.d_list);
   ln.d_list = nullptr;
   ln.list_cap = 0;
-  DNV_CUDA(cudaMalloc(&ln.d_list, ((size_t)n + kScreenSites) * 4));
+  DNV_CUDA(cudaMalloc(&ln.d_list, ((size_t)n + kSC_Tile) * 4));  // a segment starts at its owner's first site: + one tile of slack
   ln.list_cap = n;
   return DNV_OK;
 }
@@ -276,6 +277,22 @@ static int ensure_call_idx(dnv_ctx* ctx, int64_t cap) {
   ctx->call_idx_cap = 0;
   DNV_CUDA(cudaMalloc(&ctx->d_call_idx, (size_t)(cap > 0 ? cap : 1) * 8));
   ctx->call_idx_cap = cap;
+  return DNV_OK;
+}
+
+int launch_pileup_scatter(dnv_ctx* ctx, cudaStream_t st, const int64_t* d_read_start, const int64_t* d_base_off, const char* d_bases,
+                          long long* meta, const int64_t* d_site_pos, int64_t n_sites, int64_t n_reads, uint16_t* d_counts) {
+  const size_t smem = sizeof(ScatterShared);
+  if (!ctx->scatter_plain_per_sm) {
+    DNV_CUDA(cudaFuncSetAttribute(pileup_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int q = 1;
+    DNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, pileup_scatter_kernel, kSC_Threads, smem));
+    ctx->scatter_plain_per_sm = std::max(q, 1);
+  }
+  const int grid = scatter_grid(ctx->sms, (n_sites + kSC_Tile - 1) / kSC_Tile, ctx->scatter_plain_per_sm, 1 << 20);
+  pileup_scatter_kernel<<<grid, kSC_Threads, smem, st>>>(d_read_start, d_base_off, d_bases, meta, d_site_pos, n_sites, n_reads,
+                                                        d_counts);
+  DNV_CUDA(cudaGetLastError());
   return DNV_OK;
 }
 
@@ -328,9 +345,29 @@ int launch_trio_chunk(dnv_ctx* ctx, const ChunkArgs& a) {
     sk.ktrace = ch.ktrace;
     sk.ktrace_seq = ch.ktrace_seq;
     const bool u8 = ctx->count_bytes == 12;
-    int sgrid = 0;
-    rc = u8 ? launch_screen<true>(ctx, ln, st, a.d_counts, n, sk, &sgrid) : launch_screen<false>(ctx, ln, st, a.d_counts, n, sk, &sgrid);
-    if (rc) return rc;
+    int sgrid = 0, n_segments = 0, seg_sites = kScreenSites;
+    if (a.reads) {
+      // fused: pileup of the chunk's reads in shared memory, screened there; counts written for undecided sites only
+      auto kern = pileup_screen_kernel;
+      const size_t smem = sizeof(ScatterShared);
+      if (!ctx->scatter_per_sm) {
+        DNV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int q = 1;
+        DNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, kSC_Threads, smem));
+        ctx->scatter_per_sm = std::max(q, 1);
+      }
+      sgrid = scatter_grid(sms, (n + kSC_Tile - 1) / kSC_Tile, ctx->scatter_per_sm, kScreenMaxWarps);
+      kern<<<sgrid, kSC_Threads, smem, st>>>(a.reads->read_start, a.reads->base_off, a.reads->bases, a.reads->meta,
+                                            a.reads->site_pos, n, a.reads->n_reads, (uint16_t*)const_cast<void*>(a.d_counts), sk,
+                                            ln.d_list, ln.d_wcount);
+      DNV_CUDA(cudaGetLastError());
+      n_segments = sgrid;
+      seg_sites = kSC_Tile;
+    } else {
+      rc = u8 ? launch_screen<true>(ctx, ln, st, a.d_counts, n, sk, &sgrid) : launch_screen<false>(ctx, ln, st, a.d_counts, n, sk, &sgrid);
+      if (rc) return rc;
+      n_segments = sgrid * kScreenWarps;
+    }
     if (timed) DNV_CUDA(cudaEventRecord(ctx->ev_s1[ctx->n_timed], st));
     if (tl != st) {
       DNV_CUDA(cudaEventRecord(ln.ev_screen, st));
@@ -338,11 +375,11 @@ int launch_trio_chunk(dnv_ctx* ctx, const ChunkArgs& a) {
     }
     const bool beside = parallel(ctx) && !a.tail_alone;
     if (map)
-      rc = u8 ? launch_trio_list<true, true>(ctx, ln, tl, a.d_counts, n, a.site_base, sgrid, ch, a.d_calls, a.cap, beside)
-              : launch_trio_list<false, true>(ctx, ln, tl, a.d_counts, n, a.site_base, sgrid, ch, a.d_calls, a.cap, beside);
+      rc = u8 ? launch_trio_list<true, true>(ctx, ln, tl, a.d_counts, n, a.site_base, n_segments, seg_sites, ch, a.d_calls, a.cap, beside)
+              : launch_trio_list<false, true>(ctx, ln, tl, a.d_counts, n, a.site_base, n_segments, seg_sites, ch, a.d_calls, a.cap, beside);
     else
-      rc = u8 ? launch_trio_list<true, false>(ctx, ln, tl, a.d_counts, n, a.site_base, sgrid, ch, a.d_calls, a.cap, beside)
-              : launch_trio_list<false, false>(ctx, ln, tl, a.d_counts, n, a.site_base, sgrid, ch, a.d_calls, a.cap, beside);
+      rc = u8 ? launch_trio_list<true, false>(ctx, ln, tl, a.d_counts, n, a.site_base, n_segments, seg_sites, ch, a.d_calls, a.cap, beside)
+              : launch_trio_list<false, false>(ctx, ln, tl, a.d_counts, n, a.site_base, n_segments, seg_sites, ch, a.d_calls, a.cap, beside);
     if (rc) return rc;
     if (timed) DNV_CUDA(cudaEventRecord(ctx->ev_k1[ctx->n_timed++], tl));
     ctx->screened = true;

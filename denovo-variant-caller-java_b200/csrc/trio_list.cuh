@@ -100,7 +100,7 @@ template <bool kU8, bool kMap>
 __global__ void __launch_bounds__(kListThreads, kTailCtasPerSm)
 trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsigned char* __restrict__ counts,
                  int64_t n, int64_t site_base, const uint32_t* __restrict__ list, const uint32_t* __restrict__ wcount,
-                 uint32_t n_warps, uint32_t range_base, uint32_t range_rem, unsigned long long* status,
+                 uint32_t n_warps, uint32_t range_base, uint32_t range_rem, uint32_t seg_sites, unsigned long long* status,
                  const CallChain ch, int64_t cap, dnv_call* __restrict__ stage) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ListShared<kMap>& s = *reinterpret_cast<ListShared<kMap>*>(smem_raw);
@@ -256,7 +256,7 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
       const uint32_t mid = (a + b) >> 1;
       if (s.woff[mid] <= item) a = mid; else b = mid;
     }
-    return __ldg(list + (size_t)screen_range_lo(a, range_base, range_rem) * kScreenSites + (item - s.woff[a]));
+    return __ldg(list + (size_t)screen_range_lo(a, range_base, range_rem) * seg_sites + (item - s.woff[a]));
   };
   auto fetch_counts = [&](uint32_t site, uint32_t* words) {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(counts + (size_t)site * kBps);
@@ -550,8 +550,11 @@ inline int tail_ctas_beside_screen() {
 // Launches the list kernel (after the previous chain-extending kernel: ctx->ev_chain) and the finish kernel on
 // stream `st`, reading lane `ln`'s list and staging its records in the lane's scratch.
 template <bool kU8, bool kMap>
+// The undecided sites arrive as n_segments sorted segments of ln.d_list (lengths ln.d_wcount), segment g starting at
+// the first site of the g-th balanced range of seg_sites-site tiles: the screen's warps (seg_sites = 128) or the fused
+// pileup-screen kernel's CTAs (1024).
 static int launch_trio_list(dnv_ctx* ctx, TrioLane& ln, cudaStream_t st, const void* d_counts, int64_t n, int64_t site_base,
-                            int screen_grid_size, const CallChain& ch, dnv_call* d_calls, int64_t cap, bool beside_screen) {
+                            int n_segments, int seg_sites, const CallChain& ch, dnv_call* d_calls, int64_t cap, bool beside_screen) {
   const int sms = ctx->sms;
   const size_t smem = sizeof(ListShared<kMap>);
   auto kern = trio_list_kernel<kU8, kMap>;
@@ -570,8 +573,8 @@ static int launch_trio_list(dnv_ctx* ctx, TrioLane& ln, cudaStream_t st, const v
   // completion.  Alone (last chunk of a synchronous call, serial contexts) the kernel takes the whole machine.
   const int64_t want = (n + kListThreads - 1) / kListThreads;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sms * (beside_screen ? tail_ctas_beside_screen() : per_sm)));
-  const uint32_t n_tiles = (uint32_t)((n + kScreenSites - 1) / kScreenSites);
-  const uint32_t n_warps = (uint32_t)screen_grid_size * kScreenWarps;
+  const uint32_t n_tiles = (uint32_t)((n + seg_sites - 1) / seg_sites);
+  const uint32_t n_warps = (uint32_t)n_segments;
   if (reinterpret_cast<uintptr_t>(d_calls) & 15) {
     set_error("d_calls must be 16-byte aligned (records are written as 16-byte words)");
     return DNV_E_INVALID;
@@ -593,7 +596,7 @@ static int launch_trio_list(dnv_ctx* ctx, TrioLane& ln, cudaStream_t st, const v
   // are private to the lane, so lists of different batches need no ordering)
   if (parallel(ctx) && ch.before) DNV_CUDA(cudaStreamWaitEvent(st, ctx->ev_chain, 0));
   kern<<<grid, kListThreads, smem, st>>>(ctx->d_tab, fk, (const unsigned char*)d_counts, n, site_base, ln.d_list,
-                                        ln.d_wcount, n_warps, n_tiles / n_warps, n_tiles % n_warps,
+                                        ln.d_wcount, n_warps, n_tiles / n_warps, n_tiles % n_warps, (uint32_t)seg_sites,
                                         ln.d_tile_status, ch, cap, ln.d_list_stage);
   if (parallel(ctx) && !ch.last) DNV_CUDA(cudaEventRecord(ctx->ev_chain, st));
   // one thread per call; CTAs beyond the number of calls leave at once

@@ -29,7 +29,7 @@ EXPORTS = ["dnv_create", "dnv_destroy", "dnv_last_error", "dnv_abi_version", "dn
            "dnv_gather_create", "dnv_gather_destroy", "dnv_gather_export", "dnv_gather_import", "dnv_gather_attach",
            "dnv_gather_slot", "dnv_infer_counts_device_gather", "dnv_infer_counts8_device_gather", "dnv_gather_arrive",
            "dnv_gather_wait", "dnv_gather_fetch", "dnv_group_create", "dnv_group_destroy", "dnv_group_infer_counts",
-           "dnv_group_infer_counts8", "dnv_group_size", "dnv_group_ctx", "dnv_group_get_stats", "dnv_pileup", "dnv_pileup_device",
+           "dnv_group_infer_counts8", "dnv_group_size", "dnv_group_ctx", "dnv_group_get_stats", "dnv_pileup", "dnv_pileup_device", "dnv_infer_reads", "dnv_infer_reads_device",
            "dnv_mendel_filter", "dnv_mendel_filter_device", "dnv_synth_counts_device", "dnv_synth_counts_at_device",
            "dnv_synth_counts_at", "dnv_measure_fp64_peak"]
 
@@ -120,6 +120,8 @@ def load():
     L.dnv_free_pinned.argtypes = [vp]
     L.dnv_pileup.argtypes = [vp, vp, vp, vp, vp, i64, vp, i64, vp]
     L.dnv_pileup_device.argtypes = [vp, vp, vp, vp, vp, i64, vp, i64, vp]
+    L.dnv_infer_reads.argtypes = [vp, vp, vp, vp, vp, i64, vp, i64, vp, i64, C.POINTER(i64)]
+    L.dnv_infer_reads_device.argtypes = [vp, vp, vp, vp, vp, i64, vp, i64, vp, i64, C.POINTER(i64)]
     L.dnv_mendel_filter.argtypes = [vp, vp, i64, vp, i64, C.POINTER(i64)]
     L.dnv_mendel_filter_device.argtypes = [vp, vp, i64, vp, i64, C.POINTER(i64)]
     L.dnv_synth_counts_device.argtypes = [vp, u64, i64, i64, vp, i32, u32, vp]

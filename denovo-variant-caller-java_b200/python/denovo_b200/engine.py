@@ -148,6 +148,28 @@ class TrioEngine:
         L.check(self.lib.dnv_pileup_device(self._h, L.ptr(d_read_start), L.ptr(d_base_off), L.ptr(d_bases),
                                            L.ptr(d_person), n_reads, L.ptr(d_site_pos), n_sites, L.ptr(d_counts)))
 
+    def infer_reads(self, read_start, base_off, bases, person, site_pos, cap=None):
+        """reads -> calls in one fused pass (dnv_infer_reads): the records of infer(pileup(...))."""
+        read_start = np.ascontiguousarray(read_start, np.int64)
+        base_off = np.ascontiguousarray(base_off, np.int64)
+        bases = np.ascontiguousarray(bases, np.uint8)
+        person = np.ascontiguousarray(person, np.uint8)
+        site_pos = np.ascontiguousarray(site_pos, np.int64)
+        n = site_pos.shape[0]
+        cap = n if cap is None else cap
+        calls = np.zeros(max(cap, 1), L.CALL_DT)
+        nc = C.c_int64(0)
+        L.check(self.lib.dnv_infer_reads(self._h, L.ptr(read_start), L.ptr(base_off), L.ptr(bases), L.ptr(person),
+                                         read_start.shape[0], L.ptr(site_pos), n, L.ptr(calls) if cap > 0 else None, cap,
+                                         C.byref(nc)))
+        return calls[:nc.value]
+
+    def infer_reads_device(self, d_read_start, d_base_off, d_bases, d_person, n_reads, d_site_pos, n_sites, d_calls, cap):
+        nc = C.c_int64(0)
+        L.check(self.lib.dnv_infer_reads_device(self._h, L.ptr(d_read_start), L.ptr(d_base_off), L.ptr(d_bases), L.ptr(d_person),
+                                                n_reads, L.ptr(d_site_pos), n_sites, L.ptr(d_calls), cap, C.byref(nc)))
+        return nc.value
+
     # ---- VARIANT mode
     def mendel_filter(self, calls, cap=None):
         calls = np.ascontiguousarray(calls, L.VCALL_DT)

@@ -245,6 +245,20 @@ int dnv_pileup_device(dnv_ctx *ctx, const int64_t *d_read_start,
                       const int64_t *d_site_pos, int64_t n_sites,
                       uint16_t *d_counts_out);
 
+/* ---- READ mode: reads -> calls, fused ------------------------------------- */
+/* ReadCaller.runBayesDenovoInference for a whole batch of candidate sites (M/ReadCaller.java:111-130):
+ * `new ReadSummary(reads, position)` x3 (:138-146, M/ReadSummary.java:45-59) and BayesInfer.infer (:119-120) in
+ * one pass.  Same read layout as dnv_pileup; same records as dnv_infer_counts over the counts dnv_pileup would
+ * produce (site = index into site_pos).  For consecutive positions the pileup of a tile is accumulated in shared
+ * memory and screened there; per-site counts only ever reach HBM for the ~1 % of sites the screen cannot decide. */
+int dnv_infer_reads(dnv_ctx *ctx, const int64_t *read_start, const int64_t *base_off, const char *bases,
+                    const uint8_t *person, int64_t n_reads, const int64_t *site_pos, int64_t n_sites,
+                    dnv_call *calls, int64_t cap, int64_t *n_calls);
+int dnv_infer_reads_device(dnv_ctx *ctx, const int64_t *d_read_start, const int64_t *d_base_off,
+                           const char *d_bases, const uint8_t *d_person, int64_t n_reads,
+                           const int64_t *d_site_pos, int64_t n_sites, dnv_call *d_calls, int64_t cap,
+                           int64_t *n_calls);
+
 /* ---- VARIANT mode: Mendelian-inconsistency filter ----------------------- */
 /* One shard of VariantCaller.callSimpleDenovo (M/VariantCaller.java:120-210):
  * admission (checkAndAdd), trio interval join (retrieveNextCall) and

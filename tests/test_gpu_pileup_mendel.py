@@ -84,6 +84,80 @@ def test_pileup_dense_bad_base_only_at_requested_sites(n_sites):
         assert ei.value.code == D.DNV_E_BADBASE
 
 
+@pytest.mark.parametrize("kernel", ["scatter", "stage"])
+def test_both_pileup_kernels_dense_and_ragged(kernel, monkeypatch):
+    """The read-major scatter kernel (default) and the position-major gather kernel (DNV_PILEUP_KERNEL=stage) are
+    both bit-exact against the oracle: dense sites, variable-length reads, 200x depth (several rounds of 255 reads),
+    gaps, an uncovered flank, a site count that is not a multiple of the tile."""
+    import subprocess, sys, os
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, "tests")
+import denovo_b200 as D, oracle_lib as O, synth_inputs as S
+for seed, depth, rl, var in ((21, 30, 100, False), (22, 200, 150, True), (23, 8, 37, True)):
+    rs, bo, ba, pe = S.make_reads(seed, 5000, 2500, depth=depth, read_len=rl, gap_rate=5e-3, var_len=var)
+    pos = np.arange(4800, 7777, dtype=np.int64)
+    rc, want = O.pileup_sorted(rs, bo, ba, pe, pos)
+    assert rc == 0
+    with D.TrioEngine() as eng:
+        got = eng.pileup(rs, bo, ba, pe, pos)
+    assert np.array_equal(got, want), (seed, int((got != want).sum()))
+print("ok")
+"""
+    env = dict(os.environ, DNV_PILEUP_KERNEL=kernel, PYTHONPATH=os.pathsep.join(sys.path))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-1000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("method", ["BAYES", "MAP", "LRT"])
+def test_fused_reads_to_calls_equals_pileup_then_inference(method):
+    """dnv_infer_reads (pileup in shared memory, screened there, counts only for undecided sites) returns the records
+    of dnv_infer_counts over dnv_pileup's counts — and those are the oracle's: dense every-position layout with
+    planted de novo / inherited variants, a ragged tail, then a sparse candidate list (per-site path)."""
+    n_sites = 300_000 + 77
+    rs, bo, ba, pe = S.make_reads(17, 1, n_sites, depth=30, err=1e-2)
+    # plant variants every 211 sites (vectorised): at even plants the child alone carries an alternative allele in
+    # about half of its reads (the de novo pattern), at odd ones one parent carries it too (inherited)
+    rng = np.random.default_rng(3)
+    lens = np.diff(bo)
+    posn = np.repeat(rs, lens) + (np.arange(bo[-1]) - np.repeat(bo[:-1], lens))
+    per = np.repeat(pe, lens)
+    k = (posn - 500) // 211
+    planted = (posn >= 500) & ((posn - 500) % 211 == 0) & (ba != ord("-")) & (rng.random(len(posn)) < 0.5)
+    carrier = (per == 2) | ((k % 2 == 1) & (per == (k // 2) % 2))
+    sel = np.nonzero(planted & carrier)[0]
+    alt = np.frombuffer(b"ACGT", np.uint8)[(k[sel] + 1) % 4]
+    alt = np.where(alt == ba[sel], np.frombuffer(b"ACGT", np.uint8)[(k[sel] + 2) % 4], alt)
+    ba[sel] = alt
+    pos = np.arange(1, n_sites + 1, dtype=np.int64)
+    lrt = 10.0 if method == "LRT" else 1.0
+    with D.TrioEngine(1e-2, 1e-8, lrt, method) as eng:
+        counts = eng.pileup(rs, bo, ba, pe, pos)
+        want, _ = eng.infer(counts)
+        got = eng.infer_reads(rs, bo, ba, pe, pos)
+        assert len(want) > (20 if method == "LRT" else 100) and got.tobytes() == want.tobytes()
+        st = eng.stats()
+        assert st["n_sites"] == n_sites and st["n_calls"] == len(want)
+        # sparse candidates (not consecutive positions): the per-site path of the fused kernel
+        cand = np.unique(np.concatenate([want["site"][::3] + 1, rng.integers(1, n_sites, 5000)])).astype(np.int64)
+        c2 = eng.pileup(rs, bo, ba, pe, cand)
+        w2, _ = eng.infer(c2)
+        g2 = eng.infer_reads(rs, bo, ba, pe, cand)
+        assert len(w2) > 10 and g2.tobytes() == w2.tobytes()
+        with pytest.raises(D.DenovoError) as ei:
+            eng.infer_reads(rs, bo, ba, pe, pos, cap=7)
+        assert ei.value.code == D.DNV_E_CAPACITY and str(len(want)) in str(ei.value)
+        bad = ba.copy()
+        bad[bo[len(rs) // 2] + 3] = ord("N")
+        with pytest.raises(D.DenovoError) as ei:
+            eng.infer_reads(rs, bo, bad, pe, pos)
+        assert ei.value.code == D.DNV_E_BADBASE
+    ref = O.infer(O.params(1e-2, 1e-8, lrt), O.pileup_sorted(rs, bo, ba, pe, pos)[1])
+    field = {"BAYES": "denovo_bayes", "MAP": "denovo_map", "LRT": "denovo_lrt"}[method]
+    assert np.array_equal(want["site"], np.nonzero(ref[field])[0])
+
+
 def test_pileup_then_inference_end_to_end():
     """reads -> counts -> calls on the device equals oracle pileup -> oracle inference."""
     rs, bo, ba, pe = S.make_reads(13, 1, 20000, depth=30, err=2e-2)
