@@ -142,7 +142,9 @@ def reference_arm(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "READ-mode BAYES inference, synthetic trio pileups at 30x, eps 1e-2, mu 1e-8 "
-                                   "(BASELINE configs[2]); %d-site sample per step" % sample},
+                                   "(BASELINE configs[2]); %d-site sample per step" % sample,
+                       "same_workload_as_our_arm": "a bounded sample of it: the CPU path costs the same per site at any batch "
+                                                   "size (one independent task per site, M/ReadCaller.java:91-95), so sites/s compares"},
             "cpu_baseline": {"value": value, "unit": "sites/s", "cores": threads, "kind": "port",
                              "sample": "%d sites/step x %d steps; C restatement of the reference's direct form "
                                        "(3 log + 1 exp per genotype triple, as DenovoBayesNet.java:220-233,269-273); "

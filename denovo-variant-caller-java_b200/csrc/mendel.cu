@@ -30,7 +30,6 @@
 #include <algorithm>
 
 #include "dnv_internal.cuh"
-#include "scan_util.cuh"
 
 namespace dnv {
 

@@ -23,7 +23,6 @@
 
 #include <algorithm>
 
-#include "scan_util.cuh"
 #include "trio_exact.cuh"
 #include "trio_fast.cuh"
 #include "trio_list.cuh"
@@ -72,7 +71,6 @@ trio_direct_all_kernel(const Tables* __restrict__ tab, const void* __restrict__ 
 // ch (CallChain): *before = calls before this chunk, pair[0..1] <- calls before / after it, work[0] block ticket.
 constexpr int kCompactThreads = 256;
 static_assert(kWcountWords >= kScreenMaxWarps, "wcount buffers hold one word per screen warp");
-static_assert(kCompactThreads == kScanThreads, "one bit-word per thread");
 
 __global__ void __launch_bounds__(kCompactThreads)
 compact_calls_kernel(int64_t site_base, const uint32_t* __restrict__ bits, int64_t n_words,
@@ -231,11 +229,7 @@ static int ensure_lane_status(dnv_ctx* ctx, TrioLane& ln, int64_t n, cudaStream_
   ln.d_tile_status = nullptr;
   ln.tile_cap = 0;
   const int64_t n_status = (n + kListThreads - 1) / kListThreads + 1;  // one entry per list tile (kListThreads undecided sites)
-#ifdef DNV_LIST_TRACE
-  const int64_t n_status_alloc = (1 << 20) + 8 * 8192;  // room for the per-CTA time stamps of trio_list_kernel
-#else
   const int64_t n_status_alloc = n_status;
-#endif
   DNV_CUDA(cudaMalloc(&ln.d_tile_status, (size_t)n_status_alloc * 8));
   DNV_CUDA(cudaMemsetAsync(ln.d_tile_status, 0, (size_t)n_status * 8, st));
   ln.tile_status_bytes = (size_t)n_status * 8;
@@ -440,8 +434,3 @@ extern "C" int dnv_debug_ktrace(dnv_ctx* ctx, unsigned long long* out, unsigned 
   return ctx->n_lanes;
 }
 
-#ifdef DNV_LIST_TRACE
-extern "C" int dnv_debug_list_trace(dnv_ctx* ctx, unsigned long long* out, int n_ctas) {
-  return cudaMemcpy(out, ctx->d_tile_status + (1 << 20), (size_t)n_ctas * 64, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
-}
-#endif

@@ -106,13 +106,6 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
   ListShared<kMap>& s = *reinterpret_cast<ListShared<kMap>*>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int kBps = kU8 ? 12 : 24;
-#ifdef DNV_LIST_TRACE
-  unsigned long long* trace = status + (1 << 20) + blockIdx.x * 8;
-  auto stamp = [&](int i) { if (threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); trace[i] = t; } };
-#else
-  auto stamp = [&](int) {};
-#endif
-  stamp(0);
   if (threadIdx.x == 0) ktrace_stamp(ch.ktrace, ch.ktrace_seq, 1, false);
   // the first tile is claimed before the prologue: by the time any CTA asks for its second tile, every
   // running CTA holds a first one, so tile order stays close to processing order (short look-back waits)
@@ -242,7 +235,6 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
     }
   }
   const ListPow<kMap> pw{s, tab};
-  stamp(1);
 
   // Tiles are handed out by ticket, in increasing order, to CTAs that are running: the look-back below
   // therefore only ever waits for tiles held by running CTAs (no co-residency assumption).  A CTA claims
@@ -267,7 +259,6 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
   uint32_t site_cur = fetch_site(tile), site_nxt = 0;
   uint32_t words_cur[kBps / 4];
   fetch_counts(site_cur, words_cur);
-  bool first_trip = true;
   int trip = 0;
   while (tile < n_tiles) {
     trip ^= 1;
@@ -322,8 +313,6 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
         }
       }
     }
-    if (first_trip) stamp(2);
-    first_trip = false;
     // order-preserving rank of the called sites inside the tile
     const uint32_t dw = __ballot_sync(0xffffffffu, dn);
     __syncthreads();  // s.warp_sum / s.excl of the previous trip are no longer read; s.ticket is written
@@ -408,9 +397,7 @@ trio_list_kernel(const Tables* __restrict__ tab, const FastConsts k, const unsig
     }
     tile = tile_nxt;
   }
-  stamp(3);
   __syncthreads();
-  stamp(5);
   // the last CTA to leave clears the status entries this launch used and resets the ticket for the next launch
   // (by then every ticket has been taken and every look-back has finished)
   __shared__ int s_is_last;
