@@ -30,6 +30,8 @@ struct Tables {
   int32_t map_screen_ok;       // ... and for the MAP decision
   uint32_t c_hom_fx, c_het_fx; // log2(r_j) in 16.16 fixed point
   uint32_t scr_w[4];           // screen level 1: signed-byte weights (A,C,G,T) when allele X is the candidate
+  int32_t l3_lambda_fx;        // screen level 3 (trio_screen.cuh): log2 threshold in 16.16 fixed point, 0 = disabled
+  int32_t l3_max_depth;        // ... largest total depth of a site it may decide (everything stays in FP64's normal range)
   double mm2;                  // log2(eps/3)
   double k_men;                // ((1-mu)/4)/64
   double k_den[4];             // (mu/256)/nDen for nDen = 9,8,7,6

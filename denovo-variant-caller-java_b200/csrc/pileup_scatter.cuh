@@ -308,7 +308,8 @@ pileup_screen_kernel(const int64_t* __restrict__ read_start, const int64_t* __re
       if (i < n_live) {
         const uint2 d = sh.tot[0][i], m = sh.tot[1][i], c = sh.tot[2][i];
         w[0] = d.x; w[1] = d.y; w[2] = m.x; w[3] = m.y; w[4] = c.x; w[5] = c.y;
-        undecided = !screen_level1<false>(w, k) && !screen_site<false>(w, k);
+        undecided = !screen_level1<false>(w, k) && !screen_site<false>(w, k) &&
+                    !(k.l3_lambda > 0 && screen_level3_words<false>(w, k));
       }
       const uint32_t uw = __ballot_sync(0xffffffffu, undecided);
       if (lane == 0) sh.warp_cnt[warp] = __popc(uw);

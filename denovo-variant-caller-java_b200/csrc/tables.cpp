@@ -120,6 +120,24 @@ void build_tables(const dnv_params& p, Tables* t) {
   }
   t->early_ok = (t->fast_ok && fits && log2r[0] > log2r[1] && p.method != DNV_METHOD_MAP && thr_eff > 0.0 && std::isfinite(thr_eff) &&
                  4.0 * 5334.0 * mu / (1.0 - mu) < 0.999 * thr_eff) ? 1 : 0;
+  // screen level 3 (trio_screen.cuh: both parents clearly homozygous, child genotype not explained by them):
+  //   Lden <= 1.0143 * (mu / 2304) * a* b* e*     and     Lmen >= ((1 - mu) / 256) * (one alternative's likelihoods),
+  // so the site is not de novo when log2(likelihood ratio best / alternative) < log2(9 T (1 - mu) / mu) - 0.0205;
+  // another 0.05 bits cover the 16.16 fixed point (<= 3 products of depth <= 127 counts, 2^-17 each) and FP64 rounding.
+  // Only sites whose smallest relevant term stays a NORMAL double in the reference's raw-exp sums are decided.
+  t->l3_lambda_fx = 0;
+  t->l3_max_depth = 0;
+  if (t->early_ok) {
+    const long double lam = log2l(9.0L * (long double)thr_eff * (1.0L - (long double)mu) / (long double)mu) - 0.0705L;
+    const long double room = 690.0L - fabsl(logl((long double)mu / 2304.0L));
+    const long double per_read = fabsl(logl(le) - logl(3.0L));
+    long long nmax = room > 0 ? (long long)floorl(room / per_read) : 0;
+    nmax = std::min<long long>(nmax, ((1ll << 31) - (1ll << 21)) / std::max<long long>(1, std::max(t->c_hom_fx, t->c_het_fx)));  // int32 products
+    if (lam > 1.0L && lam < 30000.0L && nmax >= 3) {
+      t->l3_lambda_fx = (int32_t)floorl(lam * 65536.0L);
+      t->l3_max_depth = (int32_t)std::min<long long>(nmax, 4000);
+    }
+  }
   // MAP through the same screen: the chosen Mendelian triple t* (each genotype within a factor 2 of its
   // person's best) has ll(t*) >= sum Lmax - 3 ln 2 + log((1/16)(1/16)(1-mu)/4); every de novo triple has
   // ll <= sum Lmax + log((1/8)(1/8) mu/6).  The gap is log(0.046875 (1-mu)/mu): with mu < 0.01 it exceeds

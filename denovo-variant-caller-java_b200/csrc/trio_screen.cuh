@@ -43,6 +43,8 @@ constexpr int kScreenWarps = kScreenThreads / 32;
 struct ScreenConsts {
   uint32_t c_hom, c_het;  // log2(r_hom), log2(r_het) in 16.16 fixed point
   uint32_t w[4];          // level 1 weights per candidate allele (Tables::scr_w)
+  int32_t l3_lambda;      // level 3: log2 threshold (16.16), 0 = level 3 off
+  int32_t l3_max_depth;   // level 3: largest total depth it may decide
   uint32_t shift32;       // 32 (a run-time value the assembler cannot fold: x >> 32 == 0 orders the tile refill)
   unsigned long long* ktrace;  // DNV_KTRACE time line of the lane, or null
   const unsigned int* ktrace_seq;
@@ -60,6 +62,95 @@ __device__ __forceinline__ int screen_person(int k0, int k1, int k2, int k3, con
   const bool het = (uint32_t)k_het * k.c_het > (uint32_t)k_hom * k.c_hom;  // r_het^k_het > r_hom^k_hom
   const int y2 = het ? y : x;
   return ((1 << x) | (1 << y2)) | (x << 4) | (y2 << 6) | (k_het >= kPowTable ? 256 : 0);
+}
+
+// Level 3 — the sites level 2 leaves are almost all of ONE kind: both parents clearly homozygous (alleles x_d, x_m), and
+// a child whose most likely genotype c* they cannot have transmitted (the de novo pattern).  Most of them are still
+// not called: one more read in a parent would have made "the parent is heterozygous and we missed it" the better
+// explanation.  With d* = x_d x_d, m* = x_m x_m and every person's best genotype at least 13 bits ahead of its
+// second best (so that the nine other genotypes add at most 9 * 2^-13 to a person's likelihood sum):
+//     Lden <= P(d*) P(m*) (mu / 9) a* b* E + (mu / 384) (A B - a* b*) E  <=  1.0143 * (mu / 2304) a* b* e*
+// (nDen = 9 for two homozygous parents; every other parental pair carries a factor 2^-13), while each Mendelian
+// ALTERNATIVE is a single term of Lmen with the same weight (1 - mu) / 256:
+//     child x_d x_m instead of c*                                  (1/16)(1/16)(1 - mu)        a*  b*  e_alt
+//     dad x_d u instead of x_d x_d, if c* = {u, x_m}               (1/8)(1/16)((1 - mu) / 2)   a_alt b* e*
+//     mom x_m u instead of x_m x_m, if c* = {u, x_d}               (1/16)(1/8)((1 - mu) / 2)   a*  b_alt e*
+// so Lden < T * Lmen as soon as the likelihood ratio best / alternative of ONE of them is below
+// 9 T (1 - mu) / (1.0143 mu) — compared as k * log2(r) in 16.16 fixed point like level 2 (tables.cpp folds the
+// constant, the fixed-point error and a guard for FP64 rounding into l3_lambda).  The site's total depth is
+// limited so that both sides stay normal doubles in the reference's raw-exp sums (no flush / subnormal effects).
+// Checked against the oracle in tests/test_screen_theory.py.  n = counts [person][allele].
+__device__ __forceinline__ int pick4(int n0, int n1, int n2, int n3, int a) {  // n[a] without dynamic indexing
+  return a == 0 ? n0 : a == 1 ? n1 : a == 2 ? n2 : n3;
+}
+// top allele (first maximiser) and the largest count among the others
+__device__ __forceinline__ void top_two(int n0, int n1, int n2, int n3, int& xa, int& k1, int& k2) {
+  xa = 0; k1 = n0;
+  if (n1 > k1) { k1 = n1; xa = 1; }
+  if (n2 > k1) { k1 = n2; xa = 2; }
+  if (n3 > k1) { k1 = n3; xa = 3; }
+  k2 = max(max(xa == 0 ? 0 : n0, xa == 1 ? 0 : n1), max(xa == 2 ? 0 : n2, xa == 3 ? 0 : n3));
+}
+__device__ __forceinline__ bool screen_level3(const int (&n)[3][4], const ScreenConsts& k) {
+  const int c_hom = (int)k.c_hom, c_het = (int)k.c_het;
+  constexpr int kGap = 13 << 16;
+  const int total = ((n[0][0] + n[0][1]) + (n[0][2] + n[0][3])) + ((n[1][0] + n[1][1]) + (n[1][2] + n[1][3])) +
+                    ((n[2][0] + n[2][1]) + (n[2][2] + n[2][3]));
+  if (total > k.l3_max_depth) return false;
+  // parents: the homozygote of the top allele, 13 bits ahead of everything else
+  int xd, xm, k1, k2;
+  top_two(n[0][0], n[0][1], n[0][2], n[0][3], xd, k1, k2);
+  if (k1 * c_hom < max(k2 * c_hom, (k1 + k2) * c_het) + kGap) return false;
+  const int nd_x = k1;
+  top_two(n[1][0], n[1][1], n[1][2], n[1][3], xm, k1, k2);
+  if (k1 * c_hom < max(k2 * c_hom, (k1 + k2) * c_het) + kGap) return false;
+  const int nm_x = k1;
+  // child: top three alleles, best genotype (hom of the top one or het of the top two), 13 bits ahead of its second best
+  int t1;
+  top_two(n[2][0], n[2][1], n[2][2], n[2][3], t1, k1, k2);
+  int t2 = -1, kk = -1;  // first allele other than t1 holding k2 reads
+  if (t1 != 0 && n[2][0] > kk) { kk = n[2][0]; t2 = 0; }
+  if (t1 != 1 && n[2][1] > kk) { kk = n[2][1]; t2 = 1; }
+  if (t1 != 2 && n[2][2] > kk) { kk = n[2][2]; t2 = 2; }
+  if (t1 != 3 && n[2][3] > kk) { kk = n[2][3]; t2 = 3; }
+  const int k3 = max(max((t1 == 0 || t2 == 0) ? 0 : n[2][0], (t1 == 1 || t2 == 1) ? 0 : n[2][1]),
+                     max((t1 == 2 || t2 == 2) ? 0 : n[2][2], (t1 == 3 || t2 == 3) ? 0 : n[2][3]));
+  const int hom_c = k1 * c_hom, het_c = (k1 + k2) * c_het;
+  const bool het = het_c > hom_c;
+  const int e_star = het ? het_c : hom_c;
+  const int second = het ? max(hom_c, (k1 + k3) * c_het) : max(k2 * c_hom, het_c);
+  if (e_star < second + kGap) return false;
+  const int a1 = t1, a2 = het ? t2 : t1;  // alleles of c*
+  // alternative 1: the child is x_d x_m after all
+  const int nc_xd = pick4(n[2][0], n[2][1], n[2][2], n[2][3], xd), nc_xm = pick4(n[2][0], n[2][1], n[2][2], n[2][3], xm);
+  const int e_alt = xd == xm ? nc_xd * c_hom : (nc_xd + nc_xm) * c_het;
+  int ratio = e_star - e_alt;
+  if (a1 == xm || a2 == xm) {  // alternative 2: dad is x_d u, u = the child's other allele
+    const int u = a1 == xm ? a2 : a1;
+    if (u != xd) ratio = min(ratio, nd_x * c_hom - (nd_x + pick4(n[0][0], n[0][1], n[0][2], n[0][3], u)) * c_het);
+  }
+  if (a1 == xd || a2 == xd) {  // alternative 3: mom is x_m u
+    const int u = a1 == xd ? a2 : a1;
+    if (u != xm) ratio = min(ratio, nm_x * c_hom - (nm_x + pick4(n[1][0], n[1][1], n[1][2], n[1][3], u)) * c_het);
+  }
+  return ratio < k.l3_lambda;
+}
+
+// level 3 on a site's packed count words
+template <bool kU8>
+__device__ __forceinline__ bool screen_level3_words(const uint32_t* w, const ScreenConsts& k) {
+  int n[3][4];
+#pragma unroll
+  for (int p = 0; p < 3; p++) {
+    if (kU8) {
+#pragma unroll
+      for (int a = 0; a < 4; a++) n[p][a] = (int)((w[p] >> (8 * a)) & 0xFFu);
+    } else {
+      n[p][0] = (int)(w[2 * p] & 0xFFFFu); n[p][1] = (int)(w[2 * p] >> 16);
+      n[p][2] = (int)(w[2 * p + 1] & 0xFFFFu); n[p][3] = (int)(w[2 * p + 1] >> 16);
+    }
+  }
+  return screen_level3(n, k);
 }
 
 // true = provably not de novo (see the header of this file); w = the site's three uint2 words
@@ -191,9 +282,24 @@ trio_screen_kernel(const unsigned char* __restrict__ counts, int64_t n, const Sc
   uint32_t pw[kWords], psite = 0;  // the batch in flight: one parked site per lane
 #pragma unroll
   for (int q = 0; q < kWords; q++) pw[q] = 0;
-  auto flush = [&](uint32_t take) {  // the oldest `take` undecided sites -> this warp's segment of the list
-    if (lane < take) my_list[written + lane] = my_fails[(fhead + lane) & (kScreenRing - 1)];
-    written += take;
+  // the oldest `take` sites level 2 could not decide: level 3 (32 of them at a time, so the ~1 % of sites that need
+  // it cost one warp-wide evaluation per 32), the survivors -> this warp's segment of the list, still ascending
+  auto flush = [&](uint32_t take) {
+    uint32_t site = 0;
+    bool keep = lane < take;
+    if (keep) {
+      site = my_fails[(fhead + lane) & (kScreenRing - 1)];
+      if (k.l3_lambda > 0) {
+        uint32_t lw[kWords];
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(counts + (size_t)site * kBps);
+#pragma unroll
+        for (int q = 0; q < kWords; q++) lw[q] = __ldg(src + q);
+        keep = !screen_level3_words<kU8>(lw, k);
+      }
+    }
+    const uint32_t km = __ballot_sync(kFull, keep);
+    if (keep) my_list[written + __popc(km & lt_mask)] = site;
+    written += __popc(km);
     fhead += take;
     fcount -= take;
     __syncwarp();
