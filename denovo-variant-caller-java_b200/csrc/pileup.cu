@@ -15,6 +15,7 @@
 #include <algorithm>
 #include "dnv_internal.cuh"
 #include "pileup_stage.cuh"
+#include "pileup_pipe.cuh"
 
 namespace dnv {
 
@@ -84,10 +85,24 @@ int dnv_pileup_device(dnv_ctx* ctx, const int64_t* d_read_start, const int64_t* 
   // dense tiles: position-major gather (pileup_stage.cuh; 6.9 G sites/s at 30x); DNV_PILEUP_KERNEL=scatter selects the
   // read-major formulation with shared-memory atomics (pileup_scatter.cuh; 6.3 G sites/s — its tile routine is what the
   // fused reads -> calls kernel builds on); sparse tiles: one site at a time in either
-  static const bool use_stage = [] { const char* e = getenv("DNV_PILEUP_KERNEL"); return !(e && std::string(e) == "scatter"); }();
-  if (use_stage) {
-    DNV_CUDA(launch_pileup_stage<8>(ctx->stream, sms, d_read_start, d_base_off, d_bases, meta, d_site_pos, n_sites, n_reads,
-                                    d_counts_out));
+  static const std::string which = [] { const char* e = getenv("DNV_PILEUP_KERNEL"); return std::string(e ? e : "pipe"); }();
+  static const int stage_s = [] { const char* e = getenv("DNV_PILEUP_S"); return e ? atoi(e) : 16; }();  // sites per thread
+  if (which == "pipe") {
+    if (stage_s == 8) {
+      DNV_CUDA(launch_pileup_pipe<8>(ctx->stream, sms, d_read_start, d_base_off, d_bases, meta, d_site_pos, n_sites, n_reads,
+                                     d_counts_out));
+    } else {
+      DNV_CUDA(launch_pileup_pipe<16>(ctx->stream, sms, d_read_start, d_base_off, d_bases, meta, d_site_pos, n_sites, n_reads,
+                                      d_counts_out));
+    }
+  } else if (which == "stage") {
+    if (stage_s == 8) {
+      DNV_CUDA(launch_pileup_stage<8>(ctx->stream, sms, d_read_start, d_base_off, d_bases, meta, d_site_pos, n_sites, n_reads,
+                                      d_counts_out));
+    } else {
+      DNV_CUDA(launch_pileup_stage<16>(ctx->stream, sms, d_read_start, d_base_off, d_bases, meta, d_site_pos, n_sites, n_reads,
+                                       d_counts_out));
+    }
   } else {
     const int rc2 = launch_pileup_scatter(ctx, ctx->stream, d_read_start, d_base_off, d_bases, meta, d_site_pos, n_sites, n_reads,
                                           d_counts_out);

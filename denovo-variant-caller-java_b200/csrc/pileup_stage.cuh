@@ -37,8 +37,10 @@ __host__ __device__ __forceinline__ unsigned long long pileup_err(long long inde
   return ((unsigned long long)(index + 1) << 4) | (at_site ? 8ull : 0ull) | kind;
 }
 
+template <int S>
 struct PileStageShared {
   alignas(16) unsigned char stage[kPS_Pad + kPS_StageBytes + kPS_Pad];
+  uint2 tot[S][kPS_Threads];  // 16-bit totals (A | C << 16, G | T << 16) of thread t's site k: [k][t], conflict free
   int rel[kPS_ReadCap];    // read start - P0
   int soff[kPS_ReadCap];   // offset of the read's first base in stage[]
   int len[kPS_ReadCap];
@@ -64,25 +66,66 @@ __device__ __forceinline__ int64_t ps_warp_upper_bound(const int64_t* __restrict
   return lo + __popc(__ballot_sync(0xffffffffu, le));
 }
 
+// the six window bounds of a tile at once: out[2p] = first read of person p with start > key_lo, out[2p+1] = first
+// with start > key_hi (person p's reads are [meta[p], meta[p+1])); 32-ary, the loads of all six searches of a round
+// in flight together (4 round trips for 600 k reads per person instead of 24)
+__device__ __forceinline__ void ps_warp_upper_bound6(const int64_t* __restrict__ a, const long long* meta, int64_t key_lo,
+                                                     int64_t key_hi, int lane, int64_t (&out)[6]) {
+  constexpr long long kInf = 0x7fffffffffffffffll;
+  int64_t lo[6], hi[6];
+#pragma unroll
+  for (int q = 0; q < 6; q++) { lo[q] = meta[q >> 1]; hi[q] = meta[(q >> 1) + 1]; }
+  for (;;) {
+    bool big = false;
+#pragma unroll
+    for (int q = 0; q < 6; q++) big |= hi[q] - lo[q] > 32;
+    if (!big) break;
+    int64_t step[6];
+    long long v[6];
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+      step[q] = (hi[q] - lo[q] + 32) / 33;
+      const int64_t idx = lo[q] + (int64_t)(lane + 1) * step[q] - 1;
+      v[q] = (hi[q] - lo[q] > 32 && idx < hi[q]) ? __ldg(a + idx) : kInf;
+    }
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+      if (hi[q] - lo[q] > 32) {  // warp uniform
+        const int c = __popc(__ballot_sync(0xffffffffu, v[q] <= ((q & 1) ? key_hi : key_lo)));
+        const int64_t new_lo = c ? lo[q] + (int64_t)c * step[q] : lo[q];
+        const int64_t new_hi = c < 32 ? min(hi[q], lo[q] + (int64_t)(c + 1) * step[q] - 1) : hi[q];
+        lo[q] = new_lo; hi[q] = new_hi;
+      }
+    }
+  }
+  long long v[6];
+#pragma unroll
+  for (int q = 0; q < 6; q++) v[q] = lo[q] + lane < hi[q] ? __ldg(a + lo[q] + lane) : kInf;
+#pragma unroll
+  for (int q = 0; q < 6; q++) out[q] = lo[q] + __popc(__ballot_sync(0xffffffffu, v[q] <= ((q & 1) ? key_hi : key_lo)));
+}
+
 // one person of one dense tile: out01[k] = A | C << 16, out23[k] = G | T << 16 for my S sites
 template <int S>
-__device__ __forceinline__ void ps_person(PileStageShared& sh, int64_t c_first, int64_t c_last,
+__device__ __forceinline__ void ps_person(PileStageShared<S>& sh, int64_t c_first, int64_t c_last,
                                           const int64_t* __restrict__ read_start,
                                           const int64_t* __restrict__ base_off, const char* __restrict__ bases,
                                           long long n_bases, int64_t P0, int my_off, int n_live, int lmax,
-                                          uint32_t (&out01)[S], uint32_t (&out23)[S], bool& bad, bool& over) {
+                                          bool& bad, bool& over) {
   constexpr int NW = S / 4;
   uint32_t acc[S];
 #pragma unroll
-  for (int k = 0; k < S; k++) { acc[k] = 0; out01[k] = 0; out23[k] = 0; }
+  for (int k = 0; k < S; k++) { acc[k] = 0; sh.tot[k][threadIdx.x] = make_uint2(0u, 0u); }
   uint32_t badacc = 0;
   int since_flush = 0, visits = 0;
-  auto flush = [&]() {
+  auto flush = [&]() {  // 6-bit lanes -> this thread's 16-bit totals in shared memory (once per 63 visits)
 #pragma unroll
     for (int k = 0; k < S; k++) {
       const uint32_t a = acc[k];
-      out01[k] += (a & 0x3Fu) | ((a << 10) & 0x3F0000u);
-      out23[k] += ((a >> 12) & 0x3Fu) | ((a >> 2) & 0x3F0000u);
+      uint2 t = sh.tot[k][threadIdx.x];
+      t.x += (a & 0x3Fu) | ((a << 10) & 0x3F0000u);
+      t.y += ((a >> 12) & 0x3Fu) | ((a >> 2) & 0x3F0000u);
+      sh.tot[k][threadIdx.x] = t;
       badacc |= a >> 24;
       acc[k] = 0;
     }
@@ -181,7 +224,7 @@ pileup_stage_kernel(const int64_t* __restrict__ read_start, const int64_t* __res
                     const char* __restrict__ bases, long long* meta, const int64_t* __restrict__ site_pos,
                     int64_t n_sites, int64_t n_reads, uint16_t* __restrict__ counts) {
   extern __shared__ __align__(16) unsigned char ps_smem[];
-  PileStageShared& sh = *reinterpret_cast<PileStageShared*>(ps_smem);
+  PileStageShared<S>& sh = *reinterpret_cast<PileStageShared<S>*>(ps_smem);
   constexpr int kSites = kPS_Threads * S;
   const int lmax = (int)meta[4];
   const long long n_bases = n_reads > 0 ? base_off[n_reads] : 0;
@@ -217,12 +260,11 @@ pileup_stage_kernel(const int64_t* __restrict__ read_start, const int64_t* __res
     if (dense) {
 #pragma unroll 1
       for (int p = 0; p < 3; p++) {
-        uint32_t o01[S], o23[S];
-        ps_person<S>(sh, sh.win[p][0], sh.win[p][1], read_start, base_off, bases, n_bases, P0, my_off, n_live, lmax, o01, o23, bad, over);
+        ps_person<S>(sh, sh.win[p][0], sh.win[p][1], read_start, base_off, bases, n_bases, P0, my_off, n_live, lmax, bad, over);
 #pragma unroll
         for (int k = 0; k < S; k++) {
           const int64_t s = s0 + my_off + k;
-          if (s < n_sites) *reinterpret_cast<uint2*>(counts + s * 12 + p * 4) = make_uint2(o01[k], o23[k]);
+          if (s < n_sites) *reinterpret_cast<uint2*>(counts + s * 12 + p * 4) = sh.tot[k][threadIdx.x];
         }
       }
     } else {
@@ -273,7 +315,7 @@ static cudaError_t launch_pileup_stage(cudaStream_t st, int sms, const int64_t* 
                                        const char* d_bases, long long* meta, const int64_t* d_site_pos, int64_t n_sites,
                                        int64_t n_reads, uint16_t* d_counts) {
   auto kern = pileup_stage_kernel<S>;
-  const size_t smem = sizeof(PileStageShared);
+  const size_t smem = sizeof(PileStageShared<S>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int per_sm = 1;
