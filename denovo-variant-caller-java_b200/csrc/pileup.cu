@@ -49,6 +49,16 @@ pileup_prep_kernel(const int64_t* __restrict__ read_start, const int64_t* __rest
   if ((threadIdx.x & 31) == 0 && lmax > 0) atomicMax(&meta[4], lmax);
 }
 
+// meta[7] = number of places where the candidate positions are not consecutive (0: every tile is a dense tile and
+// the pileup kernel need not look at the positions again)
+__global__ void __launch_bounds__(256)
+pileup_sites_kernel(const int64_t* __restrict__ site_pos, int64_t n_sites, long long* __restrict__ meta) {
+  int breaks = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i + 1 < n_sites; i += (int64_t)gridDim.x * blockDim.x)
+    breaks += __ldg(site_pos + i + 1) != __ldg(site_pos + i) + 1;
+  if (__any_sync(0xffffffffu, breaks != 0) && breaks) atomicAdd((unsigned long long*)&meta[7], (unsigned long long)breaks);
+}
+
 }  // namespace dnv
 
 using namespace dnv;
@@ -72,7 +82,9 @@ int dnv_pileup_device(dnv_ctx* ctx, const int64_t* d_read_start, const int64_t* 
     return DNV_E_INVALID;
   }
   DNV_CUDA(cudaSetDevice(ctx->device));
-  int rc = ensure_scratch(ctx, 64);
+  // scratch: meta[8] (see pileup_prep_kernel), then one record per tile of the pipeline kernel
+  const int64_t n_tiles = (n_sites + kPP_Consumers * 8 - 1) / (kPP_Consumers * 8);
+  int rc = ensure_scratch(ctx, 64 + (size_t)n_tiles * kPP_TileWords * sizeof(long long));
   if (rc) return rc;
   long long* meta = (long long*)ctx->d_scratch;
   DNV_CUDA(cudaMemsetAsync(meta, 0, 64, ctx->stream));
@@ -81,28 +93,22 @@ int dnv_pileup_device(dnv_ctx* ctx, const int64_t* d_read_start, const int64_t* 
   if (n_reads > 0) {
     const int grid = (int)std::min<int64_t>((n_reads + 255) / 256, (int64_t)sms * 8);
     pileup_prep_kernel<<<grid, 256, 0, ctx->stream>>>(d_read_start, d_base_off, d_person, n_reads, meta);
+    const int grid_s = (int)std::min<int64_t>((n_sites + 255) / 256, (int64_t)sms * 8);
+    pileup_sites_kernel<<<grid_s, 256, 0, ctx->stream>>>(d_site_pos, n_sites, meta);
   }
-  // dense tiles: position-major gather (pileup_stage.cuh; 6.9 G sites/s at 30x); DNV_PILEUP_KERNEL=scatter selects the
-  // read-major formulation with shared-memory atomics (pileup_scatter.cuh; 6.3 G sites/s — its tile routine is what the
-  // fused reads -> calls kernel builds on); sparse tiles: one site at a time in either
+  // dense tiles: the producer / consumer pipeline of pileup_pipe.cuh (it bulk-copies slices of read_start / base_off:
+  // 16-byte aligned arrays); otherwise, or with DNV_PILEUP_KERNEL=stage, the position-major gather of
+  // pileup_stage.cuh; DNV_PILEUP_KERNEL=scatter selects the read-major formulation with shared-memory atomics
+  // (pileup_scatter.cuh — its tile routine is what the fused reads -> calls kernel builds on); sparse tiles: one site
+  // at a time in all of them
   static const std::string which = [] { const char* e = getenv("DNV_PILEUP_KERNEL"); return std::string(e ? e : "pipe"); }();
-  static const int stage_s = [] { const char* e = getenv("DNV_PILEUP_S"); return e ? atoi(e) : 16; }();  // sites per thread
-  if (which == "pipe") {
-    if (stage_s == 8) {
-      DNV_CUDA(launch_pileup_pipe<8>(ctx->stream, sms, d_read_start, d_base_off, d_bases, meta, d_site_pos, n_sites, n_reads,
-                                     d_counts_out));
-    } else {
-      DNV_CUDA(launch_pileup_pipe<16>(ctx->stream, sms, d_read_start, d_base_off, d_bases, meta, d_site_pos, n_sites, n_reads,
-                                      d_counts_out));
-    }
-  } else if (which == "stage") {
-    if (stage_s == 8) {
-      DNV_CUDA(launch_pileup_stage<8>(ctx->stream, sms, d_read_start, d_base_off, d_bases, meta, d_site_pos, n_sites, n_reads,
-                                      d_counts_out));
-    } else {
-      DNV_CUDA(launch_pileup_stage<16>(ctx->stream, sms, d_read_start, d_base_off, d_bases, meta, d_site_pos, n_sites, n_reads,
-                                       d_counts_out));
-    }
+  const bool aligned16 = ((reinterpret_cast<uintptr_t>(d_read_start) | reinterpret_cast<uintptr_t>(d_base_off)) & 15) == 0;
+  if (which == "pipe" && aligned16) {
+    DNV_CUDA(launch_pileup_pipe<8>(ctx->stream, sms, d_read_start, d_base_off, d_bases, meta, meta + 8, d_site_pos, n_sites,
+                                   n_reads, d_counts_out));
+  } else if (which == "pipe" || which == "stage") {
+    DNV_CUDA(launch_pileup_stage<8>(ctx->stream, sms, d_read_start, d_base_off, d_bases, meta, d_site_pos, n_sites, n_reads,
+                                    d_counts_out));
   } else {
     const int rc2 = launch_pileup_scatter(ctx, ctx->stream, d_read_start, d_base_off, d_bases, meta, d_site_pos, n_sites, n_reads,
                                           d_counts_out);

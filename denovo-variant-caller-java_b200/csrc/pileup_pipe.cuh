@@ -4,22 +4,23 @@
 // Reads are sorted by (person, start) and their alignedSequence strings are concatenated in that order, so the reads
 // that can reach a tile of consecutive positions are ONE contiguous byte range of `bases` per person.  A CTA owns a
 // tile of 128*S consecutive positions at a time (tiles are handed out by a ticket) and has
-//   * ONE PRODUCER WARP: per tile it finds the three read windows (six 32-ary searches, their loads in flight
-//     together); per person it writes the read descriptors (start relative to the tile, offset in the stage, length)
-//     into the descriptor buffer the consumers are NOT reading, waits until they are done with the stage buffer and
-//     starts ONE TMA bulk copy (cp.async.bulk -> mbarrier) of ALL the person's bytes for the tile — every base is
-//     read from HBM once per tile it touches ((tile + read length) / tile of the algorithmic bytes);
+//   * ONE PRODUCER WARP that only moves data: per tile it reads the tile's record (position, density, the three read
+//     windows: pileup_windows_kernel, a pre-pass with one warp per tile), and per person it waits until the consumers
+//     are done with the stage and starts THREE TMA bulk copies (cp.async.bulk -> one mbarrier): ALL the person's bases
+//     for the tile, and the slices of read_start[] and base_off[] that describe them, raw — every base is read from
+//     HBM once per tile it touches ((tile + read length) / tile of the algorithmic bytes);
 //   * FOUR CONSUMER WARPS that never touch global memory on the dense path except to write the counts: a thread owns
 //     S neighbouring sites, binary-searches its sub-window of the staged reads and per read takes S+4 staged bytes as
 //     aligned words + funnel shifts; each base goes through a 256-entry shared-memory LUT whose entry is the
 //     increment of a packed accumulator (6-bit lanes A, C, G, T and "not a base" — anything outside {A,C,G,T,-}: the
-//     reference's IllegalArgumentException, M/ReadSummary.java:55), flushed into 16-bit totals every 63 reads.
+//     reference's IllegalArgumentException, M/ReadSummary.java:55), flushed into the 16-bit counts every 63 reads.
 // Staging a whole person-tile at once matters: every lane of a warp then walks ITS reads in the same pass (lane
 // efficiency = mean / max trip count, ~0.7); with smaller chunks only the lanes whose windows overlap the chunk work
 // while the warp still runs the longest lane's trip count (0.37-0.5 measured, profiles/r02_pileup_pipe_ncu.md).
-// The stage buffer is single (36 KB: four CTAs per SM cover each other's refills), the descriptors are double
-// buffered; one full / one empty mbarrier hand the stage back and forth, so the consumers' instruction stream has no
-// global-load latency and no CTA-wide barrier in it.  A person-tile that does not fit the stage (deep pileups) is
+// The stage is single buffered (36 KB of bases + 6 KB of descriptors: five CTAs per SM cover each other's refills);
+// one full / one empty mbarrier hand it back and forth, so the consumers' instruction stream has no global-load
+// latency and no CTA-wide barrier in it, and a refill costs one TMA round trip (the two global loads the producer
+// needs for the copy — the byte range of the reads — are issued before it waits for the stage).  A person-tile that does not fit the stage (deep pileups) is
 // cut into chunks of reads; tiles that are not consecutive positions, and reads longer than the stage, take the
 // per-site path (the consumers walk their own windows).  No atomics on the counts, deterministic, counts written once.
 //
@@ -41,28 +42,35 @@ constexpr int kPP_Pad = 64;                             // readable slack on bot
 
 enum { kPP_Dense = 0, kPP_Sparse = 1, kPP_Stop = 2 };
 struct PipeStep {    // what the producer tells the consumers about one step
-  long long s0, P0;  // first site of the tile, its position
+  long long s0;      // first site of the tile
+  int P0_lo;         // low word of the tile's first position (read starts are used relative to it: 32 bits do)
   int n_live;        // sites of the tile
   int person, m;     // dense: person and number of staged reads
   int kind;
   int first, last;   // first / last chunk of this person: zero / write the totals
+  int skip;          // the staged slices of read_start[] / base_off[] begin `skip` (0 / 1) entries before the first read
+  int bias;          // offset of a read's first base in stage[] = low word of its base_off + bias
 };
+// record of a tile (pileup_windows_kernel): [0..5] = per person the first read with start > P0 - lmax and the first
+// with start > P0 + n_live - 1; [6] = P0; [7] = 1 if the tile's positions are consecutive
+constexpr int kPP_TileWords = 8;
 
 template <int S>
 struct PipeShared {
   alignas(128) unsigned char stage[kPP_Pad + kPP_StageBytes + kPP_Pad];
-  int2 desc[2][kPP_ReadCap];    // x = read start - P0; y = offset of the read's first base in stage[] | length << 16
-  uint2 tot[S][kPP_Consumers];  // 16-bit totals (A | C << 16, G | T << 16) of thread t's site k: conflict free
+  alignas(16) long long rs_raw[kPP_ReadCap + 2];  // read_start[] of the staged reads (16-byte aligned slice)
+  alignas(16) long long bo_raw[kPP_ReadCap + 4];  // base_off[] of the staged reads and one more
   uint32_t lut[256];
   PipeStep step[2];
   alignas(8) unsigned long long full, empty;
 };
 
 template <int S>
-__global__ void __launch_bounds__(kPP_Threads, 4)
+__global__ void __launch_bounds__(kPP_Threads, 5)
 pileup_pipe_kernel(const int64_t* __restrict__ read_start, const int64_t* __restrict__ base_off,
-                   const char* __restrict__ bases, long long* meta, const int64_t* __restrict__ site_pos,
-                   int64_t n_sites, int64_t n_reads, uint16_t* __restrict__ counts) {
+                   const char* __restrict__ bases, long long* meta, const long long* __restrict__ tiles,
+                   const int64_t* __restrict__ site_pos, int64_t n_sites, int64_t n_reads,
+                   uint16_t* __restrict__ counts) {
   extern __shared__ __align__(128) unsigned char pp_smem[];
   PipeShared<S>& sh = *reinterpret_cast<PipeShared<S>*>(pp_smem);
   constexpr int kSites = kPP_Consumers * S;
@@ -81,7 +89,6 @@ pileup_pipe_kernel(const int64_t* __restrict__ read_start, const int64_t* __rest
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const bool stageable = lmax > 0 && lmax <= min(kPP_StageBytes - 16, 0xFFFF);
   uint32_t it = 0;  // steps so far: descriptor buffer it & 1, barrier phase it & 1
 
   if (warp == kPP_Consumers / 32) {
@@ -90,98 +97,112 @@ pileup_pipe_kernel(const int64_t* __restrict__ read_start, const int64_t* __rest
     // free buffer, so their latency overlaps the consumers' work on the buffers already filled.
     const uintptr_t bases_abs = reinterpret_cast<uintptr_t>(bases);
     const int chunk_reads = min(kPP_ReadCap, (kPP_StageBytes - 16) / max(lmax, 1));
-    int64_t s0 = 0, P0 = 0, win[6] = {0, 0, 0, 0, 0, 0}, c0 = 0, c_first = 0, c_last = 0;
-    int n_live = 0, p = 0;
-    bool dense = false;
-    auto next_tile = [&]() -> bool {
+    struct TileInfo { int64_t s0, P0, win[6]; int n_live; bool dense; };
+    auto fetch = [&](TileInfo& t) -> bool {  // ticket + one round trip for the tile's record
       long long tile = 0;
       if (lane == 0) tile = (long long)atomicAdd((unsigned long long*)&meta[6], 1ull);
       tile = __shfl_sync(kFull, tile, 0);
       if (tile >= n_tiles) return false;
-      s0 = tile * kSites;
-      n_live = (int)min((int64_t)kSites, n_sites - s0);
-      P0 = __ldg(site_pos + s0);
-      // windows of reads per person: start in (P0 - lmax, P0 + n_live - 1]; the six searches run together
-      ps_warp_upper_bound6(read_start, meta, P0 - lmax, P0 + n_live - 1, lane, win);
-      // strictly increasing positions with last - first == n - 1  <=>  consecutive
-      dense = stageable && __ldg(site_pos + s0 + n_live - 1) - P0 == n_live - 1;
-      if (dense) {
-        int ok = 1;
-#pragma unroll 8
-        for (int i = lane; i < n_live - 1; i += 32) ok &= __ldg(site_pos + s0 + i + 1) > __ldg(site_pos + s0 + i);
-        dense = __all_sync(kFull, ok);
-      }
-      p = 0;
-      c0 = c_first = win[0];
-      c_last = win[1];
+      t.s0 = tile * kSites;
+      t.n_live = (int)min((int64_t)kSites, n_sites - t.s0);
+      const long long w = lane < kPP_TileWords ? __ldg(tiles + tile * kPP_TileWords + lane) : 0;
+#pragma unroll
+      for (int q = 0; q < 6; q++) t.win[q] = __shfl_sync(kFull, w, q);
+      t.P0 = __shfl_sync(kFull, w, 6);
+      t.dense = __shfl_sync(kFull, w, 7) != 0;
       return true;
     };
-    bool more = next_tile();
+    TileInfo cur, nxt;
+    bool more = fetch(cur);
     while (more) {
-      const int b = (int)(it & 1u);
-      const int m = dense ? (int)min((int64_t)chunk_reads, c_last - c0) : 0;  // may be 0: a person without reads here
-      long long g0 = 0, g1 = 0, a0 = 0;
-      if (m > 0) {
-        g0 = __ldg(base_off + c0);
-        g1 = __ldg(base_off + c0 + m);
-        a0 = g0 - (long long)((bases_abs + (uintptr_t)g0) & 15);  // stage[i] <-> bases[a0 + i], 16-byte aligned
-#pragma unroll 4
-        for (int i = lane; i < m; i += 32) {  // descriptor buffer b: the consumers are at most reading the other one
-          const long long b0 = __ldg(base_off + c0 + i);
-          const int len = (int)(__ldg(base_off + c0 + i + 1) - b0);
-          sh.desc[b][i] = make_int2((int)(__ldg(read_start + c0 + i) - P0), (int)(b0 - a0) | (len << 16));
+      // the steps of this tile: one per person and chunk of reads (at least one per person, even without reads: the
+      // consumers zero and write the counts in it), or a single "sparse tile" step.  The NEXT tile's ticket and
+      // record are fetched after the first step is on its way, while the consumers are busy with it.
+      bool have_nxt = false, more_nxt = false;
+      int p = 0;
+      int64_t c_first = cur.win[0], c_last = cur.win[1], c0 = c_first;
+      for (int k = 0, tile_done = 0; !tile_done; k++) {
+        const int b = (int)(it & 1u);
+        const int m = cur.dense ? (int)min((int64_t)chunk_reads, c_last - c0) : 0;
+        long long g0 = 0, g1 = 0;
+        if (m > 0) {  // the byte range of the reads: in flight while we wait for the stage
+          g0 = __ldg(base_off + c0);
+          g1 = __ldg(base_off + c0 + m);
         }
-      }
-      mbar_wait(&sh.empty, (it & 1u) ^ 1u);  // the consumers are done with the previous step: the stage is free
-      if (!dense) {
-        if (lane == 0) {
-          sh.step[b] = PipeStep{s0, P0, n_live, 0, 0, kPP_Sparse, 1, 1};
-          mbar_arrive(&sh.full);
+        if (!have_nxt && k > 0) {
+          more_nxt = fetch(nxt);
+          have_nxt = true;
         }
-      } else {
-        const int n16 = m > 0 ? (int)((g1 - a0 + 15) >> 4) : 0;
-        // the first / last 16 bytes of the buffer may straddle its ends: byte loads inside [0, n_bases) for those
-        int v_lo = 0, v_hi = n16;
-        if (n16 > 0 && a0 < 0) v_lo = 1;
-        if (n16 > v_lo && a0 + 16ll * n16 > n_bases) v_hi = n16 - 1;
-        if (lane < 16) {
-          if (v_lo == 1) {
-            const long long gb = a0 + lane;
-            sh.stage[kPP_Pad + lane] = (gb >= 0 && gb < n_bases) ? (unsigned char)__ldg(bases + gb) : (unsigned char)'-';
-          }
-          if (v_hi < n16 && v_hi >= v_lo) {
-            const long long gb = a0 + 16ll * v_hi + lane;
-            sh.stage[kPP_Pad + 16 * v_hi + lane] = (gb >= 0 && gb < n_bases) ? (unsigned char)__ldg(bases + gb) : (unsigned char)'-';
-          }
-        }
-        __syncwarp();  // the lanes' descriptor and edge writes happen before lane 0's release below
-        if (lane == 0) {
-          sh.step[b] = PipeStep{s0, P0, n_live, p, m, kPP_Dense, c0 == c_first ? 1 : 0, c0 + m >= c_last ? 1 : 0};
-          const uint32_t tx = v_hi > v_lo ? (uint32_t)(v_hi - v_lo) * 16u : 0u;
-          if (tx) {
-            mbar_expect_tx(&sh.full, tx);
-            tma_bulk_g2s(sh.stage + kPP_Pad + 16 * v_lo, bases + a0 + 16ll * v_lo, tx, &sh.full);
-          } else {
+        mbar_wait(&sh.empty, (it & 1u) ^ 1u);  // the consumers are done with the previous step: the stage is free
+        if (!cur.dense) {
+          if (lane == 0) {
+            sh.step[b] = PipeStep{cur.s0, (int)cur.P0, cur.n_live, 0, 0, kPP_Sparse, 1, 1, 0, 0};
             mbar_arrive(&sh.full);
           }
-        }
-      }
-      it++;
-      // advance: next chunk, next person (at least one step each, even without reads: the consumers zero and write
-      // the totals in it), next tile
-      if (!dense) {
-        more = next_tile();
-      } else {
-        c0 += m;
-        if (c0 >= c_last) {
-          if (++p == 3) {
-            more = next_tile();
-          } else {
-            c0 = c_first = p == 1 ? win[2] : win[4];
-            c_last = p == 1 ? win[3] : win[5];
+          tile_done = 1;
+        } else {
+          const int align = (int)((bases_abs + (uintptr_t)g0) & 15);
+          const long long a0 = g0 - align;  // stage[i] <-> bases[a0 + i], 16-byte aligned
+          const int n16 = m > 0 ? (int)((g1 - a0 + 15) >> 4) : 0;
+          // the first / last 16 bytes of the buffer may straddle its ends: byte loads inside [0, n_bases) for those
+          int v_lo = 0, v_hi = n16;
+          if (n16 > 0 && a0 < 0) v_lo = 1;
+          if (n16 > v_lo && a0 + 16ll * n16 > n_bases) v_hi = n16 - 1;
+          if (lane < 16) {
+            if (v_lo == 1) {
+              const long long gb = a0 + lane;
+              sh.stage[kPP_Pad + lane] = (gb >= 0 && gb < n_bases) ? (unsigned char)__ldg(bases + gb) : (unsigned char)'-';
+            }
+            if (v_hi < n16 && v_hi >= v_lo) {
+              const long long gb = a0 + 16ll * v_hi + lane;
+              sh.stage[kPP_Pad + 16 * v_hi + lane] = (gb >= 0 && gb < n_bases) ? (unsigned char)__ldg(bases + gb) : (unsigned char)'-';
+            }
+          }
+          // descriptor slices: entries [ce, ce + n) of read_start[] and [ce, ce + n + ...) of base_off[], ce even
+          // (the arrays are 16-byte aligned: launch_pileup_pipe checks); a pair that would straddle the end of an
+          // array is loaded by hand
+          const int skip = (int)(c0 & 1);
+          const int64_t ce = c0 - skip;
+          int n_rs = m > 0 ? (skip + m + 1) & ~1 : 0;      // entries ce .. ce + n_rs - 1 cover reads c0 .. c0 + m - 1
+          int n_bo = m > 0 ? (skip + m + 2) & ~1 : 0;      // ... and base_off[c0 + m]
+          if (ce + n_rs > n_reads) {
+            n_rs -= 2;
+            if (lane < 2) sh.rs_raw[n_rs + lane] = ce + n_rs + lane < n_reads ? __ldg(read_start + ce + n_rs + lane) : 0;
+          }
+          if (ce + n_bo > n_reads + 1) {
+            n_bo -= 2;
+            if (lane < 2) sh.bo_raw[n_bo + lane] = ce + n_bo + lane < n_reads + 1 ? __ldg(base_off + ce + n_bo + lane) : 0;
+          }
+          __syncwarp();  // the lanes' edge writes happen before lane 0's release below
+          if (lane == 0) {
+            sh.step[b] = PipeStep{cur.s0, (int)cur.P0, cur.n_live, p, m, kPP_Dense, c0 == c_first ? 1 : 0,
+                                  c0 + m >= c_last ? 1 : 0, skip, align - (int)g0};
+            const uint32_t tx_b = v_hi > v_lo ? (uint32_t)(v_hi - v_lo) * 16u : 0u;
+            const uint32_t tx = tx_b + (uint32_t)(n_rs + n_bo) * 8u;
+            if (tx) {
+              mbar_expect_tx(&sh.full, tx);
+              if (tx_b) tma_bulk_g2s(sh.stage + kPP_Pad + 16 * v_lo, bases + a0 + 16ll * v_lo, tx_b, &sh.full);
+              if (n_rs) tma_bulk_g2s(sh.rs_raw, read_start + ce, (uint32_t)n_rs * 8u, &sh.full);
+              if (n_bo) tma_bulk_g2s(sh.bo_raw, base_off + ce, (uint32_t)n_bo * 8u, &sh.full);
+            } else {
+              mbar_arrive(&sh.full);
+            }
+          }
+          c0 += m;
+          if (c0 >= c_last) {
+            if (++p == 3) {
+              tile_done = 1;
+            } else {
+              c0 = c_first = p == 1 ? cur.win[2] : cur.win[4];
+              c_last = p == 1 ? cur.win[3] : cur.win[5];
+            }
           }
         }
+        it++;
       }
+      if (!have_nxt) more_nxt = fetch(nxt);
+      cur = nxt;
+      more = more_nxt;
     }
     mbar_wait(&sh.empty, (it & 1u) ^ 1u);
     if (lane == 0) {
@@ -198,17 +219,26 @@ pileup_pipe_kernel(const int64_t* __restrict__ read_start, const int64_t* __rest
   uint32_t acc[S];
   uint32_t badacc = 0;
   int since_flush = 0, visits = 0;
-  auto flush = [&]() {  // 6-bit lanes -> this thread's 16-bit totals in shared memory (once per 63 visits)
+  bool wrote = false;  // this person's counts of my sites are in global memory already (more than 63 reads over them)
+  // 6-bit lanes -> 16-bit totals (A | C << 16, G | T << 16), straight into the output: a plain store the first time
+  // (the usual case: once per person), my own read-modify-write after that (every 63 visits of a deep pileup)
+  auto flush = [&](int64_t s0, int p, int lim) {
 #pragma unroll
     for (int k = 0; k < S; k++) {
       const uint32_t a = acc[k];
-      uint2 t = sh.tot[k][threadIdx.x];
-      t.x += (a & 0x3Fu) | ((a << 10) & 0x3F0000u);
-      t.y += ((a >> 12) & 0x3Fu) | ((a >> 2) & 0x3F0000u);
-      sh.tot[k][threadIdx.x] = t;
+      if (k < lim) {
+        uint2* dst = reinterpret_cast<uint2*>(counts + (s0 + my_off + k) * 12 + p * 4);
+        uint2 t = make_uint2(0u, 0u);
+        if (wrote) t = *dst;
+        t.x += (a & 0x3Fu) | ((a << 10) & 0x3F0000u);
+        t.y += ((a >> 12) & 0x3Fu) | ((a >> 2) & 0x3F0000u);
+        *dst = t;
+      }
       badacc |= a >> 24;
       acc[k] = 0;
     }
+    wrote = true;
+    visits += since_flush;
     since_flush = 0;
   };
 #pragma unroll
@@ -268,28 +298,32 @@ pileup_pipe_kernel(const int64_t* __restrict__ read_start, const int64_t* __rest
     const int is_last = sh.step[b].last;
     if (sh.step[b].first) {
 #pragma unroll
-      for (int k = 0; k < S; k++) { acc[k] = 0; sh.tot[k][threadIdx.x] = make_uint2(0u, 0u); }
-      badacc = 0; since_flush = 0; visits = 0;
+      for (int k = 0; k < S; k++) acc[k] = 0;
+      badacc = 0; since_flush = 0; visits = 0; wrote = false;
     }
     {
-      const int2* desc_b = sh.desc[b];
-      const uint32_t stage_s = smem_u32(sh.stage + kPP_Pad);
+      const int skip = sh.step[b].skip;
+      const int P0_lo = sh.step[b].P0_lo;
+      const int* rs_lo = reinterpret_cast<const int*>(sh.rs_raw + skip);  // low words: entry j at [2 * j]
+      const int* bo_lo = reinterpret_cast<const int*>(sh.bo_raw + skip);
+      const uint32_t stage_s = smem_u32(sh.stage + kPP_Pad) + (uint32_t)sh.step[b].bias;
       const int lim = n_live - my_off;  // my sites at or past it are not requested (last, partial tile)
       int lo = 0, hi = m;  // first staged read with rel > my_off - lmax (earlier ones end before my first site)
       const int key = my_off - lmax;
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (desc_b[mid].x <= key) lo = mid + 1; else hi = mid;
+        if (rs_lo[2 * mid] - P0_lo <= key) lo = mid + 1; else hi = mid;
       }
       for (int j = lo; j < m; j++) {
-        const int2 d = desc_b[j];
-        if (d.x > my_off + S - 1) break;
-        const int q = my_off - d.x;  // offset of my first site inside the read (M/ReadSummary.java:48)
-        const int len = (int)((uint32_t)d.y >> 16);
+        const int rel = rs_lo[2 * j] - P0_lo;
+        if (rel > my_off + S - 1) break;
+        const int q = my_off - rel;  // offset of my first site inside the read (M/ReadSummary.java:48)
+        const int b0 = bo_lo[2 * j];
+        const int len = bo_lo[2 * j + 2] - b0;
         if (q >= len) continue;      // read ends before my first site
-        const int addr = (d.y & 0xFFFF) + q;  // >= -(S-1): inside the front pad
-        const uint32_t wa = stage_s + (uint32_t)(addr & ~3);
-        const uint32_t shft = ((uint32_t)addr & 3u) * 8u;
+        const uint32_t addr = stage_s + (uint32_t)(b0 + q);  // >= -(S-1) from the staged bytes: inside the front pad
+        const uint32_t wa = addr & ~3u;
+        const uint32_t shft = (addr & 3u) * 8u;
         uint32_t x[NW + 1], w[NW];
 #pragma unroll
         for (int i = 0; i <= NW; i++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x[i]) : "r"(wa + 4 * i));
@@ -320,18 +354,12 @@ pileup_pipe_kernel(const int64_t* __restrict__ read_start, const int64_t* __rest
             acc[4 * i + k] += e;
           }
         }
-        visits++;
-        if (++since_flush >= 63) flush();
+        if (++since_flush >= 63) flush(s0, p, lim);
       }
     }
     mbar_arrive(&sh.empty);  // my last read of the stage and of this step's descriptors is behind me
     if (is_last) {
-      flush();
-#pragma unroll
-      for (int k = 0; k < S; k++) {
-        if (my_off + k < n_live)
-          *reinterpret_cast<uint2*>(counts + (s0 + my_off + k) * 12 + p * 4) = sh.tot[k][threadIdx.x];
-      }
+      flush(s0, p, n_live - my_off);
       if (badacc != 0 && my_off < n_live) {
         atomicMax((unsigned long long*)&meta[5], pileup_err(s0 + my_off, true, kPileErrBadBase));
       } else if (visits > 65535 && my_off < n_live) {  // a 16-bit total could have wrapped: fail loudly
@@ -341,10 +369,39 @@ pileup_pipe_kernel(const int64_t* __restrict__ read_start, const int64_t* __rest
   }
 }
 
+// pre-pass: one warp per tile writes the tile's record (kPP_TileWords words)
+__global__ void __launch_bounds__(256)
+pileup_windows_kernel(const int64_t* __restrict__ read_start, const long long* __restrict__ meta,
+                      const int64_t* __restrict__ site_pos, int64_t n_sites, int tile_sites, int stage_limit,
+                      long long* __restrict__ tiles) {
+  const int lane = threadIdx.x & 31;
+  const int64_t tile = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_tiles = (n_sites + tile_sites - 1) / tile_sites;
+  if (tile >= n_tiles) return;
+  const int lmax = (int)meta[4];
+  const int64_t s0 = tile * tile_sites;
+  const int n_live = (int)min((int64_t)tile_sites, n_sites - s0);
+  const int64_t P0 = __ldg(site_pos + s0);
+  int64_t win[6];
+  ps_warp_upper_bound6(read_start, meta, P0 - lmax, P0 + n_live - 1, lane, win);
+  // strictly increasing positions with last - first == n - 1  <=>  consecutive; meta[7] == 0: all of them are
+  bool dense = lmax > 0 && lmax <= stage_limit;
+  if (dense && meta[7] != 0) {
+    int ok = __ldg(site_pos + s0 + n_live - 1) - P0 == n_live - 1;
+    for (int i = lane; i < n_live - 1; i += 32) ok &= __ldg(site_pos + s0 + i + 1) > __ldg(site_pos + s0 + i);
+    dense = __all_sync(0xffffffffu, ok);
+  }
+  long long w = lane == 6 ? P0 : lane == 7 ? (dense ? 1 : 0) : 0;
+#pragma unroll
+  for (int q = 0; q < 6; q++) w = lane == q ? win[q] : w;
+  if (lane < kPP_TileWords) tiles[tile * kPP_TileWords + lane] = w;
+}
+
+// The pipeline kernel wants 16-byte aligned read_start / base_off (its bulk copies of their slices).
 template <int S>
 static cudaError_t launch_pileup_pipe(cudaStream_t st, int sms, const int64_t* d_read_start, const int64_t* d_base_off,
-                                      const char* d_bases, long long* meta, const int64_t* d_site_pos, int64_t n_sites,
-                                      int64_t n_reads, uint16_t* d_counts) {
+                                      const char* d_bases, long long* meta, long long* tiles, const int64_t* d_site_pos,
+                                      int64_t n_sites, int64_t n_reads, uint16_t* d_counts) {
   auto kern = pileup_pipe_kernel<S>;
   const size_t smem = sizeof(PipeShared<S>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -352,9 +409,13 @@ static cudaError_t launch_pileup_pipe(cudaStream_t st, int sms, const int64_t* d
   int per_sm = 1;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kPP_Threads, smem);
   if (e != cudaSuccess) return e;
-  const int64_t n_tiles = (n_sites + kPP_Consumers * S - 1) / (kPP_Consumers * S);
+  constexpr int kSites = kPP_Consumers * S;
+  const int64_t n_tiles = (n_sites + kSites - 1) / kSites;
+  const int64_t wblocks = (n_tiles * 32 + 255) / 256;
+  pileup_windows_kernel<<<(unsigned)wblocks, 256, 0, st>>>(d_read_start, meta, d_site_pos, n_sites, kSites,
+                                                           std::min(kPP_StageBytes - 16, 0x7FFFFFFF), tiles);
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)sms * std::max(per_sm, 1)));
-  kern<<<grid, kPP_Threads, smem, st>>>(d_read_start, d_base_off, d_bases, meta, d_site_pos, n_sites, n_reads, d_counts);
+  kern<<<grid, kPP_Threads, smem, st>>>(d_read_start, d_base_off, d_bases, meta, tiles, d_site_pos, n_sites, n_reads, d_counts);
   return cudaGetLastError();
 }
 

@@ -26,6 +26,25 @@ def test_pileup_dense_sites(var_len):
     assert got[0].sum() == 0 and got[-50:].sum() == 0 and 15 < got[500:2500].sum(axis=2).mean() < 35
 
 
+def test_pileup_device_arrays_that_are_only_8_byte_aligned():
+    """The pipeline kernel bulk-copies slices of read_start / base_off and wants them 16-byte aligned; arrays that are
+    only 8-byte aligned (a view one element into a buffer) take the gather kernel: same counts."""
+    import torch
+    rs, bo, ba, pe = S.make_reads(31, 5000, 4000, depth=30)
+    pos = np.arange(4900, 9100, dtype=np.int64)
+    rc, want = O.pileup(rs, bo, ba, pe, pos)
+    assert rc == 0
+    with D.TrioEngine() as eng:
+        pad = lambda a: torch.from_numpy(np.concatenate([a[:1], a])).cuda()[1:]
+        d_rs, d_bo = pad(rs), pad(bo)
+        assert d_rs.data_ptr() % 16 == 8 and d_bo.data_ptr() % 16 == 8
+        d_ba, d_pe, d_pos = (torch.from_numpy(x).cuda() for x in (ba, pe, pos))
+        out = torch.zeros((len(pos), 12), dtype=torch.int16, device="cuda")
+        eng.pileup_device(d_rs, d_bo, d_ba, d_pe, len(rs), d_pos, len(pos), out)
+        got = out.cpu().numpy().view(np.uint16).reshape(len(pos), 3, 4)
+    assert np.array_equal(got, want)
+
+
 def test_pileup_sparse_sites_and_edges():
     rs, bo, ba, pe = S.make_reads(12, 100000, 20000, depth=200, read_len=150, gap_rate=0.01)
     rng = np.random.default_rng(1)
@@ -84,19 +103,21 @@ def test_pileup_dense_bad_base_only_at_requested_sites(n_sites):
         assert ei.value.code == D.DNV_E_BADBASE
 
 
-@pytest.mark.parametrize("kernel", ["scatter", "stage"])
-def test_both_pileup_kernels_dense_and_ragged(kernel, monkeypatch):
-    """The read-major scatter kernel (default) and the position-major gather kernel (DNV_PILEUP_KERNEL=stage) are
-    both bit-exact against the oracle: dense sites, variable-length reads, 200x depth (several rounds of 255 reads),
-    gaps, an uncovered flank, a site count that is not a multiple of the tile."""
+@pytest.mark.parametrize("kernel", ["pipe", "scatter", "stage"])
+def test_all_pileup_kernels_dense_and_ragged(kernel, monkeypatch):
+    """The producer / consumer pipeline (default), the read-major scatter kernel (DNV_PILEUP_KERNEL=scatter) and the
+    position-major gather kernel (=stage) are all bit-exact against the oracle: dense sites, variable-length reads,
+    200x depth (person-tiles cut into several chunks of reads / several rounds of 255 reads), gaps, an uncovered flank,
+    a site count that is not a multiple of the tile, reads that end with the arrays."""
     import subprocess, sys, os
     code = r"""
 import sys, numpy as np
 sys.path.insert(0, "tests")
 import denovo_b200 as D, oracle_lib as O, synth_inputs as S
-for seed, depth, rl, var in ((21, 30, 100, False), (22, 200, 150, True), (23, 8, 37, True)):
+for seed, depth, rl, var, first in ((21, 30, 100, False, 4800), (22, 200, 150, True, 4800), (23, 8, 37, True, 4800),
+                                    (24, 30, 100, False, 5100), (25, 31, 99, True, 5101), (26, 700, 100, False, 5500)):
     rs, bo, ba, pe = S.make_reads(seed, 5000, 2500, depth=depth, read_len=rl, gap_rate=5e-3, var_len=var)
-    pos = np.arange(4800, 7777, dtype=np.int64)
+    pos = np.arange(first, 7777, dtype=np.int64)
     rc, want = O.pileup_sorted(rs, bo, ba, pe, pos)
     assert rc == 0
     with D.TrioEngine() as eng:
