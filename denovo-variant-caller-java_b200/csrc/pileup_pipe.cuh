@@ -57,10 +57,12 @@ constexpr int kPP_TileWords = 8;
 
 template <int S>
 struct PipeShared {
+  static_assert(S == 8, "the edge-mask table is for 8-site windows");
   alignas(128) unsigned char stage[kPP_Pad + kPP_StageBytes + kPP_Pad];
   alignas(16) long long rs_raw[kPP_ReadCap + 2];  // read_start[] of the staged reads (16-byte aligned slice)
   alignas(16) long long bo_raw[kPP_ReadCap + 4];  // base_off[] of the staged reads and one more
   uint32_t lut[256];
+  unsigned long long keep[8][9];  // keep[t_lo][t_hi]: 0xFF in bytes t_lo <= k < t_hi of an 8-byte window
   PipeStep step[2];
   alignas(8) unsigned long long full, empty;
 };
@@ -83,6 +85,11 @@ pileup_pipe_kernel(const int64_t* __restrict__ read_start, const int64_t* __rest
   for (int i = threadIdx.x; i < 256; i += kPP_Threads)
     sh.lut[i] = i == 'A' ? 1u : i == 'C' ? 1u << 6 : i == 'G' ? 1u << 12 : i == 'T' ? 1u << 18
               : i == '-' ? 0u : 1u << 24;
+  for (int i = threadIdx.x; i < 72; i += kPP_Threads) {
+    const int t_lo = i / 9, t_hi = i % 9;
+    const unsigned long long below_hi = t_hi >= 8 ? ~0ull : ~(~0ull << (8 * t_hi));
+    sh.keep[t_lo][t_hi] = t_hi > t_lo ? (below_hi & (~0ull << (8 * t_lo))) : 0ull;
+  }
   if (threadIdx.x == 0) {
     mbar_init(&sh.full, 1);
     mbar_init(&sh.empty, kPP_Consumers);
@@ -314,52 +321,61 @@ pileup_pipe_kernel(const int64_t* __restrict__ read_start, const int64_t* __rest
         const int mid = (lo + hi) >> 1;
         if (rs_lo[2 * mid] - P0_lo <= key) lo = mid + 1; else hi = mid;
       }
-      for (int j = lo; j < m; j++) {
-        const int rel = rs_lo[2 * j] - P0_lo;
-        if (rel > my_off + S - 1) break;
-        const int q = my_off - rel;  // offset of my first site inside the read (M/ReadSummary.java:48)
-        const int b0 = bo_lo[2 * j];
-        const int len = bo_lo[2 * j + 2] - b0;
-        if (q >= len) continue;      // read ends before my first site
-        const uint32_t addr = stage_s + (uint32_t)(b0 + q);  // >= -(S-1) from the staged bytes: inside the front pad
-        const uint32_t wa = addr & ~3u;
-        const uint32_t shft = (addr & 3u) * 8u;
-        uint32_t x[NW + 1], w[NW];
+      // The descriptors of the next read are fetched while this one is processed (no load latency in front of the
+      // two tests), and base_off of the next read is this read's end.  Blocks of at most 63 iterations: the 6-bit
+      // lanes cannot overflow inside one, so the loop itself carries no flush counter.
+      const uint32_t keep_s = smem_u32(sh.keep);
+      int rel_n = rs_lo[2 * lo] - P0_lo, b0_n = bo_lo[2 * lo], b1_n = bo_lo[2 * lo + 2];
+      int skipped = 0;
+      bool done = false;
+      for (int jb = lo; jb < m && !done; jb += 63) {
+        const int je = min(jb + 63, m);
+        int j = jb;
+        for (; j < je; j++) {
+          const int rel = rel_n, b0 = b0_n, b1 = b1_n;
+          rel_n = rs_lo[2 * j + 2] - P0_lo;  // (one entry past the last read at the end: inside the arrays, unused)
+          b0_n = b1;
+          b1_n = bo_lo[2 * j + 4];
+          if (rel > my_off + S - 1) { done = true; break; }
+          const int q = my_off - rel;  // offset of my first site inside the read (M/ReadSummary.java:48)
+          const int len = b1 - b0;
+          if (q >= len) { skipped++; continue; }  // read ends before my first site
+          const uint32_t addr = stage_s + (uint32_t)(b0 + q);  // >= -(S-1) from the staged bytes: inside the front pad
+          const uint32_t wa = addr & ~3u;
+          const uint32_t shft = (addr & 3u) * 8u;
+          uint32_t x[NW + 1], w[NW];
 #pragma unroll
-        for (int i = 0; i <= NW; i++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x[i]) : "r"(wa + 4 * i));
+          for (int i = 0; i <= NW; i++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x[i]) : "r"(wa + 4 * i));
 #pragma unroll
-        for (int i = 0; i < NW; i++) w[i] = __funnelshift_r(x[i], x[i + 1], shft);
-        // bytes of my window outside [0, len) of this read are not its bases, and window positions at or past
-        // n_live (last, partial tile) are not requested sites — the reference only looks at the base AT a
-        // candidate position (M/ReadSummary.java:48-55), so an 'N' next to the last site must not fail the
-        // batch: turn both kinds into '-' (branch free).  t_lo in [0, S-1], t_hi <= S (<= 0: nothing of mine)
-        const int t_lo = max(0, -q), t_hi = min(min(S, len - q), lim);
+          for (int i = 0; i < NW; i++) w[i] = __funnelshift_r(x[i], x[i + 1], shft);
+          // bytes of my window outside [0, len) of this read are not its bases, and window positions at or past
+          // n_live (last, partial tile) are not requested sites — the reference only looks at the base AT a
+          // candidate position (M/ReadSummary.java:48-55), so an 'N' next to the last site must not fail the
+          // batch: turn both kinds into '-' (branch free, one table look-up).  t_lo in [0, 7], t_hi in [0, 8]
+          const int t_lo = max(0, -q), t_hi = max(min(min(S, len - q), lim), 0);
+          uint32_t k0, k1;
+          asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(k0), "=r"(k1) : "r"(keep_s + (uint32_t)(t_lo * 9 + t_hi) * 8u));
+          w[0] = (w[0] & k0) | (0x2D2D2D2Du & ~k0);
+          w[1] = (w[1] & k1) | (0x2D2D2D2Du & ~k1);
 #pragma unroll
-        for (int i = 0; i < NW; i += 2) {  // 8 window bytes at a time as one 64-bit mask
-          const int a = min(max(t_lo - 4 * i, 0), 8), e = min(max(t_hi - 4 * i, 0), 8);
-          const unsigned long long from = a >= 8 ? 0ull : ~0ull << (8 * a);
-          const unsigned long long to = e >= 8 ? ~0ull : ~(~0ull << (8 * e));
-          const unsigned long long keep = from & to;
-          const uint32_t k0 = (uint32_t)keep, k1 = (uint32_t)(keep >> 32);
-          w[i] = (w[i] & k0) | (0x2D2D2D2Du & ~k0);
-          w[i + 1] = (w[i + 1] & k1) | (0x2D2D2D2Du & ~k1);
-        }
+          for (int i = 0; i < NW; i++) {
 #pragma unroll
-        for (int i = 0; i < NW; i++) {
-#pragma unroll
-          for (int k = 0; k < 4; k++) {
-            const uint32_t byte = __byte_perm(w[i], 0, 0x4440 + k);  // PRMT: byte k, zero extended
-            uint32_t e;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(lut_s + byte * 4u));  // '-' adds nothing (:51-53)
-            acc[4 * i + k] += e;
+            for (int k = 0; k < 4; k++) {
+              const uint32_t byte = __byte_perm(w[i], 0, 0x4440 + k);  // PRMT: byte k, zero extended
+              uint32_t e;
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(lut_s + byte * 4u));  // '-' adds nothing (:51-53)
+              acc[4 * i + k] += e;
+            }
           }
         }
-        if (++since_flush >= 63) flush(s0, p, lim);
+        since_flush = j - jb;
+        if (!done && je < m) flush(s0, p, lim);  // more reads to come in this step
       }
+      visits -= skipped;
     }
     mbar_arrive(&sh.empty);  // my last read of the stage and of this step's descriptors is behind me
+    flush(s0, p, n_live - my_off);  // every step ends with empty lanes (a person has several only in deep pileups)
     if (is_last) {
-      flush(s0, p, n_live - my_off);
       if (badacc != 0 && my_off < n_live) {
         atomicMax((unsigned long long*)&meta[5], pileup_err(s0 + my_off, true, kPileErrBadBase));
       } else if (visits > 65535 && my_off < n_live) {  // a 16-bit total could have wrapped: fail loudly
