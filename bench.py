@@ -305,13 +305,38 @@ def aux_mendel(D, torch, np, local):
             "bit_exact_vs_oracle_block": ok}
 
 
-def aux_pileup(D, torch, np, local, n_sites=2_000_000):
+def tile_reads(np, rs, bo, ba, pe, span, reps):
+    """`reps` copies of a read set side by side on the position axis (copy k shifted by k * span), still sorted by
+    (person, start): a large input without generating every base on the CPU."""
+    lens = np.diff(bo)
+    out_rs, out_len, out_ba, out_pe = [], [], [], []
+    for p in range(3):
+        sel = np.nonzero(pe == p)[0]
+        if len(sel) == 0:
+            continue
+        lo0, hi = sel[0], sel[-1] + 1
+        first_pos = int(rs[lo0:hi].max()) - span + 1   # copies after the first keep the reads that start at or after
+        for k in range(reps):                          # their own first position: the concatenation stays sorted
+            lo = lo0 if k == 0 else lo0 + int(np.searchsorted(rs[lo0:hi], max(first_pos, 1), side="left"))
+            out_rs.append(rs[lo:hi] + k * span)
+            out_len.append(lens[lo:hi])
+            out_ba.append(ba[bo[lo]:bo[hi]])
+            out_pe.append(pe[lo:hi])
+    rs2, ba2, pe2 = np.concatenate(out_rs), np.concatenate(out_ba), np.concatenate(out_pe)
+    bo2 = np.zeros(len(rs2) + 1, np.int64)
+    np.cumsum(np.concatenate(out_len), out=bo2[1:])
+    return rs2, bo2, ba2, pe2
+
+
+def aux_pileup(D, torch, np, local, n_sites=8_000_000, reps=4):
     """Secondary metric of SURVEY.md 8(d): reads -> counts (pileup kernel) and reads -> counts -> calls chained on
-    the device, every-position layout, 30x, read length 100."""
+    the device, every-position layout, 30x, read length 100 (8 M positions: four copies of a 2 M-position read set
+    side by side)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
     import synth_inputs as S
-    rs, bo, ba, pe = S.make_reads(41, 1, n_sites, depth=DEPTH)
+    rs, bo, ba, pe = S.make_reads(41, 1, n_sites // reps, depth=DEPTH)
+    rs, bo, ba, pe = tile_reads(np, rs, bo, ba, pe, n_sites // reps, reps)
     pos = np.arange(1, n_sites + 1, dtype=np.int64)
     stream = torch.cuda.Stream(device=local)
     with D.TrioEngine(device=local) as eng:
@@ -329,10 +354,14 @@ def aux_pileup(D, torch, np, local, n_sites=2_000_000):
             eng.pileup_device(d[0], d[1], d[2], d[3], len(rs), d[4], n_sites, d_counts)
             chain["calls"] = eng.infer_device(d_counts, n_sites, d_calls, cap)
 
-        def fused():
+        def reads_api():  # dnv_infer_reads_device: pileup pipeline chained to the READ pipeline inside the library
+            chain["api_calls"] = eng.infer_reads_device(d[0], d[1], d[2], d[3], len(rs), d[4], n_sites, d_calls, cap)
+
+        def fused():      # the same entry point with the single fused kernel (DNV_READS_FUSED=1)
             chain["fused_calls"] = eng.infer_reads_device(d[0], d[1], d[2], d[3], len(rs), d[4], n_sites, d_calls, cap)
         times = []
-        for fn in (pile, both, fused):
+        for fn in (pile, both, reads_api, fused):
+            os.environ["DNV_READS_FUSED"] = "1" if fn is fused else "0"
             with torch.cuda.stream(stream):
                 for _ in range(3):
                     fn()
@@ -344,6 +373,8 @@ def aux_pileup(D, torch, np, local, n_sites=2_000_000):
                 e1.record(stream)
                 torch.cuda.synchronize()
             times.append(e0.elapsed_time(e1) / 5)
+        os.environ.pop("DNV_READS_FUSED", None)
+        pile()
         got = d_counts.cpu().numpy().view(np.uint16).reshape(n_sites, 3, 4)
     m = 20000
     sel = slice(n_sites // 2, n_sites // 2 + m)
@@ -358,9 +389,10 @@ def aux_pileup(D, torch, np, local, n_sites=2_000_000):
     return {"sites": n_sites, "reads": len(rs), "bases": int(len(ba)), "pileup_ms": times[0], "pileup_sites_per_s": n_sites / times[0] * 1e3,
             "algorithmic_bytes_per_site": alg / n_sites, "algorithmic_GBps": alg / times[0] / 1e6, "frac_of_hbm": alg / times[0] / 1e6 / hbm,
             "bit_exact_vs_oracle_window": bool(rc == 0 and np.array_equal(got[sel], want)),
-            "reads_to_calls_ms": times[1], "reads_to_calls_sites_per_s": n_sites / times[1] * 1e3, "reads_to_calls_calls": int(chain["calls"]),
-            "fused_reads_to_calls_ms": times[2], "fused_reads_to_calls_sites_per_s": n_sites / times[2] * 1e3,
-            "fused_equals_chained": bool(chain["fused_calls"] == chain["calls"])}
+            "pileup_then_infer_two_calls_ms": times[1], "reads_to_calls_calls": int(chain["calls"]),
+            "reads_to_calls_ms": times[2], "reads_to_calls_sites_per_s": n_sites / times[2] * 1e3,
+            "single_kernel_reads_to_calls_ms": times[3], "single_kernel_reads_to_calls_sites_per_s": n_sites / times[3] * 1e3,
+            "all_paths_same_calls": bool(chain["fused_calls"] == chain["calls"] == chain["api_calls"])}
 
 
 def genome_walk(D, torch, np, dist, eng, stream, gather, rank, world, local, chunk=1 << 26, seed=0x5EED0004):

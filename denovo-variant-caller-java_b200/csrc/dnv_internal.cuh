@@ -283,6 +283,19 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
       "DONE_%=:\n"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// the same with a suspend-time hint (ns): the warp sleeps in hardware until the phase completes or the hint expires,
+// instead of re-issuing the test every few cycles and taking issue slots from the warps that have work
+__device__ __forceinline__ void mbar_wait_sleepy(unsigned long long* bar, uint32_t parity, uint32_t hint_ns) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(hint_ns) : "memory");
+}
 __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
                                              unsigned long long* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

@@ -49,16 +49,6 @@ pileup_prep_kernel(const int64_t* __restrict__ read_start, const int64_t* __rest
   if ((threadIdx.x & 31) == 0 && lmax > 0) atomicMax(&meta[4], lmax);
 }
 
-// meta[7] = number of places where the candidate positions are not consecutive (0: every tile is a dense tile and
-// the pileup kernel need not look at the positions again)
-__global__ void __launch_bounds__(256)
-pileup_sites_kernel(const int64_t* __restrict__ site_pos, int64_t n_sites, long long* __restrict__ meta) {
-  int breaks = 0;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i + 1 < n_sites; i += (int64_t)gridDim.x * blockDim.x)
-    breaks += __ldg(site_pos + i + 1) != __ldg(site_pos + i) + 1;
-  if (__any_sync(0xffffffffu, breaks != 0) && breaks) atomicAdd((unsigned long long*)&meta[7], (unsigned long long)breaks);
-}
-
 }  // namespace dnv
 
 using namespace dnv;
@@ -93,8 +83,6 @@ int dnv_pileup_device(dnv_ctx* ctx, const int64_t* d_read_start, const int64_t* 
   if (n_reads > 0) {
     const int grid = (int)std::min<int64_t>((n_reads + 255) / 256, (int64_t)sms * 8);
     pileup_prep_kernel<<<grid, 256, 0, ctx->stream>>>(d_read_start, d_base_off, d_person, n_reads, meta);
-    const int grid_s = (int)std::min<int64_t>((n_sites + 255) / 256, (int64_t)sms * 8);
-    pileup_sites_kernel<<<grid_s, 256, 0, ctx->stream>>>(d_site_pos, n_sites, meta);
   }
   // dense tiles: the producer / consumer pipeline of pileup_pipe.cuh (it bulk-copies slices of read_start / base_off:
   // 16-byte aligned arrays); otherwise, or with DNV_PILEUP_KERNEL=stage, the position-major gather of
@@ -207,8 +195,13 @@ int dnv_infer_reads_device(dnv_ctx* ctx, const int64_t* d_read_start, const int6
     DNV_CUDA(cudaMalloc(&ctx->d_reads_counts, (size_t)n_sites * 24));
     ctx->reads_counts_cap = n_sites;
   }
-  if (!will_screen(ctx, false) || ctx->dense_mode) {
-    // parameters outside the screen's validity, or screen-hostile input: pileup, then the all-sites path
+  // Default: the pileup pipeline into the context's counts buffer, then the READ pipeline on it — fusing the two saves
+  // only the 48 B/site of writing and re-reading the counts (of ~185), while the pileup formulation that CAN be fused
+  // with the screen (read-major scatter, pileup_scatter.cuh) costs 2.4x the instructions of the pipeline kernel.
+  // DNV_READS_FUSED=1 selects the single-kernel variant (pileup_screen_kernel) where the screen applies.
+  const char* fused_env = getenv("DNV_READS_FUSED");
+  const bool want_fused = fused_env && fused_env[0] == '1';
+  if (!want_fused || !will_screen(ctx, false) || ctx->dense_mode) {
     int rc = dnv_pileup_device(ctx, d_read_start, d_base_off, d_bases, d_person, n_reads, d_site_pos, n_sites, ctx->d_reads_counts);
     if (rc) return rc;
     return dnv_infer_counts_device(ctx, ctx->d_reads_counts, n_sites, nullptr, d_calls, cap, n_calls);

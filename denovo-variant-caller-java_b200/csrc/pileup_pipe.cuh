@@ -140,7 +140,7 @@ pileup_pipe_kernel(const int64_t* __restrict__ read_start, const int64_t* __rest
           more_nxt = fetch(nxt);
           have_nxt = true;
         }
-        mbar_wait(&sh.empty, (it & 1u) ^ 1u);  // the consumers are done with the previous step: the stage is free
+        mbar_wait_sleepy(&sh.empty, (it & 1u) ^ 1u, 20000u);  // the consumers are done with the previous step: the stage is free
         if (!cur.dense) {
           if (lane == 0) {
             sh.step[b] = PipeStep{cur.s0, (int)cur.P0, cur.n_live, 0, 0, kPP_Sparse, 1, 1, 0, 0};
@@ -211,7 +211,7 @@ pileup_pipe_kernel(const int64_t* __restrict__ read_start, const int64_t* __rest
       cur = nxt;
       more = more_nxt;
     }
-    mbar_wait(&sh.empty, (it & 1u) ^ 1u);
+    mbar_wait_sleepy(&sh.empty, (it & 1u) ^ 1u, 20000u);
     if (lane == 0) {
       sh.step[it & 1u].kind = kPP_Stop;
       mbar_arrive(&sh.full);
@@ -252,7 +252,7 @@ pileup_pipe_kernel(const int64_t* __restrict__ read_start, const int64_t* __rest
   for (int k = 0; k < S; k++) acc[k] = 0;
   for (;; it++) {
     const int b = (int)(it & 1u);
-    mbar_wait(&sh.full, it & 1u);
+    mbar_wait_sleepy(&sh.full, it & 1u, 20000u);
     const int kind = sh.step[b].kind;
     if (kind == kPP_Stop) break;
     const int64_t s0 = sh.step[b].s0;
@@ -315,29 +315,29 @@ pileup_pipe_kernel(const int64_t* __restrict__ read_start, const int64_t* __rest
       const int* bo_lo = reinterpret_cast<const int*>(sh.bo_raw + skip);
       const uint32_t stage_s = smem_u32(sh.stage + kPP_Pad) + (uint32_t)sh.step[b].bias;
       const int lim = n_live - my_off;  // my sites at or past it are not requested (last, partial tile)
-      int lo = 0, hi = m;  // first staged read with rel > my_off - lmax (earlier ones end before my first site)
-      const int key = my_off - lmax;
+      const int off0 = P0_lo + my_off;  // low word of my first site's position (differences of low words are exact)
+      int lo = 0, hi = m;  // first staged read that starts after my_off - lmax (earlier ones end before my first site)
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (rs_lo[2 * mid] - P0_lo <= key) lo = mid + 1; else hi = mid;
+        if (off0 - rs_lo[2 * mid] >= lmax) lo = mid + 1; else hi = mid;
       }
       // The descriptors of the next read are fetched while this one is processed (no load latency in front of the
       // two tests), and base_off of the next read is this read's end.  Blocks of at most 63 iterations: the 6-bit
       // lanes cannot overflow inside one, so the loop itself carries no flush counter.
       const uint32_t keep_s = smem_u32(sh.keep);
-      int rel_n = rs_lo[2 * lo] - P0_lo, b0_n = bo_lo[2 * lo], b1_n = bo_lo[2 * lo + 2];
+      int rs_n = rs_lo[2 * lo], b0_n = bo_lo[2 * lo], b1_n = bo_lo[2 * lo + 2];
       int skipped = 0;
       bool done = false;
       for (int jb = lo; jb < m && !done; jb += 63) {
         const int je = min(jb + 63, m);
         int j = jb;
         for (; j < je; j++) {
-          const int rel = rel_n, b0 = b0_n, b1 = b1_n;
-          rel_n = rs_lo[2 * j + 2] - P0_lo;  // (one entry past the last read at the end: inside the arrays, unused)
+          const int q = off0 - rs_n;  // offset of my first site inside the read (M/ReadSummary.java:48)
+          const int b0 = b0_n, b1 = b1_n;
+          rs_n = rs_lo[2 * j + 2];    // (one entry past the last read at the end: inside the arrays, unused)
           b0_n = b1;
           b1_n = bo_lo[2 * j + 4];
-          if (rel > my_off + S - 1) { done = true; break; }
-          const int q = my_off - rel;  // offset of my first site inside the read (M/ReadSummary.java:48)
+          if (q < -(S - 1)) { done = true; break; }  // this read and all later ones start after my last site
           const int len = b1 - b0;
           if (q >= len) { skipped++; continue; }  // read ends before my first site
           const uint32_t addr = stage_s + (uint32_t)(b0 + q);  // >= -(S-1) from the staged bytes: inside the front pad
@@ -385,7 +385,15 @@ pileup_pipe_kernel(const int64_t* __restrict__ read_start, const int64_t* __rest
   }
 }
 
-// pre-pass: one warp per tile writes the tile's record (kPP_TileWords words)
+// pre-pass 1 (streaming): marks the tiles whose positions are not consecutive in word 7 of their (zeroed) records
+__global__ void __launch_bounds__(256)
+pileup_breaks_kernel(const int64_t* __restrict__ site_pos, int64_t n_sites, int tile_sites, long long* __restrict__ tiles) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i + 1 < n_sites; i += (int64_t)gridDim.x * blockDim.x) {
+    if (__ldg(site_pos + i + 1) != __ldg(site_pos + i) + 1 && (i + 1) % tile_sites != 0) tiles[i / tile_sites * kPP_TileWords + 7] = 1;
+  }
+}
+
+// pre-pass 2: one warp per tile writes the tile's record (kPP_TileWords words)
 __global__ void __launch_bounds__(256)
 pileup_windows_kernel(const int64_t* __restrict__ read_start, const long long* __restrict__ meta,
                       const int64_t* __restrict__ site_pos, int64_t n_sites, int tile_sites, int stage_limit,
@@ -400,13 +408,9 @@ pileup_windows_kernel(const int64_t* __restrict__ read_start, const long long* _
   const int64_t P0 = __ldg(site_pos + s0);
   int64_t win[6];
   ps_warp_upper_bound6(read_start, meta, P0 - lmax, P0 + n_live - 1, lane, win);
-  // strictly increasing positions with last - first == n - 1  <=>  consecutive; meta[7] == 0: all of them are
-  bool dense = lmax > 0 && lmax <= stage_limit;
-  if (dense && meta[7] != 0) {
-    int ok = __ldg(site_pos + s0 + n_live - 1) - P0 == n_live - 1;
-    for (int i = lane; i < n_live - 1; i += 32) ok &= __ldg(site_pos + s0 + i + 1) > __ldg(site_pos + s0 + i);
-    dense = __all_sync(0xffffffffu, ok);
-  }
+  // word 7 comes in as "some neighbouring positions of this tile are not consecutive" (pileup_breaks_kernel, 0 = none)
+  const bool dense = lmax > 0 && lmax <= stage_limit && tiles[tile * kPP_TileWords + 7] == 0;
+  __syncwarp();
   long long w = lane == 6 ? P0 : lane == 7 ? (dense ? 1 : 0) : 0;
 #pragma unroll
   for (int q = 0; q < 6; q++) w = lane == q ? win[q] : w;
@@ -428,6 +432,9 @@ static cudaError_t launch_pileup_pipe(cudaStream_t st, int sms, const int64_t* d
   constexpr int kSites = kPP_Consumers * S;
   const int64_t n_tiles = (n_sites + kSites - 1) / kSites;
   const int64_t wblocks = (n_tiles * 32 + 255) / 256;
+  e = cudaMemsetAsync(tiles, 0, (size_t)n_tiles * kPP_TileWords * sizeof(long long), st);
+  if (e != cudaSuccess) return e;
+  pileup_breaks_kernel<<<(unsigned)std::min<int64_t>((n_sites + 255) / 256, (int64_t)sms * 8), 256, 0, st>>>(d_site_pos, n_sites, kSites, tiles);
   pileup_windows_kernel<<<(unsigned)wblocks, 256, 0, st>>>(d_read_start, meta, d_site_pos, n_sites, kSites,
                                                            std::min(kPP_StageBytes - 16, 0x7FFFFFFF), tiles);
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)sms * std::max(per_sm, 1)));

@@ -131,11 +131,13 @@ print("ok")
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-1000:] + r.stderr[-2000:]
 
 
-@pytest.mark.parametrize("method", ["BAYES", "MAP", "LRT"])
-def test_fused_reads_to_calls_equals_pileup_then_inference(method):
-    """dnv_infer_reads (pileup in shared memory, screened there, counts only for undecided sites) returns the records
-    of dnv_infer_counts over dnv_pileup's counts — and those are the oracle's: dense every-position layout with
-    planted de novo / inherited variants, a ragged tail, then a sparse candidate list (per-site path)."""
+@pytest.mark.parametrize("method,fused", [("BAYES", "0"), ("BAYES", "1"), ("MAP", "1"), ("LRT", "0"), ("LRT", "1")])
+def test_reads_to_calls_equals_pileup_then_inference(method, fused, monkeypatch):
+    """dnv_infer_reads — by default the pileup pipeline chained to the READ pipeline on the device, with
+    DNV_READS_FUSED=1 one kernel (pileup in shared memory, screened there, counts only for undecided sites) — returns
+    the records of dnv_infer_counts over dnv_pileup's counts, and those are the oracle's: dense every-position layout
+    with planted de novo / inherited variants, a ragged tail, then a sparse candidate list (per-site path)."""
+    monkeypatch.setenv("DNV_READS_FUSED", fused)
     n_sites = 300_000 + 77
     rs, bo, ba, pe = S.make_reads(17, 1, n_sites, depth=30, err=1e-2)
     # plant variants every 211 sites (vectorised): at even plants the child alone carries an alternative allele in
