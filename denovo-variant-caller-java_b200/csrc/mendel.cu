@@ -101,55 +101,75 @@ __device__ __forceinline__ unsigned long long lookback(unsigned long long* statu
 
 // ---- kernel A: admission (checkAndAdd) + domain checks + ordered compaction into the three
 // queues + running max of end for the parents, in ONE pass over the 32-byte records.
-// A block owns kMI * kMB consecutive records (round j: record b*kMI*kMB + j*kMB + thread, so
-// every load is coalesced); the essentials of its records stay in registers while the block's
-// totals go through the look-back chains.
-constexpr int kMI = 8;                    // records (A) / child SNPs (B) per thread
-constexpr int kMTile = kMI * kMB;
+// A block owns kMTile consecutive records: ONE TMA bulk copy brings them into shared memory
+// (32 KB in flight per block, five blocks per SM: the kernel no longer waits on its own loads
+// record by record); thread t then handles records t, t + 256, ... (a warp = 32 consecutive
+// records per round, which is what the ordered ranks are built on).  The essentials of a
+// thread's records stay in registers while the block's totals go through the look-back chains.
+// The running max of `end` is scanned inside a warp on 32-bit values relative to the tile's
+// first start; a tile holding an admitted entry that ends 2^32 or more past it (no such genome)
+// takes the same code on 64-bit values.
+constexpr int kMI = 4;                    // records per thread
+constexpr int kMTile = kMI * kMB;         // 1024 records = 32 KB
 constexpr int kMW = kMB / 32;             // warps per block
 
-__global__ void __launch_bounds__(kMB)
-mendel_admit_compact_kernel(const dnv_vcall* __restrict__ calls, int64_t n, MendelArrays A) {
-  __shared__ unsigned int s_bid;
-  __shared__ int s_cnt[3][kMI * kMW + 1];                 // per (round, warp) admitted counts -> exclusive offsets
-  __shared__ unsigned long long s_max[2][kMI * kMW + 1];  // per (round, warp) max of end+1 -> exclusive running max
-  __shared__ unsigned long long s_excl[5];
-  if (threadIdx.x == 0) s_bid = (unsigned int)atomicAdd(&A.totals[6], 1ull);
-  __syncthreads();
-  const unsigned int b = s_bid;
+// allele index of a base, -1 outside ACGT: (c >> 1) & 3 is a perfect hash of A, C, G, T (0, 1, 3, 2)
+__device__ __forceinline__ int allele_fast(uint32_t c) {
+  const uint32_t h = (c >> 1) & 3u;
+  const uint32_t canon = (0x47544341u >> (8 * h)) & 0xFFu;  // "ACTG"[h]
+  return canon == c ? (int)((0x2310u >> (4 * h)) & 3u) : -1;
+}
+
+template <typename T>
+__device__ __forceinline__ void mendel_admit_tile(const uint4* s_rec, const dnv_vcall* __restrict__ calls, int64_t n,
+                                                  const MendelArrays& A, unsigned int b, int n_here,
+                                                  int (*s_cnt)[kMI * kMW + 1], unsigned long long (*s_max)[kMI * kMW + 1],
+                                                  unsigned long long* s_excl) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t tile0 = (int64_t)b * kMTile;
+  const int64_t base = (int64_t)(((unsigned long long)s_rec[0].y << 32) | s_rec[0].x);  // first start of the tile
   int64_t st[kMI];
   uint32_t meta[kMI];  // bit0 admitted, bits 2:1 person, bits 15:8 genotype code, bits 23:16 ref allele, bits 31:24 rank in warp
-  unsigned long long myrun[kMI];  // warp-inclusive running max (end+1) over entries of my own parent queue
+  T myrun[kMI];        // warp-inclusive running max of (end + 1 - base) over entries of my own parent queue; 0 = none
 #pragma unroll
   for (int j = 0; j < kMI; j++) {
-    const int64_t i = (int64_t)b * kMTile + (int64_t)j * kMB + threadIdx.x;
+    const int r = j * kMB + threadIdx.x;
     bool adm = false;
     int person = 3;
-    dnv_vcall v;
-    v.start = 0; v.end = 0; v.gt0 = v.gt1 = 0; v.ref_base = 0; v.alt0_base = v.alt1_base = 0;
-    if (i < n) {
-      v = calls[i];
-      person = v.person;
-      const bool ins = (v.ngt >= 1 && v.gt0 > 0 && v.alt0_len != 1) || (v.ngt >= 2 && v.gt1 > 0 && v.alt1_len != 1);
-      const bool del = v.ref_len != 1;
-      const bool snp = (v.end == v.start + 1) && !del && !ins;
-      const bool dot = (v.ngt >= 1 && v.gt0 == -1) || (v.ngt >= 2 && v.gt1 == -1);
-      adm = person <= 2 && !((person == kChild && !snp) || dot || v.ngt != 2 || !v.filter_pass || ins || del);
-      bool bad = false;
-      if (i > 0 && calls[i - 1].start > v.start) bad = true;  // stream must be sorted by start
-      if (adm && (v.end <= v.start || v.start < 0 || v.end >= (1ll << 60))) bad = true;  // outside the batch-equivalence domain
-      if (bad) atomicMax(&A.totals[4], ((unsigned long long)(i + 1) << 2) | kErrUnsorted);
-    }
+    int64_t start = 0, end = 0;
     uint32_t code = kCodeBlock, ref = 0xFF;
-    if (adm) {
-      if (v.end == v.start + 1) {  // admitted => ref_len == 1 and no insertion: getGenotypeFromSNP, :228-239
-        const int a0 = allele_of(v.gt0 > 0 ? v.alt0_base : v.ref_base);
-        const int a1 = allele_of(v.gt1 > 0 ? v.alt1_base : v.ref_base);
-        code = (a0 < 0 || a1 < 0) ? kCodeBad : (uint32_t)geno_of(a0, a1);
+    if (r < n_here) {
+      const uint4 lo = s_rec[2 * r], hi = s_rec[2 * r + 1];
+      start = (int64_t)(((unsigned long long)lo.y << 32) | lo.x);
+      end = (int64_t)(((unsigned long long)lo.w << 32) | lo.z);
+      // hi.x variant_id; hi.y = gt0 | gt1 << 8 | ngt << 16 | person << 24;
+      // hi.z = filter_pass | ref_len << 8 | ref_base << 16 | alt0_len << 24; hi.w = alt0_base | alt1_len << 8 | alt1_base << 16
+      const int gt0 = (int)(int8_t)(hi.y & 0xFFu), gt1 = (int)(int8_t)((hi.y >> 8) & 0xFFu);
+      const uint32_t ngt = (hi.y >> 16) & 0xFFu;
+      person = (int)(hi.y >> 24);
+      const uint32_t filter_pass = hi.z & 0xFFu, ref_len = (hi.z >> 8) & 0xFFu, ref_base = (hi.z >> 16) & 0xFFu;
+      const uint32_t alt0_len = hi.z >> 24, alt0_base = hi.w & 0xFFu, alt1_len = (hi.w >> 8) & 0xFFu, alt1_base = (hi.w >> 16) & 0xFFu;
+      const bool ins = (ngt >= 1 && gt0 > 0 && alt0_len != 1) || (ngt >= 2 && gt1 > 0 && alt1_len != 1);
+      const bool del = ref_len != 1;
+      const bool snp = (end == start + 1) && !del && !ins;
+      const bool dot = (ngt >= 1 && gt0 == -1) || (ngt >= 2 && gt1 == -1);
+      adm = person <= 2 && !((person == kChild && !snp) || dot || ngt != 2 || !filter_pass || ins || del);
+      // stream must be sorted by start (the record before the tile's first one comes from global memory)
+      int64_t prev = start;
+      if (r > 0) prev = (int64_t)(((unsigned long long)s_rec[2 * r - 2].y << 32) | s_rec[2 * r - 2].x);
+      else if (tile0 > 0) prev = calls[tile0 - 1].start;
+      bool bad = prev > start;
+      if (adm && (end <= start || start < 0 || end >= (1ll << 60))) bad = true;  // outside the batch-equivalence domain
+      if (bad) atomicMax(&A.totals[4], ((unsigned long long)(tile0 + r + 1) << 2) | kErrUnsorted);
+      if (adm) {
+        if (end == start + 1) {  // admitted => ref_len == 1 and no insertion: getGenotypeFromSNP, :228-239
+          const int a0 = allele_fast(gt0 > 0 ? alt0_base : ref_base);
+          const int a1 = allele_fast(gt1 > 0 ? alt1_base : ref_base);
+          code = (a0 < 0 || a1 < 0) ? kCodeBad : (uint32_t)geno_of(a0, a1);
+        }
+        const int rb = allele_fast(ref_base);
+        ref = rb < 0 ? 0xFFu : (uint32_t)rb;
       }
-      const int r = allele_of(v.ref_base);
-      ref = r < 0 ? 0xFFu : (uint32_t)r;
     }
     int rank = 0;
 #pragma unroll
@@ -158,49 +178,44 @@ mendel_admit_compact_kernel(const dnv_vcall* __restrict__ calls, int64_t n, Mend
       if (person == p) rank = __popc(m & ((1u << lane) - 1));
       if (lane == 0) s_cnt[p][j * kMW + warp] = __popc(m);
     }
-    unsigned long long mine = 0;
+    // running max of end (+1, relative to base; 0 = none) per parent queue: shfl_up hands lanes below the offset
+    // their own value back, so no predicate is needed
+    const T rel = (adm && person != kChild) ? (T)(unsigned long long)(end + 1 - base) : (T)0;
+    T mine = 0;
 #pragma unroll
     for (int par = 0; par < 2; par++) {
-      unsigned long long x = (adm && person == par + 1) ? (unsigned long long)v.end + 1ull : 0ull;
+      T x = person == par + 1 ? rel : (T)0;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
-        if (lane >= o) x = y > x ? y : x;
+        const T y = __shfl_up_sync(0xffffffffu, x, o);
+        x = y > x ? y : x;
       }
       if (person == par + 1) mine = x;
-      if (lane == 31) s_max[par][j * kMW + warp] = x;
+      if (lane == 31) s_max[par][j * kMW + warp] = x ? (unsigned long long)base + (unsigned long long)x : 0ull;
     }
-    st[j] = v.start; myrun[j] = mine;
+    st[j] = start; myrun[j] = mine;
     meta[j] = (adm ? 1u : 0u) | ((uint32_t)(person & 3) << 1) | (code << 8) | (ref << 16) | ((uint32_t)rank << 24);
   }
   __syncthreads();
   // exclusive scans over the kMI*kMW (round, warp) cells: five small scans, one warp each
   unsigned long long block_total = 0;
+  static_assert(kMI * kMW == 32, "one warp-wide scan covers the cells");
   if (warp < 3) {
-    int carry = 0;
-    for (int c0 = 0; c0 < kMI * kMW; c0 += 32) {
-      const int v0 = s_cnt[warp][c0 + lane];
-      int x = v0;
+    const int v0 = s_cnt[warp][lane];
+    int x = v0;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
-      s_cnt[warp][c0 + lane] = carry + x - v0;
-      carry += __shfl_sync(0xffffffffu, x, 31);
-    }
-    block_total = (unsigned long long)carry;
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    s_cnt[warp][lane] = x - v0;
+    block_total = (unsigned long long)__shfl_sync(0xffffffffu, x, 31);
   } else if (warp < 5) {
-    unsigned long long carry = 0;
-    for (int c0 = 0; c0 < kMI * kMW; c0 += 32) {
-      const unsigned long long v0 = s_max[warp - 3][c0 + lane];
-      unsigned long long x = v0;
+    const unsigned long long v0 = s_max[warp - 3][lane];
+    unsigned long long x = v0;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x = y > x ? y : x; }
-      unsigned long long ex = __shfl_up_sync(0xffffffffu, x, 1);
-      if (lane == 0) ex = 0;
-      s_max[warp - 3][c0 + lane] = ex > carry ? ex : carry;
-      const unsigned long long last = __shfl_sync(0xffffffffu, x, 31);
-      carry = last > carry ? last : carry;
-    }
-    block_total = carry;
+    for (int o = 1; o < 32; o <<= 1) { const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x = y > x ? y : x; }
+    unsigned long long ex = __shfl_up_sync(0xffffffffu, x, 1);
+    if (lane == 0) ex = 0;
+    s_max[warp - 3][lane] = ex;
+    block_total = __shfl_sync(0xffffffffu, x, 31);
   }
   // five look-back chains, one warp each
   if (warp < 3) {
@@ -220,15 +235,53 @@ mendel_admit_compact_kernel(const dnv_vcall* __restrict__ calls, int64_t n, Mend
     A.code[p][pos] = (uint8_t)(meta[j] >> 8);
     if (p == kChild) {
       A.ref[pos] = (uint8_t)(meta[j] >> 16);
-      A.src[pos] = (int64_t)b * kMTile + (int64_t)j * kMB + threadIdx.x;
+      A.src[pos] = tile0 + (int64_t)j * kMB + threadIdx.x;
     } else {
-      unsigned long long rm = myrun[j];
+      unsigned long long rm = myrun[j] ? (unsigned long long)base + (unsigned long long)myrun[j] : 0ull;
       const unsigned long long e1 = s_max[p - 1][j * kMW + warp], e2 = s_excl[2 + p];
       rm = e1 > rm ? e1 : rm;
       rm = e2 > rm ? e2 : rm;
       A.runmax[p][pos] = (int64_t)rm - 1;
     }
   }
+}
+
+__global__ void __launch_bounds__(kMB, 5)
+mendel_admit_compact_kernel(const dnv_vcall* __restrict__ calls, int64_t n, MendelArrays A) {
+  extern __shared__ __align__(128) unsigned char mendel_smem[];
+  uint4* s_rec = reinterpret_cast<uint4*>(mendel_smem);   // the tile's records
+  __shared__ unsigned int s_bid;
+  __shared__ alignas(8) unsigned long long s_bar;
+  __shared__ int s_cnt[3][kMI * kMW + 1];                 // per (round, warp) admitted counts -> exclusive offsets
+  __shared__ unsigned long long s_max[2][kMI * kMW + 1];  // per (round, warp) max of end+1 -> exclusive running max
+  __shared__ unsigned long long s_excl[5];
+  if (threadIdx.x == 0) {
+    const unsigned int t = (unsigned int)atomicAdd(&A.totals[6], 1ull);
+    s_bid = t;
+    mbar_init(&s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t bytes = (uint32_t)min((int64_t)kMTile, n - (int64_t)t * kMTile) * (uint32_t)sizeof(dnv_vcall);
+    mbar_expect_tx(&s_bar, bytes);
+    tma_bulk_g2s(s_rec, calls + (int64_t)t * kMTile, bytes, &s_bar);
+  }
+  __syncthreads();
+  const unsigned int b = s_bid;
+  const int n_here = (int)min((int64_t)kMTile, n - (int64_t)b * kMTile);
+  mbar_wait(&s_bar, 0);
+  // does any admitted-looking entry end 2^32 or more past the tile's first start?  (block uniform)
+  const int64_t base = (int64_t)(((unsigned long long)s_rec[0].y << 32) | s_rec[0].x);
+  int wide = 0;
+#pragma unroll
+  for (int j = 0; j < kMI; j++) {
+    const int r = j * kMB + threadIdx.x;
+    if (r < n_here) {
+      const uint4 lo = s_rec[2 * r];
+      const int64_t end = (int64_t)(((unsigned long long)lo.w << 32) | lo.z);
+      wide |= (unsigned long long)(end + 1 - base) >= (1ull << 32);  // (negative differences land here too)
+    }
+  }
+  if (__syncthreads_or(wide)) mendel_admit_tile<unsigned long long>(s_rec, calls, n, A, b, n_here, s_cnt, s_max, s_excl);
+  else mendel_admit_tile<uint32_t>(s_rec, calls, n, A, b, n_here, s_cnt, s_max, s_excl);
 }
 
 // ---- kernel B: join every admitted child SNP against both parents and emit the PositionCalls
@@ -426,7 +479,13 @@ int dnv_mendel_filter_device(dnv_ctx* ctx, const dnv_vcall* d_calls, int64_t n, 
   A.ref = (uint8_t*)(base + o_ref); A.src = (int64_t*)(base + o_src);
 
   DNV_CUDA(cudaMemsetAsync(base + o_status, 0, 7 * status_bytes + 64, st));
-  mendel_admit_compact_kernel<<<n_blocks, kMB, 0, st>>>(d_calls, n, A);
+  if (reinterpret_cast<uintptr_t>(d_calls) & 15) {
+    set_error("dnv_mendel_filter_device: the record array must be 16-byte aligned");
+    return DNV_E_INVALID;
+  }
+  const size_t a_smem = (size_t)kMTile * sizeof(dnv_vcall);
+  DNV_CUDA(cudaFuncSetAttribute(mendel_admit_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a_smem));
+  mendel_admit_compact_kernel<<<n_blocks, kMB, a_smem, st>>>(d_calls, n, A);
   const int j_blocks = (int)((n + kJTile - 1) / kJTile);  // children <= records; empty blocks retire at once
   const size_t j_smem = (size_t)4 * kJCap * sizeof(int64_t);
   DNV_CUDA(cudaFuncSetAttribute(mendel_join_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)j_smem));
