@@ -46,6 +46,8 @@ __device__ __forceinline__ int geno_of(int x, int y) {  // Genotype.valueOfPairA
 }
 
 constexpr int kMB = 256;  // records (kernel A) / child SNPs (kernel B) per block
+constexpr int kJI = 2;                 // child SNPs per thread in kernel B
+constexpr int kJTile = kJI * kMB;      // 512 children per block
 
 struct MendelArrays {
   // per-person admitted entries in stream order (SoA queues)
@@ -58,6 +60,7 @@ struct MendelArrays {
   unsigned long long* st_sum[3];   // admitted counts per person
   unsigned long long* st_max[3];   // running max of end (+1; 0 = none) per parent
   unsigned long long* st_found;    // PositionCalls
+  unsigned long long* win;         // per block of kernel B: [lo_mom, hi_mom, lo_dad, hi_dad] + 1 each, 0 = not written
   unsigned long long* totals;      // [0..2] admitted per person, [3] PositionCalls, [4] error: (record index + 1) << 2 | kind, [6],[7] tickets
 };
 
@@ -124,7 +127,7 @@ template <typename T>
 __device__ __forceinline__ void mendel_admit_tile(const uint4* s_rec, const dnv_vcall* __restrict__ calls, int64_t n,
                                                   const MendelArrays& A, unsigned int b, int n_here,
                                                   int (*s_cnt)[kMI * kMW + 1], unsigned long long (*s_max)[kMI * kMW + 1],
-                                                  unsigned long long* s_excl) {
+                                                  unsigned long long* s_excl, unsigned long long* s_tot) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t tile0 = (int64_t)b * kMTile;
   const int64_t base = (int64_t)(((unsigned long long)s_rec[0].y << 32) | s_rec[0].x);  // first start of the tile
@@ -220,7 +223,7 @@ __device__ __forceinline__ void mendel_admit_tile(const uint4* s_rec, const dnv_
   // five look-back chains, one warp each
   if (warp < 3) {
     const unsigned long long e = lookback<false>(A.st_sum[warp], b, block_total, lane);
-    if (lane == 0) { s_excl[warp] = e; if (b == gridDim.x - 1) A.totals[warp] = e + block_total; }
+    if (lane == 0) { s_excl[warp] = e; s_tot[warp] = block_total; if (b == gridDim.x - 1) A.totals[warp] = e + block_total; }
   } else if (warp < 5) {
     const unsigned long long e = lookback<true>(A.st_max[warp - 2], b, block_total, lane);
     if (lane == 0) s_excl[warp] = e;
@@ -236,6 +239,12 @@ __device__ __forceinline__ void mendel_admit_tile(const uint4* s_rec, const dnv_
     if (p == kChild) {
       A.ref[pos] = (uint8_t)(meta[j] >> 16);
       A.src[pos] = tile0 + (int64_t)j * kMB + threadIdx.x;
+      // kernel B's window of each parent queue for the block of children this one opens / closes: every parent entry
+      // of an earlier tile starts at or before this child, and (up to ties, which B checks) none of a later tile does
+      const int64_t jb = pos / kJTile;
+      const int wi = (int)(pos % kJTile);
+      if (wi == 0) { A.win[jb * 4 + 0] = s_excl[kMom] + 1; A.win[jb * 4 + 2] = s_excl[kDad] + 1; }
+      if (wi == kJTile - 1) { A.win[jb * 4 + 1] = s_excl[kMom] + s_tot[kMom] + 1; A.win[jb * 4 + 3] = s_excl[kDad] + s_tot[kDad] + 1; }
     } else {
       unsigned long long rm = myrun[j] ? (unsigned long long)base + (unsigned long long)myrun[j] : 0ull;
       const unsigned long long e1 = s_max[p - 1][j * kMW + warp], e2 = s_excl[2 + p];
@@ -255,6 +264,7 @@ mendel_admit_compact_kernel(const dnv_vcall* __restrict__ calls, int64_t n, Mend
   __shared__ int s_cnt[3][kMI * kMW + 1];                 // per (round, warp) admitted counts -> exclusive offsets
   __shared__ unsigned long long s_max[2][kMI * kMW + 1];  // per (round, warp) max of end+1 -> exclusive running max
   __shared__ unsigned long long s_excl[5];
+  __shared__ unsigned long long s_tot[3];
   if (threadIdx.x == 0) {
     const unsigned int t = (unsigned int)atomicAdd(&A.totals[6], 1ull);
     s_bid = t;
@@ -280,8 +290,8 @@ mendel_admit_compact_kernel(const dnv_vcall* __restrict__ calls, int64_t n, Mend
       wide |= (unsigned long long)(end + 1 - base) >= (1ull << 32);  // (negative differences land here too)
     }
   }
-  if (__syncthreads_or(wide)) mendel_admit_tile<unsigned long long>(s_rec, calls, n, A, b, n_here, s_cnt, s_max, s_excl);
-  else mendel_admit_tile<uint32_t>(s_rec, calls, n, A, b, n_here, s_cnt, s_max, s_excl);
+  if (__syncthreads_or(wide)) mendel_admit_tile<unsigned long long>(s_rec, calls, n, A, b, n_here, s_cnt, s_max, s_excl, s_tot);
+  else mendel_admit_tile<uint32_t>(s_rec, calls, n, A, b, n_here, s_cnt, s_max, s_excl, s_tot);
 }
 
 // ---- kernel B: join every admitted child SNP against both parents and emit the PositionCalls
@@ -309,61 +319,89 @@ __device__ __forceinline__ int64_t upper_bound_le(const int64_t* __restrict__ a,
   return lo;  // first index with a[idx] > key
 }
 
-constexpr int kJI = 2;                 // child SNPs per thread in kernel B
-constexpr int kJTile = kJI * kMB;      // 512 children per block
-constexpr int kJCap = 1536;            // parent entries staged per parent (start + running max: 24 KB)
+constexpr int kJCap = 1536;            // parent entries staged per parent (start + running max as 32-bit offsets, code: 13.5 KB)
 
-__device__ __forceinline__ int smem_upper_bound_le(const int64_t* a, int lo, int hi, int64_t key) {
+__device__ __forceinline__ int smem_upper_bound_le32(const uint32_t* a, int lo, int hi, uint32_t key) {
   while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] <= key) lo = mid + 1; else hi = mid; }
   return lo;
+}
+// v - base saturated to [0, 2^32 - 1]: every comparison against a key in (0, 2^32 - 1) keeps its outcome
+__device__ __forceinline__ uint32_t sat_rel(int64_t v, int64_t base) {
+  const int64_t d = v - base;
+  return d < 0 ? 0u : d > 0xFFFFFFFFll ? 0xFFFFFFFFu : (uint32_t)d;
 }
 
 __global__ void __launch_bounds__(kMB)
 mendel_join_emit_kernel(const Tables* __restrict__ tab, MendelArrays A, dnv_pcall* __restrict__ out, int64_t cap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  int64_t* s_start = reinterpret_cast<int64_t*>(smem_raw);  // [2][kJCap]
-  int64_t* s_rmax = s_start + 2 * kJCap;                      // [2][kJCap]
+  uint32_t* s_start = reinterpret_cast<uint32_t*>(smem_raw);  // [2][kJCap] start - base
+  uint32_t* s_rmax = s_start + 2 * kJCap;                       // [2][kJCap] running max of end - base
+  uint8_t* s_code = reinterpret_cast<uint8_t*>(s_rmax + 2 * kJCap);  // [2][kJCap]
   __shared__ unsigned int s_bid;
   __shared__ long long s_win[2][4];
   __shared__ int s_cnt[kJI * kMW + 32];
   __shared__ unsigned long long s_excl;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t n_child = (int64_t)A.totals[kChild];
+  // persistent blocks: tiles of 512 children are handed out by a ticket (the look-back below needs every earlier
+  // tile to be running or done), until the children run out — their number is only known on the device
+  for (;;) {
+  __syncthreads();  // the previous tile's shared state is no longer in use
   if (threadIdx.x == 0) s_bid = (unsigned int)atomicAdd(&A.totals[7], 1ull);
   __syncthreads();
   const unsigned int b = s_bid;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t n_child = (int64_t)A.totals[kChild];
   const int64_t i0 = (int64_t)b * kJTile;
-  if (i0 >= n_child) {  // no child SNP here: nothing to publish, later blocks never look at this one
+  if (i0 >= n_child) {  // no child SNP left
     if (n_child == 0 && b == 0 && threadIdx.x == 0) A.totals[3] = 0;
-    return;
+    break;
   }
-  const bool live_block = true;
   const bool last_live = n_child <= i0 + kJTile;
-  // window of each parent queue that the block's children can touch: one warp per bound
-  if (live_block) {
-    const int par = 1 + (warp >> 2), kind = warp & 3;
+  const int64_t i_last = min(n_child, i0 + kJTile) - 1;
+  const int64_t pos0 = A.start[kChild][i0], pos_last = A.start[kChild][i_last];
+  // Window of each parent queue that the block's children can touch.  Fast path: kernel A left the tile-granular
+  // bracket of "#entries with start <= pos" for the block's first and last child (every entry of an earlier tile of
+  // the stream starts at or before the child; up to ties — checked — none of a later tile does), and the first entry
+  // whose running max of `end` exceeds pos0 is rarely more than a few entries before that (checked 64 back).  Every
+  // thread evaluates the same few loads (broadcasts).  The exact bounds are then found by 32-ary searches inside the
+  // bracket (a parent whose checks fail: inside its whole queue).
+  long long br_lo[2], br_g[2], br_hi[2];  // bracket per parent: ub in [lo, hi], first covering entry in [g, hi]
+#pragma unroll
+  for (int q = 0; q < 2; q++) {
+    const int par = q + 1;
     const int64_t np = (int64_t)A.totals[par];
-    const int64_t key = (kind & 1) ? A.start[kChild][min(n_child, i0 + kJTile) - 1] : A.start[kChild][i0];
-    const int64_t r = warp_upper_bound64(kind < 2 ? A.start[par] : A.runmax[par], 0, np, key, lane);
-    if (lane == 0) s_win[par - 1][kind] = r;
+    const unsigned long long w_lo = A.win[(int64_t)b * 4 + 2 * q], w_hi = A.win[(int64_t)b * 4 + 2 * q + 1];
+    const int64_t lo_ub = (int64_t)w_lo - 1;                  // written: the block's first child exists
+    const int64_t hi_ub = w_hi ? (int64_t)w_hi - 1 : np;      // the stream's last, partial block of children
+    const int64_t g = max(lo_ub - 64, (int64_t)0);
+    const bool ok = w_lo != 0 && (g == 0 || __ldg(A.runmax[par] + g - 1) <= pos0) && (hi_ub >= np || __ldg(A.start[par] + hi_ub) > pos_last);
+    br_lo[q] = ok ? lo_ub : 0; br_g[q] = ok ? g : 0; br_hi[q] = ok ? hi_ub : np;
+  }
+  {  // the four exact bounds per parent inside its bracket: one warp each (two probes for a bracket of a few thousand)
+    const int q = warp >> 2, kind = warp & 3;
+    const int64_t key = (kind & 1) ? pos_last : pos0;
+    const int64_t r = warp_upper_bound64(kind < 2 ? A.start[q + 1] : A.runmax[q + 1], kind < 2 ? br_lo[q] : br_g[q], br_hi[q], key, lane);
+    if (lane == 0) s_win[q][kind] = r;
   }
   __syncthreads();
-  // stage [lo, hi) of both arrays of both parents when the windows fit
+  // stage [lo, hi) of start, running max and code of both parents when the windows fit; the positions as 32-bit
+  // offsets from pos0 - 2^30, saturated (sat_rel), which needs the block's children within 2^31 of each other
   long long wlo[2], whi[2];
-  bool staged = live_block;
+  bool staged = pos_last - pos0 < (1ll << 31);
+  const int64_t base = pos0 - (1ll << 30);
 #pragma unroll
   for (int q = 0; q < 2; q++) {
     wlo[q] = min(s_win[q][0], s_win[q][2]);
     whi[q] = max(s_win[q][1], s_win[q][3]);
-    if (live_block && whi[q] - wlo[q] > kJCap) staged = false;
+    if (whi[q] - wlo[q] > kJCap) staged = false;
   }
   if (staged) {
 #pragma unroll
     for (int q = 0; q < 2; q++) {
       const int m = (int)(whi[q] - wlo[q]);
       for (int k = threadIdx.x; k < m; k += kMB) {
-        s_start[q * kJCap + k] = A.start[q + 1][wlo[q] + k];
-        s_rmax[q * kJCap + k] = A.runmax[q + 1][wlo[q] + k];
+        s_start[q * kJCap + k] = sat_rel(A.start[q + 1][wlo[q] + k], base);
+        s_rmax[q * kJCap + k] = sat_rel(A.runmax[q + 1][wlo[q] + k], base);
+        s_code[q * kJCap + k] = A.code[q + 1][wlo[q] + k];
       }
     }
   }
@@ -386,17 +424,19 @@ mendel_join_emit_kernel(const Tables* __restrict__ tab, MendelArrays A, dnv_pcal
         if (!found) break;
         const int q = par - 1;
         int64_t ub, is;
+        int c;
         if (staged) {
-          const int64_t* ss = s_start + q * kJCap;
-          const int64_t* sr = s_rmax + q * kJCap;
-          ub = wlo[q] + smem_upper_bound_le(ss, (int)(s_win[q][0] - wlo[q]), (int)(s_win[q][1] - wlo[q]), pos);  // #entries with start <= pos
-          is = wlo[q] + smem_upper_bound_le(sr, (int)(s_win[q][2] - wlo[q]), (int)(s_win[q][3] - wlo[q]), pos);  // first with running max of end > pos
+          const uint32_t key = (uint32_t)(pos - base);  // in [2^30, 2^30 + 2^31)
+          ub = wlo[q] + smem_upper_bound_le32(s_start + q * kJCap, (int)(s_win[q][0] - wlo[q]), (int)(s_win[q][1] - wlo[q]), key);  // #entries with start <= pos
+          is = wlo[q] + smem_upper_bound_le32(s_rmax + q * kJCap, (int)(s_win[q][2] - wlo[q]), (int)(s_win[q][3] - wlo[q]), key);   // first with running max of end > pos
+          if (is >= ub) { found = false; break; }  // no covering entry -> no PositionCall (:211-213)
+          c = s_code[q * kJCap + (int)(is - wlo[q])];
         } else {
           ub = upper_bound_le(A.start[par], s_win[q][0], s_win[q][1], pos);
           is = upper_bound_le(A.runmax[par], s_win[q][2], s_win[q][3], pos);
+          if (is >= ub) { found = false; break; }
+          c = A.code[par][is];
         }
-        if (is >= ub) { found = false; break; }  // no covering entry -> no PositionCall (:211-213)
-        const int c = A.code[par][is];
         if (c == kCodeBlock) { if (rb == 0xFF) bad = true; g[par] = geno_of(rb & 3, rb & 3); }  // ref+ref of the CHILD's base (:217-219)
         else { if (c == kCodeBad) bad = true; g[par] = c; }
       }
@@ -437,6 +477,7 @@ mendel_join_emit_kernel(const Tables* __restrict__ tab, MendelArrays A, dnv_pcal
       out[o_pos] = o;
     }
   }
+  }  // next tile
 }
 
 }  // namespace dnv
@@ -463,7 +504,8 @@ int dnv_mendel_filter_device(dnv_ctx* ctx, const dnv_vcall* d_calls, int64_t n, 
   for (int p = 0; p < 3; p++) { o_start[p] = take((size_t)n * 8); o_rmax[p] = take((size_t)n * 8); o_code[p] = take((size_t)n); }
   const size_t o_ref = take((size_t)n), o_src = take((size_t)n * 8);
   const size_t status_bytes = (size_t)((n + kJTile - 1) / kJTile + 1) * 8;  // sized for the finer of the two grids
-  const size_t o_status = take(7 * status_bytes + 64);  // 3 sums, 3 maxima (child unused), found, then the totals
+  const size_t win_bytes = (size_t)((n + kJTile - 1) / kJTile + 1) * 4 * 8;  // kernel B's window records
+  const size_t o_status = take(7 * status_bytes + 64 + win_bytes);  // 3 sums, 3 maxima (child unused), found, the totals, the windows
   int rc = ensure_scratch(ctx, off);
   if (rc) return rc;
   char* base = (char*)ctx->d_scratch;
@@ -476,9 +518,10 @@ int dnv_mendel_filter_device(dnv_ctx* ctx, const dnv_vcall* d_calls, int64_t n, 
   }
   A.st_found = (unsigned long long*)(base + o_status + 6 * status_bytes);
   A.totals = (unsigned long long*)(base + o_status + 7 * status_bytes);
+  A.win = (unsigned long long*)(base + o_status + 7 * status_bytes + 64);
   A.ref = (uint8_t*)(base + o_ref); A.src = (int64_t*)(base + o_src);
 
-  DNV_CUDA(cudaMemsetAsync(base + o_status, 0, 7 * status_bytes + 64, st));
+  DNV_CUDA(cudaMemsetAsync(base + o_status, 0, 7 * status_bytes + 64 + win_bytes, st));
   if (reinterpret_cast<uintptr_t>(d_calls) & 15) {
     set_error("dnv_mendel_filter_device: the record array must be 16-byte aligned");
     return DNV_E_INVALID;
@@ -487,9 +530,12 @@ int dnv_mendel_filter_device(dnv_ctx* ctx, const dnv_vcall* d_calls, int64_t n, 
   DNV_CUDA(cudaFuncSetAttribute(mendel_admit_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a_smem));
   mendel_admit_compact_kernel<<<n_blocks, kMB, a_smem, st>>>(d_calls, n, A);
   const int j_blocks = (int)((n + kJTile - 1) / kJTile);  // children <= records; empty blocks retire at once
-  const size_t j_smem = (size_t)4 * kJCap * sizeof(int64_t);
+  const size_t j_smem = (size_t)2 * kJCap * (2 * sizeof(uint32_t) + 1);
   DNV_CUDA(cudaFuncSetAttribute(mendel_join_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)j_smem));
-  mendel_join_emit_kernel<<<j_blocks, kMB, j_smem, st>>>(ctx->d_tab, A, d_out, cap);
+  int j_per_sm = 1;
+  DNV_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&j_per_sm, mendel_join_emit_kernel, kMB, j_smem));
+  const int j_grid = std::max(1, std::min(j_blocks, ctx->sms * std::max(j_per_sm, 1)));
+  mendel_join_emit_kernel<<<j_grid, kMB, j_smem, st>>>(ctx->d_tab, A, d_out, cap);
   DNV_CUDA(cudaGetLastError());
   unsigned long long h[8];
   DNV_CUDA(cudaMemcpyAsync(h, A.totals, sizeof(h), cudaMemcpyDeviceToHost, st));
