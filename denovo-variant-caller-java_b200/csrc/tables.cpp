@@ -125,9 +125,12 @@ void build_tables(const dnv_params& p, Tables* t) {
   // so the site is not de novo when log2(likelihood ratio best / alternative) < log2(9 T (1 - mu) / mu) - 0.0205;
   // another 0.05 bits cover the 16.16 fixed point (<= 3 products of depth <= 127 counts, 2^-17 each) and FP64 rounding.
   // Only sites whose smallest relevant term stays a NORMAL double in the reference's raw-exp sums are decided.
+  // MAP: the argmax triple is de novo only if some de novo triple beats every Mendelian one; max <= sum, so the same
+  // test with T = 1 proves the argmax Mendelian (the log-domain sums of the MAP path round by ~1e-13: inside the margin).
   t->l3_lambda_fx = 0;
   t->l3_max_depth = 0;
-  if (t->early_ok) {
+  const bool map_ok = t->fast_ok && fits && log2r[0] > log2r[1] && p.method == DNV_METHOD_MAP && mu < 0.01;
+  if (t->early_ok || map_ok) {
     const long double lam = log2l(9.0L * (long double)thr_eff * (1.0L - (long double)mu) / (long double)mu) - 0.0705L;
     const long double room = 690.0L - fabsl(logl((long double)mu / 2304.0L));
     const long double per_read = fabsl(logl(le) - logl(3.0L));

@@ -337,7 +337,7 @@ int launch_trio_chunk(dnv_ctx* ctx, const ChunkArgs& a) {
     for (int x = 0; x < 4; x++) sk.w[x] = ctx->h_tab.scr_w[x];
     sk.shift32 = 32;
     static const bool no_l3 = std::getenv("DNV_NO_LEVEL3") != nullptr;  // A/B knob
-    sk.l3_lambda = (map || no_l3) ? 0 : ctx->h_tab.l3_lambda_fx;
+    sk.l3_lambda = no_l3 ? 0 : ctx->h_tab.l3_lambda_fx;
     sk.l3_max_depth = ctx->h_tab.l3_max_depth;
     sk.ktrace = ch.ktrace;
     sk.ktrace_seq = ch.ktrace_seq;

@@ -165,3 +165,6 @@ def test_level3_never_discards_a_site_the_reference_calls(eps, mu, lrt):
         shallow = counts[:9000].astype(np.int64).sum(axis=(1, 2)) <= consts[3]   # within level 3's depth limit
         assert shallow.sum() > 300 and dec[:9000][shallow].mean() > 0.1   # it decides a good share of the pattern sites
         assert ref[method][:9000].sum() > 100    # ... while plenty of them are real calls, none of which it touched
+        if method == "denovo_bayes" and mu < 0.01:
+            # MAP uses the T = 1 constants: a de novo argmax needs a de novo triple above every Mendelian one
+            assert not ref["denovo_map"][dec].any(), "level 3 discarded a site whose MAP triple is de novo"
