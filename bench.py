@@ -413,6 +413,15 @@ def genome_walk(D, torch, np, dist, eng, stream, gather, rank, world, local, chu
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     k = 0
     with torch.cuda.stream(stream):
+        # untimed: four chunk-sized batches so that every lane of the context has its scratch for 2^26-site chunks
+        # (a one-time cudaMalloc per lane and process: 86 ms for the first walk of a fresh context, 18 ms for the next)
+        warm_calls = torch.zeros((cap, D.CALL_DT.itemsize), dtype=torch.uint8, device="cuda")
+        eng.synth_counts_device(seed, lo, min(chunk, hi - lo), bufs[0], depth=DEPTH)
+        for _ in range(4):
+            eng.infer_device_async(bufs[0], min(chunk, hi - lo), warm_calls, cap, h.data_ptr(), site_base=lo)
+        eng.flush()
+        eng.sync()
+        del warm_calls
         for first in range(lo, hi, chunk):
             m = min(chunk, hi - first)
             b = k % 2

@@ -13,6 +13,7 @@ LIB = os.path.join(ROOT, "denovo-variant-caller-java_b200", "lib", "libdenovo_b2
 WANT = [("trio_screen_kernel<u16, 2 buffers>", "trio_screen_kernelILb0ELi2E"), ("trio_screen_kernel<u8, 2 buffers>", "trio_screen_kernelILb1ELi2E"),
         ("trio_list_kernel<u16, BAYES/LRT>", "trio_list_kernelILb0ELb0E"), ("trio_list_kernel<u16, MAP>", "trio_list_kernelILb0ELb1E"),
         ("trio_calls_finish_kernel<BAYES/LRT>", "trio_calls_finish_kernelILb0E"), ("trio_fast_kernel (all sites, BAYES)", "trio_fast_kernelILb1ELb0ELb0ELi3ELb0E"),
+        ("pileup_pipe_kernel<8> (producer / consumer pipeline)", "pileup_pipe_kernelILi8E"), ("pileup_windows_kernel", "pileup_windows_kernel"),
         ("pileup_stage_kernel<8>", "pileup_stage_kernelILi8E"), ("pileup_scatter_kernel", "pileup_scatter_kernel"),
         ("pileup_screen_kernel (fused)", "pileup_screen_kernel"), ("mendel_admit_compact_kernel", "mendel_admit_compact_kernel"),
         ("mendel_join_emit_kernel", "mendel_join_emit_kernel"), ("gather_arrive_kernel", "gather_arrive_kernel"),
