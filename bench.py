@@ -35,7 +35,7 @@ BYTES_PER_SITE = 24.125
 FLOP_PER_SITE = 451.0
 # DRAM traffic of one screen launch over 10M sites from the ncu --set full capture committed under profiles/
 # (dram__bytes_read.sum + dram__bytes_write.sum), per site
-NCU_TRAFFIC_BYTES_PER_SITE = 26.05
+NCU_TRAFFIC_BYTES_PER_SITE = 25.08  # profiles/r02_read_pipeline_ncu.md: 246.51 MB read + 4.32 MB written per 10 M sites
 
 
 def load_peaks():
@@ -249,7 +249,7 @@ def aux_undecided(D, torch, np, local, fractions, n=10_000_000, steps=8):
             ref = O.infer(O.params(EPS, MU, LRT), sample, threads=os.cpu_count() or 1)
             got = calls[:int(h[0])].cpu().numpy().view(D.CALL_DT).reshape(-1)
             ok = bool(np.array_equal(got["site"][got["site"] < m], np.nonzero(ref["denovo_bayes"])[0]))
-            out.append({"hostile_fraction": f, "path": "all-sites fused kernel (adaptive)" if st["n_screened_out"] == 0 and f > 0.15 else "screen + list",
+            out.append({"hostile_fraction": f, "path": "all-sites fused kernel (adaptive)" if st["n_screened_out"] == 0 else "screen + list",
                         "ms_per_step": ms, "sites_per_s": n / ms * 1e3, "calls_per_step": st["n_calls"] // steps,
                         "parity_100k_sample_vs_oracle": ok})
             if not ok:
@@ -706,7 +706,7 @@ def main():
             aux["config3_LRT_T10"] = aux_read_config(D, torch, local, "LRT", DEPTH, EPS, MU, 10.0, n, SEED)
             aux["config2_mendel_filter"] = aux_mendel(D, torch, np, local)
             aux["pileup_and_reads_to_calls"] = aux_pileup(D, torch, np, local)
-            aux["undecided_sweep"] = aux_undecided(D, torch, np, local, args.undecided if args.undecided else [0.01, 0.1, 0.5, 1.0])
+            aux["undecided_sweep"] = aux_undecided(D, torch, np, local, args.undecided if args.undecided else [0.01, 0.1, 0.25, 0.5, 1.0])
         barrier()
 
     if rank != 0:

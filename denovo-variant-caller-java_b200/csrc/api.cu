@@ -183,8 +183,9 @@ bool will_screen(const dnv_ctx* ctx, bool dense) {
 // Per chunk: the screen, unless recent batches were screen-hostile.  The screen pays when it decides most sites
 // (99 % of a genome-wide or candidate-file pileup); on inputs that are mostly de-novo-pattern sites — e.g. the
 // Mendelian-inconsistent candidates FULL mode passes from the VARIANT filter to READ mode
-// (M/DenovoRunner.java:173-182) — everything it leaves goes through the list kernel at ~175 ns per site, and above
-// ~15 % undecided the all-sites fused kernel (trio_fast.cuh, ~34 ns per site) wins.  Both paths return identical
+// (M/DenovoRunner.java:173-182) — everything it leaves goes through the list and finish kernels, built for short
+// lists (measured: 53 us + ~0.7 us per 1000 undecided sites of a 10 M-site batch), and above ~5 % undecided the
+// all-sites fused kernel (trio_fast.cuh, ~34 ns per site) wins.  Both paths return identical
 // records; while in dense mode every 32nd chunk is screened again to re-measure the mix.
 bool pick_screen(dnv_ctx* ctx, bool dense) {
   if (!will_screen(ctx, dense)) return false;
@@ -447,7 +448,7 @@ int dnvi_finish_stats(dnv_ctx* ctx, int64_t n_sites) {
   ctx->stats.n_hard = (int64_t)ctx->h_acc[2];
   ctx->stats.n_screened_out = ctx->sites_screened - (int64_t)ctx->h_acc[1];
   if (ctx->sites_screened >= 4096 && !getenv("DNV_NO_DENSE_MODE"))
-    ctx->dense_mode = (double)ctx->h_acc[1] > 0.15 * (double)ctx->sites_screened;
+    ctx->dense_mode = (double)ctx->h_acc[1] > 0.05 * (double)ctx->sites_screened;
   ctx->sites_screened = 0;
   return DNV_OK;
 }

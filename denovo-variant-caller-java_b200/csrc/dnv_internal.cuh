@@ -134,7 +134,7 @@ struct dnv_ctx {
   unsigned long long epoch;           // launch tag of the compaction kernel's status words
   bool screened;           // the last call used the screen
   int64_t sites_screened;  // sites that went through the screen since the statistics were last collected
-  bool dense_mode;         // recent batches left > 15 % of their sites undecided: the all-sites fused kernel is faster
+  bool dense_mode;         // recent batches left > 5 % of their sites undecided: the all-sites fused kernel is faster
   int dense_probe;         // chunks since dense_mode last sent one through the screen to re-measure
   bool capturing;          // a CUDA graph of the current submission is being captured (no allocation allowed)
   bool use_graphs;         // DNV_GRAPHS=0 turns graph replay off
