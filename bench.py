@@ -630,7 +630,8 @@ def main():
     # ---- the same step through the synchronous entry point (one call = submit + wait + count on the host), on the
     # product context (lanes + graph replay), and the kernel times on the serial, event-bracketed context
     cptr, clptr = d_counts[0], (d_calls[0] if d_calls is not None else torch.zeros((cap, D.CALL_DT.itemsize), dtype=torch.uint8, device="cuda"))
-    sync_s = timed_sync_calls(lambda: eng.infer_device(cptr, n, clptr, cap), 30)
+    cp_raw, cl_raw = cptr.data_ptr(), clptr.data_ptr()  # raw addresses: the loop times the C entry point, not torch's accessors
+    sync_s = timed_sync_calls(lambda: eng.infer_device(cp_raw, n, cl_raw, cap), 30)
     Kt = 20
     for _ in range(3):
         eng_t.infer_device(cptr, n, clptr, cap)

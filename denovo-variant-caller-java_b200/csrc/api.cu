@@ -125,7 +125,7 @@ static int init_ctx(dnv_ctx* ctx) {
   }
   DNV_CUDA(cudaMalloc(&ctx->d_tab, sizeof(Tables)));
   DNV_CUDA(cudaMalloc(&ctx->d_counters, kCtrWords * sizeof(unsigned long long)));
-  DNV_CUDA(cudaHostAlloc((void**)&ctx->h_acc, 4 * sizeof(unsigned long long), cudaHostAllocDefault));
+  DNV_CUDA(cudaHostAlloc((void**)&ctx->h_acc, 16 * sizeof(unsigned long long), cudaHostAllocDefault));  // [0..3] acc, [8..15] pileup status (pileup.cu)
   // the kernels run on non-blocking streams, which do not order against the legacy default stream: the
   // uploads go through the context's own stream and are complete before dnv_create returns
   DNV_CUDA(cudaMemcpyAsync(ctx->d_tab, &ctx->h_tab, sizeof(Tables), cudaMemcpyHostToDevice, ctx->own_stream));
@@ -238,20 +238,25 @@ int collect(dnv_ctx* ctx) {
   return DNV_OK;
 }
 
-// chunk size of one device-resident batch: a synchronous call is split over the lanes (the tail of one chunk
-// hides behind the screen of the next); asynchronous batches overlap with each other and stay whole
+// chunk size of one device-resident batch: a LARGE synchronous call is split evenly over the lanes (the tail of one
+// chunk hides behind the screen of the next); asynchronous batches overlap with each other and stay whole.  The
+// chunks' list kernels are chained (record ranges) and each costs ~20 us of latency whatever its length, and only a
+// call that is ONE chunk ends with its finish kernel (CallChain::host_acc), so a split pays when the exposed tail
+// (~0.7 us per 1000 undecided sites) outweighs both.  Measured (benchmarks/time_sync_call.py): 10 M sites 92 us
+// whole / 130 us in three chunks; 40 M sites 236 us whole / 263 us in three.  One more chunk per kSplitSites sites,
+// up to one per lane; DNV_SYNC_MIN_CHUNK overrides kSplitSites (A/B, and the tests' way onto the split path).
 static int64_t chunk_for(const dnv_ctx* ctx, int64_t n, bool split) {
   const int64_t full = device_chunk();
   if (!split || !parallel(ctx) || getenv("DNV_DEVICE_CHUNK")) return full;
-  constexpr int64_t kMinChunk = 1ll << 20;
-  int64_t c = (n + ctx->n_lanes - 1) / ctx->n_lanes;
-  c = std::max(c, kMinChunk);
+  static const int64_t kSplitSites = [] { const char* e = getenv("DNV_SYNC_MIN_CHUNK"); const long long v = e ? atoll(e) : 0; return v > 0 ? (int64_t)v : (int64_t)(1ll << 25); }();
+  const int64_t k = std::max<int64_t>(1, std::min<int64_t>(ctx->n_lanes, n / kSplitSites));
+  int64_t c = (n + k - 1) / k;
   c = (c + 127) / 128 * 128;  // chunk boundaries keep the 16-byte alignment the bulk copies want
-  return std::min(c, full);
+  return std::min(std::max<int64_t>(c, 128), full);
 }
 
 int enqueue_device_batch(dnv_ctx* ctx, const void* d_counts, int bps, int64_t n, int64_t site_base, dnv_site_result* d_dense,
-                         dnv_call* d_calls, int64_t cap, int64_t* count_out, bool split, bool no_sub_wait) {
+                         dnv_call* d_calls, int64_t cap, int64_t* count_out, bool split, bool no_sub_wait, bool collect_to_host) {
   ctx->count_bytes = bps;
   const int64_t chunk = chunk_for(ctx, n, split);
   for (int64_t off = 0; off < n; off += chunk) {
@@ -271,6 +276,7 @@ int enqueue_device_batch(dnv_ctx* ctx, const void* d_counts, int bps, int64_t n,
     a.reads = nullptr;
     a.dense_host = nullptr;
     a.done_ev = nullptr;
+    a.collect_to_host = collect_to_host && a.first && a.last;
     const int rc = launch_trio_chunk(ctx, a);
     if (rc) return rc;
   }
@@ -554,6 +560,11 @@ static int infer_device_impl(dnv_ctx* ctx, const void* d_counts, int bps, int64_
   int rc = drain_async(ctx);
   if (rc) return rc;
   reset_call_state(ctx);
+  // A call that is ONE chunk on the calls-only pipeline ends with its finish kernel: the kernel's last CTA hands the
+  // accumulators to the host (CallChain::host_acc), no copy / memset behind it (DNV_NO_HOST_COLLECT=1: A/B knob)
+  static const bool no_host_collect = getenv("DNV_NO_HOST_COLLECT") != nullptr || getenv("DNV_DEBUG_SKIP") != nullptr;
+  const bool one = !no_host_collect && parallel(ctx) && !ctx->dense_mode && n > 0 && n <= chunk_for(ctx, n, true) &&
+                   will_screen(ctx, d_dense != nullptr);
   // the whole call — chunks over the lanes, join, statistics to the host — is replayable when its arguments repeat
   bool launched = false;
   if (ctx->use_graphs && !ctx->dense_mode && n > 0 && will_screen(ctx, d_dense != nullptr)) {
@@ -566,8 +577,8 @@ static int infer_device_impl(dnv_ctx* ctx, const void* d_counts, int bps, int64_
       DNV_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
       ctx->capturing = true;
       rc = begin_submit(ctx);
-      if (!rc) rc = enqueue_device_batch(ctx, d_counts, bps, n, 0, d_dense, d_calls, cap, nullptr, /*split=*/true, false);
-      if (!rc) rc = enqueue_collect(ctx);
+      if (!rc) rc = enqueue_device_batch(ctx, d_counts, bps, n, 0, d_dense, d_calls, cap, nullptr, /*split=*/true, false, one);
+      if (!rc) rc = one ? flush_lanes(ctx) : enqueue_collect(ctx);
       rc = end_capture(ctx, ctx->stream, rc, &ge->exec);
       if (rc) return rc;
       ctx->lane_next = 0;
@@ -586,10 +597,16 @@ static int infer_device_impl(dnv_ctx* ctx, const void* d_counts, int bps, int64_
   if (!launched) {
     rc = begin_submit(ctx);
     if (rc) return rc;
-    rc = enqueue_device_batch(ctx, d_counts, bps, n, 0, d_dense, d_calls, cap, nullptr, /*split=*/true, false);
+    rc = enqueue_device_batch(ctx, d_counts, bps, n, 0, d_dense, d_calls, cap, nullptr, /*split=*/true, false, one);
     if (rc) return rc;
-    rc = collect(ctx);
-    if (rc) return rc;
+    if (one) {
+      rc = flush_lanes(ctx);
+      if (rc) return rc;
+      DNV_CUDA(cudaStreamSynchronize(ctx->stream));
+    } else {
+      rc = collect(ctx);
+      if (rc) return rc;
+    }
   }
   rc = dnvi_finish_stats(ctx, n);
   if (rc) return rc;

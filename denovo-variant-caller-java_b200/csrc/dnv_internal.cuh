@@ -58,6 +58,8 @@ struct CallChain {
   unsigned long long* work;          // [0] tile / block ticket, [1] CTAs gone (reset by the launch that used them)
   int64_t* count_out;                // where the batch's running call total is published for the caller, or null
   int last;                          // last chunk of its batch
+  unsigned long long* host_acc;      // non-null (single-chunk synchronous call): pinned host words that receive acc[0..3] when the
+  unsigned long long* fin_gone;      // finish kernel's last CTA leaves (fin_gone counts them); acc restarts at zero
   unsigned long long* ktrace;        // DNV_KTRACE: the lane's time-line slots (6 words per chunk), or null
   const unsigned int* ktrace_seq;    // ... and which slot the lane is at (bumped after every chunk, so graph replays advance)
 };
@@ -146,9 +148,10 @@ struct dnv_ctx {
   int count_bytes;                    // bytes per site of the current call's counts: 24 (uint16) or 12 (uint8)
   int64_t* d_call_idx;     // global site index of every call, input order (unscreened path)
   int64_t call_idx_cap;
-  // [0..15] chain pairs (lane x parity x 2), [16..19] acc, [23] always zero, [24 + 2 * lane ..] tickets of the lane
+  // [0..15] chain pairs (lane x parity x 2), [16..19] acc, [20] finish CTAs gone (host-collecting launches), [23] always zero,
+  // [24 + 2 * lane ..] tickets of the lane
   unsigned long long* d_counters;
-  unsigned long long* h_acc;       // pinned [4]: acc as last collected
+  unsigned long long* h_acc;       // pinned [16]: [0..3] acc as last collected, [8..15] status words of the last pileup
   // staging of the host API
   uint16_t* d_stage_counts[2];
   dnv_site_result* d_stage_dense[2];
@@ -188,7 +191,7 @@ struct dnv_ctx {
 extern "C" int dnvi_finish_stats(dnv_ctx* ctx, int64_t n_sites);
 
 namespace dnv {
-constexpr int kCtrAcc = 16, kCtrZero = 23, kCtrWork = 24, kCtrWords = 32;
+constexpr int kCtrAcc = 16, kCtrFinGone = 20, kCtrZero = 23, kCtrWork = 24, kCtrWords = 32;
 
 // reads of a chunk whose sites are given as positions (fused reads -> calls path; device pointers)
 struct ReadsArgs {
@@ -213,6 +216,7 @@ struct ChunkArgs {
                            // fused pileup-screen kernel (pileup_scatter.cuh) instead of the screen kernel
   dnv_site_result* dense_host;  // host API: where the chunk's dense records go (copied on the chunk's stream), or null
   cudaEvent_t done_ev;     // recorded when the chunk no longer needs its input (staging ring of the host API), or null
+  bool collect_to_host = false;  // the chunk is a whole synchronous call: its finish kernel delivers the statistics (CallChain::host_acc)
 };
 constexpr int kKtraceSlots = 1024;  // per lane
 // which: 0 screen, 1 list, 2 finish; first CTA start -> word 2*which (min), last CTA end -> word 2*which+1 (max)
@@ -238,7 +242,7 @@ int collect(dnv_ctx* ctx);
 void reset_call_state(dnv_ctx* ctx);
 int ensure_stage_calls(dnv_ctx* ctx, int64_t calls_cap);
 int enqueue_device_batch(dnv_ctx* ctx, const void* d_counts, int bps, int64_t n, int64_t site_base, dnv_site_result* d_dense,
-                         dnv_call* d_calls, int64_t cap, int64_t* count_out, bool split, bool no_sub_wait);
+                         dnv_call* d_calls, int64_t cap, int64_t* count_out, bool split, bool no_sub_wait, bool collect_to_host = false);
 bool will_screen(const dnv_ctx* ctx, bool dense);
 bool pick_screen(dnv_ctx* ctx, bool dense);
 int enqueue_host_batch(dnv_ctx* ctx, const void* counts, int bps, int64_t n, int64_t site_base, dnv_site_result* dense,

@@ -24,22 +24,44 @@ __global__ void __launch_bounds__(256)
 pileup_prep_kernel(const int64_t* __restrict__ read_start, const int64_t* __restrict__ base_off,
                    const uint8_t* __restrict__ person, int64_t n_reads, long long* __restrict__ meta) {
   long long lmax = 0;
-  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += (int64_t)gridDim.x * blockDim.x) {
-    const long long len = base_off[r + 1] - base_off[r];
-    lmax = len > lmax ? len : lmax;
-    const int p = person[r];
-    if (p > 2 || len < 0) { atomicMax((unsigned long long*)&meta[5], pileup_err(r, false, kPileErrInvalid)); continue; }
-    if (r == 0) {
-      for (int q = 0; q <= p; q++) meta[q] = 0;
-    } else {
-      const int pp = person[r - 1];
-      if (pp > p || (pp == p && read_start[r - 1] > read_start[r])) {
-        atomicMax((unsigned long long*)&meta[5], pileup_err(r, false, kPileErrUnsorted));
-      }
-      for (int q = pp + 1; q <= p; q++) meta[q] = r;
+  // four reads per thread and trip, every load of a trip issued before the first is used (the kernel is a
+  // 17 B/read stream: it wants bytes in flight, not instructions)
+  constexpr int kU = 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t r0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r0 < n_reads; r0 += kU * stride) {
+    long long b0[kU], b1[kU], s0[kU], s1[kU];
+    int pc[kU], pv[kU];
+#pragma unroll
+    for (int k = 0; k < kU; k++) {
+      const int64_t r = r0 + k * stride;
+      const bool ok = r < n_reads, has_prev = ok && r > 0;
+      b0[k] = ok ? __ldg(base_off + r) : 0;
+      b1[k] = ok ? __ldg(base_off + r + 1) : 0;
+      s1[k] = ok ? __ldg(read_start + r) : 0;
+      s0[k] = has_prev ? __ldg(read_start + r - 1) : 0;
+      pc[k] = ok ? (int)__ldg(person + r) : 0;
+      pv[k] = has_prev ? (int)__ldg(person + r - 1) : 0;
     }
-    if (r == n_reads - 1)
-      for (int q = p + 1; q <= 3; q++) meta[q] = n_reads;
+#pragma unroll
+    for (int k = 0; k < kU; k++) {
+      const int64_t r = r0 + k * stride;
+      if (r >= n_reads) continue;
+      const long long len = b1[k] - b0[k];
+      lmax = len > lmax ? len : lmax;
+      const int p = pc[k];
+      if (p > 2 || len < 0) { atomicMax((unsigned long long*)&meta[5], pileup_err(r, false, kPileErrInvalid)); continue; }
+      if (r == 0) {
+        for (int q = 0; q <= p; q++) meta[q] = 0;
+      } else {
+        const int pp = pv[k];
+        if (pp > p || (pp == p && s0[k] > s1[k])) {
+          atomicMax((unsigned long long*)&meta[5], pileup_err(r, false, kPileErrUnsorted));
+        }
+        for (int q = pp + 1; q <= p; q++) meta[q] = r;
+      }
+      if (r == n_reads - 1)
+        for (int q = p + 1; q <= 3; q++) meta[q] = n_reads;
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -57,29 +79,21 @@ extern "C" {
 
 static int pileup_status(long long* h);
 
-int dnv_pileup_device(dnv_ctx* ctx, const int64_t* d_read_start, const int64_t* d_base_off, const char* d_bases,
-                      const uint8_t* d_person, int64_t n_reads, const int64_t* d_site_pos, int64_t n_sites,
-                      uint16_t* d_counts_out) {
-  if (!ctx || n_reads < 0 || n_sites < 0 || (n_sites > 0 && (!d_site_pos || !d_counts_out)) ||
-      (n_reads > 0 && (!d_read_start || !d_base_off || !d_bases || !d_person))) {
-    set_error("dnv_pileup_device: invalid argument");
-    return DNV_E_INVALID;
-  }
-  if (n_sites == 0) return DNV_OK;
-  if ((reinterpret_cast<uintptr_t>(d_counts_out) & 7) || (reinterpret_cast<uintptr_t>(d_read_start) & 7) ||
-      (reinterpret_cast<uintptr_t>(d_base_off) & 7) || (reinterpret_cast<uintptr_t>(d_site_pos) & 7)) {
-    set_error("dnv_pileup_device: counts, read_start, base_off and site_pos must be 8-byte aligned");
-    return DNV_E_INVALID;
-  }
-  DNV_CUDA(cudaSetDevice(ctx->device));
+// Everything dnv_pileup_device does on the device, enqueued on the context's stream without a host wait: validation /
+// metadata pass, windows pre-pass, pileup kernel, and the status words (meta[0..7]) on their way to the context's
+// pinned status buffer.  The caller waits for the stream and then decodes them with pileup_status(pile_host(ctx)).
+static long long* pile_host(dnv_ctx* ctx) { return reinterpret_cast<long long*>(ctx->h_acc + 8); }
+
+static int pileup_enqueue(dnv_ctx* ctx, const int64_t* d_read_start, const int64_t* d_base_off, const char* d_bases,
+                          const uint8_t* d_person, int64_t n_reads, const int64_t* d_site_pos, int64_t n_sites,
+                          uint16_t* d_counts_out) {
   // scratch: meta[8] (see pileup_prep_kernel), then one record per tile of the pipeline kernel
   const int64_t n_tiles = (n_sites + kPP_Consumers * 8 - 1) / (kPP_Consumers * 8);
   int rc = ensure_scratch(ctx, 64 + (size_t)n_tiles * kPP_TileWords * sizeof(long long));
   if (rc) return rc;
   long long* meta = (long long*)ctx->d_scratch;
   DNV_CUDA(cudaMemsetAsync(meta, 0, 64, ctx->stream));
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  const int sms = ctx->sms;
   if (n_reads > 0) {
     const int grid = (int)std::min<int64_t>((n_reads + 255) / 256, (int64_t)sms * 8);
     pileup_prep_kernel<<<grid, 256, 0, ctx->stream>>>(d_read_start, d_base_off, d_person, n_reads, meta);
@@ -103,10 +117,29 @@ int dnv_pileup_device(dnv_ctx* ctx, const int64_t* d_read_start, const int64_t* 
     if (rc2) return rc2;
   }
   DNV_CUDA(cudaGetLastError());
-  long long h[8];
-  DNV_CUDA(cudaMemcpyAsync(h, meta, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  DNV_CUDA(cudaMemcpyAsync(pile_host(ctx), meta, 8 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  return DNV_OK;
+}
+
+int dnv_pileup_device(dnv_ctx* ctx, const int64_t* d_read_start, const int64_t* d_base_off, const char* d_bases,
+                      const uint8_t* d_person, int64_t n_reads, const int64_t* d_site_pos, int64_t n_sites,
+                      uint16_t* d_counts_out) {
+  if (!ctx || n_reads < 0 || n_sites < 0 || (n_sites > 0 && (!d_site_pos || !d_counts_out)) ||
+      (n_reads > 0 && (!d_read_start || !d_base_off || !d_bases || !d_person))) {
+    set_error("dnv_pileup_device: invalid argument");
+    return DNV_E_INVALID;
+  }
+  if (n_sites == 0) return DNV_OK;
+  if ((reinterpret_cast<uintptr_t>(d_counts_out) & 7) || (reinterpret_cast<uintptr_t>(d_read_start) & 7) ||
+      (reinterpret_cast<uintptr_t>(d_base_off) & 7) || (reinterpret_cast<uintptr_t>(d_site_pos) & 7)) {
+    set_error("dnv_pileup_device: counts, read_start, base_off and site_pos must be 8-byte aligned");
+    return DNV_E_INVALID;
+  }
+  DNV_CUDA(cudaSetDevice(ctx->device));
+  const int rc = pileup_enqueue(ctx, d_read_start, d_base_off, d_bases, d_person, n_reads, d_site_pos, n_sites, d_counts_out);
+  if (rc) return rc;
   DNV_CUDA(cudaStreamSynchronize(ctx->stream));
-  return pileup_status(h);
+  return pileup_status(pile_host(ctx));
 }
 
 // decodes the error word the pileup kernels leave in meta[5]
@@ -202,9 +235,16 @@ int dnv_infer_reads_device(dnv_ctx* ctx, const int64_t* d_read_start, const int6
   const char* fused_env = getenv("DNV_READS_FUSED");
   const bool want_fused = fused_env && fused_env[0] == '1';
   if (!want_fused || !will_screen(ctx, false) || ctx->dense_mode) {
-    int rc = dnv_pileup_device(ctx, d_read_start, d_base_off, d_bases, d_person, n_reads, d_site_pos, n_sites, ctx->d_reads_counts);
+    // one host wait for both: the pileup's status words reach the host in stream order before the statistics of
+    // the inference, which starts on the device as soon as the counts are complete (a pileup that failed leaves
+    // counts that are numbers all the same; its error is what the caller gets)
+    int rc = pileup_enqueue(ctx, d_read_start, d_base_off, d_bases, d_person, n_reads, d_site_pos, n_sites, ctx->d_reads_counts);
     if (rc) return rc;
-    return dnv_infer_counts_device(ctx, ctx->d_reads_counts, n_sites, nullptr, d_calls, cap, n_calls);
+    const int rc_infer = dnv_infer_counts_device(ctx, ctx->d_reads_counts, n_sites, nullptr, d_calls, cap, n_calls);
+    DNV_CUDA(cudaStreamSynchronize(ctx->stream));  // (already idle unless the inference failed before its own wait)
+    rc = pileup_status(pile_host(ctx));
+    if (rc) { *n_calls = 0; return rc; }
+    return rc_infer;
   }
   int rc = ensure_scratch(ctx, 64);
   if (rc) return rc;

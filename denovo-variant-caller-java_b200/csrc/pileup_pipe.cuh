@@ -385,15 +385,10 @@ pileup_pipe_kernel(const int64_t* __restrict__ read_start, const int64_t* __rest
   }
 }
 
-// pre-pass 1 (streaming): marks the tiles whose positions are not consecutive in word 7 of their (zeroed) records
-__global__ void __launch_bounds__(256)
-pileup_breaks_kernel(const int64_t* __restrict__ site_pos, int64_t n_sites, int tile_sites, long long* __restrict__ tiles) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i + 1 < n_sites; i += (int64_t)gridDim.x * blockDim.x) {
-    if (__ldg(site_pos + i + 1) != __ldg(site_pos + i) + 1 && (i + 1) % tile_sites != 0) tiles[i / tile_sites * kPP_TileWords + 7] = 1;
-  }
-}
-
-// pre-pass 2: one warp per tile writes the tile's record (kPP_TileWords words)
+// pre-pass: one warp per tile writes the tile's record (kPP_TileWords words): the six window bounds and whether the
+// tile's positions are consecutive (site_pos[s0 + i] == P0 + i: 32 coalesced loads per lane, all issued before the
+// searches' dependent rounds so that they are in flight together).  Round 2 had a separate streaming kernel for the
+// density flags (18 us + a memset of the records per 8 M positions).
 __global__ void __launch_bounds__(256)
 pileup_windows_kernel(const int64_t* __restrict__ read_start, const long long* __restrict__ meta,
                       const int64_t* __restrict__ site_pos, int64_t n_sites, int tile_sites, int stage_limit,
@@ -406,11 +401,20 @@ pileup_windows_kernel(const int64_t* __restrict__ read_start, const long long* _
   const int64_t s0 = tile * tile_sites;
   const int n_live = (int)min((int64_t)tile_sites, n_sites - s0);
   const int64_t P0 = __ldg(site_pos + s0);
+  bool gap = false;
+  for (int i0 = 0; i0 < n_live; i0 += 32 * 8) {
+    long long v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int i = i0 + 32 * k + lane;
+      v[k] = i < n_live ? __ldg(site_pos + s0 + i) : P0 + i;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) gap |= v[k] != P0 + (i0 + 32 * k + lane);
+  }
   int64_t win[6];
   ps_warp_upper_bound6(read_start, meta, P0 - lmax, P0 + n_live - 1, lane, win);
-  // word 7 comes in as "some neighbouring positions of this tile are not consecutive" (pileup_breaks_kernel, 0 = none)
-  const bool dense = lmax > 0 && lmax <= stage_limit && tiles[tile * kPP_TileWords + 7] == 0;
-  __syncwarp();
+  const bool dense = lmax > 0 && lmax <= stage_limit && !__any_sync(0xffffffffu, gap);
   long long w = lane == 6 ? P0 : lane == 7 ? (dense ? 1 : 0) : 0;
 #pragma unroll
   for (int q = 0; q < 6; q++) w = lane == q ? win[q] : w;
@@ -432,9 +436,6 @@ static cudaError_t launch_pileup_pipe(cudaStream_t st, int sms, const int64_t* d
   constexpr int kSites = kPP_Consumers * S;
   const int64_t n_tiles = (n_sites + kSites - 1) / kSites;
   const int64_t wblocks = (n_tiles * 32 + 255) / 256;
-  e = cudaMemsetAsync(tiles, 0, (size_t)n_tiles * kPP_TileWords * sizeof(long long), st);
-  if (e != cudaSuccess) return e;
-  pileup_breaks_kernel<<<(unsigned)std::min<int64_t>((n_sites + 255) / 256, (int64_t)sms * 8), 256, 0, st>>>(d_site_pos, n_sites, kSites, tiles);
   pileup_windows_kernel<<<(unsigned)wblocks, 256, 0, st>>>(d_read_start, meta, d_site_pos, n_sites, kSites,
                                                            std::min(kPP_StageBytes - 16, 0x7FFFFFFF), tiles);
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)sms * std::max(per_sm, 1)));

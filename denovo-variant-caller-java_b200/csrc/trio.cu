@@ -303,6 +303,7 @@ int launch_trio_chunk(dnv_ctx* ctx, const ChunkArgs& a) {
   const int li = screen ? ctx->lane_next : 0;
   if (screen) ctx->lane_next = (ctx->lane_next + 1) % ctx->n_lanes;
   TrioLane& ln = ctx->lane[li];
+  if (a.collect_to_host && !screen) { set_error("internal: host-collecting chunk on the unscreened path"); return DNV_E_INVALID; }
   // st: where the chunk starts (the screen, or the whole unscreened path); tl: where its tail runs
   cudaStream_t st = lane_stream(ctx, li), tl = screen ? lane_tail(ctx, li) : st;
   // (the lane's own stream has already waited for the lane's previous tail — see the end of this function — so
@@ -321,6 +322,8 @@ int launch_trio_chunk(dnv_ctx* ctx, const ChunkArgs& a) {
   ch.work = ctx->d_counters + kCtrWork + 2 * li;
   ch.count_out = a.count_out;
   ch.last = a.last ? 1 : 0;
+  ch.host_acc = a.collect_to_host ? ctx->h_acc : nullptr;
+  ch.fin_gone = ctx->d_counters + kCtrFinGone;
   ch.ktrace = ctx->d_ktrace ? ctx->d_ktrace + (size_t)li * kKtraceSlots * 6 : nullptr;
   ch.ktrace_seq = ctx->d_ktrace ? ctx->d_ktrace_seq + li : nullptr;
   ctx->chain_prev = ch.pair + 1;

@@ -288,21 +288,24 @@ for method in ("BAYES", "MAP"):
         c = torch.empty((n, 12), dtype=torch.int16, device="cuda")
         eng.synth_counts_device(0x5EED0003, 77, n, c, depth=30)
         calls = torch.zeros((n, D.CALL_DT.itemsize), dtype=torch.uint8, device="cuda")
-        k = eng.infer_device(c, n, calls, n)
+        for _ in range(3):  # the third call replays the graph captured by the second
+            k = eng.infer_device(c, n, calls, n)
         st = eng.stats()
         out.append(calls[:k].cpu().numpy().tobytes())
         out.append(np.array([k, st["n_calls"], st["n_screened_out"]], np.int64).tobytes())
 sys.stdout.buffer.write(b"".join(out))
 """ % os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "denovo-variant-caller-java_b200", "python")
     res = []
-    for chunk in (None, "65536", "1280"):
+    for chunk in (None, "65536", "1280", "lanes"):
         env = dict(os.environ)
-        if chunk:
+        if chunk == "lanes":  # a synchronous call split over the context's lanes (by default only above 2^24 sites per chunk)
+            env["DNV_SYNC_MIN_CHUNK"] = "65536"
+        elif chunk:
             env["DNV_DEVICE_CHUNK"] = chunk
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, env=env, timeout=600)
         assert r.returncode == 0, r.stderr.decode()[-2000:]
         res.append(r.stdout)
-    assert len(res[0]) > 1000 and res[0] == res[1] == res[2]
+    assert len(res[0]) > 1000 and res[0] == res[1] == res[2] == res[3]
 
 
 def test_async_batches_over_the_lanes_match_synchronous_calls():
