@@ -238,17 +238,18 @@ int collect(dnv_ctx* ctx) {
   return DNV_OK;
 }
 
-// chunk size of one device-resident batch: a LARGE synchronous call is split evenly over the lanes (the tail of one
-// chunk hides behind the screen of the next); asynchronous batches overlap with each other and stay whole.  The
-// chunks' list kernels are chained (record ranges) and each costs ~20 us of latency whatever its length, and only a
-// call that is ONE chunk ends with its finish kernel (CallChain::host_acc), so a split pays when the exposed tail
-// (~0.7 us per 1000 undecided sites) outweighs both.  Measured (benchmarks/time_sync_call.py): 10 M sites 92 us
-// whole / 130 us in three chunks; 40 M sites 236 us whole / 263 us in three.  One more chunk per kSplitSites sites,
-// up to one per lane; DNV_SYNC_MIN_CHUNK overrides kSplitSites (A/B, and the tests' way onto the split path).
+// chunk size of one device-resident batch.  Round 2 first split a synchronous call over the lanes (the tail of one
+// chunk hides behind the screen of the next).  Measured against the whole call in one chunk
+// (benchmarks/time_sync_call.py; us per call whole / in three chunks): 10 M sites 92 / 130, 40 M 236 / 263,
+// 67 M 370 / 389, 100 M 523 / 543 — the chunks' list kernels are chained (record ranges) at ~20 us of latency per
+// link, and only a call that is ONE chunk ends with its finish kernel (CallChain::host_acc).  So a call is split only
+// where it has to be (the scratch is sized for device_chunk() sites); DNV_SYNC_MIN_CHUNK=<sites> asks for one chunk
+// per that many sites, up to one per lane (A/B knob, and the tests' way onto the lane-split path).
 static int64_t chunk_for(const dnv_ctx* ctx, int64_t n, bool split) {
   const int64_t full = device_chunk();
   if (!split || !parallel(ctx) || getenv("DNV_DEVICE_CHUNK")) return full;
-  static const int64_t kSplitSites = [] { const char* e = getenv("DNV_SYNC_MIN_CHUNK"); const long long v = e ? atoll(e) : 0; return v > 0 ? (int64_t)v : (int64_t)(1ll << 25); }();
+  static const int64_t kSplitSites = [] { const char* e = getenv("DNV_SYNC_MIN_CHUNK"); const long long v = e ? atoll(e) : 0; return v > 0 ? (int64_t)v : (int64_t)0; }();
+  if (kSplitSites == 0) return full;
   const int64_t k = std::max<int64_t>(1, std::min<int64_t>(ctx->n_lanes, n / kSplitSites));
   int64_t c = (n + k - 1) / k;
   c = (c + 127) / 128 * 128;  // chunk boundaries keep the 16-byte alignment the bulk copies want

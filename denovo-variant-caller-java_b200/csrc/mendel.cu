@@ -61,7 +61,9 @@ struct MendelArrays {
   unsigned long long* st_max[3];   // running max of end (+1; 0 = none) per parent
   unsigned long long* st_found;    // PositionCalls
   unsigned long long* win;         // per block of kernel B: [lo_mom, hi_mom, lo_dad, hi_dad] + 1 each, 0 = not written
-  unsigned long long* totals;      // [0..2] admitted per person, [3] PositionCalls, [4] error: (record index + 1) << 2 | kind, [6],[7] tickets
+  unsigned long long* totals;      // [0..2] admitted per person, [3] PositionCalls, [4] error: (record index + 1) << 2 | kind,
+                                   // [5] blocks of kernel B gone, [6],[7] tickets
+  unsigned long long* host_totals; // pinned host words: kernel B's last block to leave copies totals[0..4] there
 };
 
 // error word: index and kind travel in ONE atomicMax, so the reported kind always belongs to the reported record
@@ -353,6 +355,16 @@ mendel_join_emit_kernel(const Tables* __restrict__ tab, MendelArrays A, dnv_pcal
   const int64_t i0 = (int64_t)b * kJTile;
   if (i0 >= n_child) {  // no child SNP left
     if (n_child == 0 && b == 0 && threadIdx.x == 0) A.totals[3] = 0;
+    // the last block to leave hands the totals and the error word to the host: the call ends with this kernel, not
+    // with a copy behind it (every block's results — totals[3], atomicMax on totals[4] — precede its arrival)
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(&A.totals[5], 1ull) == (unsigned long long)gridDim.x - 1ull) {
+        __threadfence();
+#pragma unroll
+        for (int q = 0; q < 5; q++) A.host_totals[q] = *(volatile unsigned long long*)&A.totals[q];
+      }
+    }
     break;
   }
   const bool last_live = n_child <= i0 + kJTile;
@@ -520,6 +532,7 @@ int dnv_mendel_filter_device(dnv_ctx* ctx, const dnv_vcall* d_calls, int64_t n, 
   A.totals = (unsigned long long*)(base + o_status + 7 * status_bytes);
   A.win = (unsigned long long*)(base + o_status + 7 * status_bytes + 64);
   A.ref = (uint8_t*)(base + o_ref); A.src = (int64_t*)(base + o_src);
+  A.host_totals = ctx->h_acc + 8;  // pinned status words of the context's synchronous calls (shared with the pileup)
 
   DNV_CUDA(cudaMemsetAsync(base + o_status, 0, 7 * status_bytes + 64 + win_bytes, st));
   if (reinterpret_cast<uintptr_t>(d_calls) & 15) {
@@ -537,9 +550,9 @@ int dnv_mendel_filter_device(dnv_ctx* ctx, const dnv_vcall* d_calls, int64_t n, 
   const int j_grid = std::max(1, std::min(j_blocks, ctx->sms * std::max(j_per_sm, 1)));
   mendel_join_emit_kernel<<<j_grid, kMB, j_smem, st>>>(ctx->d_tab, A, d_out, cap);
   DNV_CUDA(cudaGetLastError());
-  unsigned long long h[8];
-  DNV_CUDA(cudaMemcpyAsync(h, A.totals, sizeof(h), cudaMemcpyDeviceToHost, st));
   DNV_CUDA(cudaStreamSynchronize(st));
+  unsigned long long h[5];
+  for (int q = 0; q < 5; q++) h[q] = A.host_totals[q];  // written by kernel B's last block
   ctx->stats = dnv_stats();
   ctx->stats.n_sites = (int64_t)h[0];
   ctx->stats.n_calls = (int64_t)h[3];

@@ -105,9 +105,12 @@ static int pileup_enqueue(dnv_ctx* ctx, const int64_t* d_read_start, const int64
   // at a time in all of them
   static const std::string which = [] { const char* e = getenv("DNV_PILEUP_KERNEL"); return std::string(e ? e : "pipe"); }();
   const bool aligned16 = ((reinterpret_cast<uintptr_t>(d_read_start) | reinterpret_cast<uintptr_t>(d_base_off)) & 15) == 0;
+  bool status_sent = false;
   if (which == "pipe" && aligned16) {
+    // (the pipeline kernel's last warp to leave writes the status words to the pinned buffer itself)
     DNV_CUDA(launch_pileup_pipe<8>(ctx->stream, sms, d_read_start, d_base_off, d_bases, meta, meta + 8, d_site_pos, n_sites,
-                                   n_reads, d_counts_out));
+                                   n_reads, d_counts_out, pile_host(ctx)));
+    status_sent = true;
   } else if (which == "pipe" || which == "stage") {
     DNV_CUDA(launch_pileup_stage<8>(ctx->stream, sms, d_read_start, d_base_off, d_bases, meta, d_site_pos, n_sites, n_reads,
                                     d_counts_out));
@@ -117,7 +120,7 @@ static int pileup_enqueue(dnv_ctx* ctx, const int64_t* d_read_start, const int64
     if (rc2) return rc2;
   }
   DNV_CUDA(cudaGetLastError());
-  DNV_CUDA(cudaMemcpyAsync(pile_host(ctx), meta, 8 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  if (!status_sent) DNV_CUDA(cudaMemcpyAsync(pile_host(ctx), meta, 8 * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
   return DNV_OK;
 }
 

@@ -67,12 +67,29 @@ struct PipeShared {
   alignas(8) unsigned long long full, empty;
 };
 
+// Every warp of the pipeline kernel passes here on its way out: the last one hands the status words (person
+// offsets, longest read, error word) to the host's pinned buffer, so a call ends with the kernel instead of a copy
+// behind it.  meta[7] counts the warps gone (zeroed with meta by the caller).
+__device__ __forceinline__ void pipe_leave(long long* meta, long long* host_meta, int lane) {
+  if (!host_meta) return;
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence();
+    const unsigned long long all = (unsigned long long)gridDim.x * (kPP_Threads / 32);
+    if (atomicAdd((unsigned long long*)&meta[7], 1ull) == all - 1ull) {
+      __threadfence();
+#pragma unroll
+      for (int q = 0; q < 6; q++) host_meta[q] = *(volatile long long*)&meta[q];
+    }
+  }
+}
+
 template <int S>
 __global__ void __launch_bounds__(kPP_Threads, 5)
 pileup_pipe_kernel(const int64_t* __restrict__ read_start, const int64_t* __restrict__ base_off,
                    const char* __restrict__ bases, long long* meta, const long long* __restrict__ tiles,
                    const int64_t* __restrict__ site_pos, int64_t n_sites, int64_t n_reads,
-                   uint16_t* __restrict__ counts) {
+                   uint16_t* __restrict__ counts, long long* host_meta) {
   extern __shared__ __align__(128) unsigned char pp_smem[];
   PipeShared<S>& sh = *reinterpret_cast<PipeShared<S>*>(pp_smem);
   constexpr int kSites = kPP_Consumers * S;
@@ -216,6 +233,7 @@ pileup_pipe_kernel(const int64_t* __restrict__ read_start, const int64_t* __rest
       sh.step[it & 1u].kind = kPP_Stop;
       mbar_arrive(&sh.full);
     }
+    pipe_leave(meta, host_meta, lane);
     return;
   }
 
@@ -383,6 +401,7 @@ pileup_pipe_kernel(const int64_t* __restrict__ read_start, const int64_t* __rest
       }
     }
   }
+  pipe_leave(meta, host_meta, lane);
 }
 
 // pre-pass: one warp per tile writes the tile's record (kPP_TileWords words): the six window bounds and whether the
@@ -425,7 +444,7 @@ pileup_windows_kernel(const int64_t* __restrict__ read_start, const long long* _
 template <int S>
 static cudaError_t launch_pileup_pipe(cudaStream_t st, int sms, const int64_t* d_read_start, const int64_t* d_base_off,
                                       const char* d_bases, long long* meta, long long* tiles, const int64_t* d_site_pos,
-                                      int64_t n_sites, int64_t n_reads, uint16_t* d_counts) {
+                                      int64_t n_sites, int64_t n_reads, uint16_t* d_counts, long long* host_meta) {
   auto kern = pileup_pipe_kernel<S>;
   const size_t smem = sizeof(PipeShared<S>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -439,7 +458,7 @@ static cudaError_t launch_pileup_pipe(cudaStream_t st, int sms, const int64_t* d
   pileup_windows_kernel<<<(unsigned)wblocks, 256, 0, st>>>(d_read_start, meta, d_site_pos, n_sites, kSites,
                                                            std::min(kPP_StageBytes - 16, 0x7FFFFFFF), tiles);
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)sms * std::max(per_sm, 1)));
-  kern<<<grid, kPP_Threads, smem, st>>>(d_read_start, d_base_off, d_bases, meta, tiles, d_site_pos, n_sites, n_reads, d_counts);
+  kern<<<grid, kPP_Threads, smem, st>>>(d_read_start, d_base_off, d_bases, meta, tiles, d_site_pos, n_sites, n_reads, d_counts, host_meta);
   return cudaGetLastError();
 }
 

@@ -298,7 +298,7 @@ sys.stdout.buffer.write(b"".join(out))
     res = []
     for chunk in (None, "65536", "1280", "lanes"):
         env = dict(os.environ)
-        if chunk == "lanes":  # a synchronous call split over the context's lanes (by default only above 2^24 sites per chunk)
+        if chunk == "lanes":  # a synchronous call split over the context's lanes (off by default: the whole call in one chunk is faster)
             env["DNV_SYNC_MIN_CHUNK"] = "65536"
         elif chunk:
             env["DNV_DEVICE_CHUNK"] = chunk
