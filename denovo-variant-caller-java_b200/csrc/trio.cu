@@ -290,6 +290,20 @@ int launch_pileup_scatter(dnv_ctx* ctx, cudaStream_t st, const int64_t* d_read_s
   return DNV_OK;
 }
 
+static ScreenConsts make_screen_consts(const dnv_ctx* ctx) {
+  ScreenConsts sk;
+  sk.c_hom = ctx->h_tab.c_hom_fx;
+  sk.c_het = ctx->h_tab.c_het_fx;
+  for (int x = 0; x < 4; x++) sk.w[x] = ctx->h_tab.scr_w[x];
+  sk.shift32 = 32;
+  static const bool no_l3 = std::getenv("DNV_NO_LEVEL3") != nullptr;  // A/B knob
+  sk.l3_lambda = no_l3 ? 0 : ctx->h_tab.l3_lambda_fx;
+  sk.l3_max_depth = ctx->h_tab.l3_max_depth;
+  sk.ktrace = nullptr;
+  sk.ktrace_seq = nullptr;
+  return sk;
+}
+
 // One chunk (n < 2^31) on the next lane.  The caller has recorded ctx->ev_sub on the front stream (parallel
 // contexts) and reads the totals through collect() at the end.
 int launch_trio_chunk(dnv_ctx* ctx, const ChunkArgs& a) {
@@ -334,14 +348,7 @@ int launch_trio_chunk(dnv_ctx* ctx, const ChunkArgs& a) {
     // (fused FP64 posterior, ordered compaction) and the per-call finish kernel
     rc = ensure_lane_list(ctx, ln, n);
     if (rc) return rc;
-    ScreenConsts sk;
-    sk.c_hom = ctx->h_tab.c_hom_fx;
-    sk.c_het = ctx->h_tab.c_het_fx;
-    for (int x = 0; x < 4; x++) sk.w[x] = ctx->h_tab.scr_w[x];
-    sk.shift32 = 32;
-    static const bool no_l3 = std::getenv("DNV_NO_LEVEL3") != nullptr;  // A/B knob
-    sk.l3_lambda = no_l3 ? 0 : ctx->h_tab.l3_lambda_fx;
-    sk.l3_max_depth = ctx->h_tab.l3_max_depth;
+    ScreenConsts sk = make_screen_consts(ctx);
     sk.ktrace = ch.ktrace;
     sk.ktrace_seq = ch.ktrace_seq;
     const bool u8 = ctx->count_bytes == 12;
@@ -427,6 +434,47 @@ int launch_trio_chunk(dnv_ctx* ctx, const ChunkArgs& a) {
 }
 
 }  // namespace dnv
+
+// Calibration (bench.py's roofline): `reps` back-to-back launches of the exact integer screen ALONE over one chunk of
+// counts resident in HBM, on the context's stream, bracketed by one pair of CUDA events — the kernel's average
+// duration with the launch latency of an idle stream amortised, as kernels are usually timed.  Uses lane 0's scratch;
+// the context must be idle (pending asynchronous batches are collected first).
+extern "C" int dnv_measure_screen(dnv_ctx* ctx, const void* d_counts, int count_bytes, int64_t n, int reps, double* ms_per_launch) {
+  using namespace dnv;
+  if (!ctx || !d_counts || !ms_per_launch || n <= 0 || n > (1ll << 27) || reps < 1 || (count_bytes != 24 && count_bytes != 12)) {
+    set_error("dnv_measure_screen: invalid argument");
+    return DNV_E_INVALID;
+  }
+  if (!will_screen(ctx, false)) { set_error("dnv_measure_screen: the screen does not apply to this context's parameters"); return DNV_E_INVALID; }
+  if (reinterpret_cast<uintptr_t>(d_counts) & 15) { set_error("dnv_measure_screen: counts must be 16-byte aligned"); return DNV_E_INVALID; }
+  DNV_CUDA(cudaSetDevice(ctx->device));
+  int rc = dnv_sync(ctx);
+  if (rc) return rc;
+  TrioLane& ln = ctx->lane[0];
+  rc = ensure_lane_list(ctx, ln, n);
+  if (rc) return rc;
+  const ScreenConsts sk = make_screen_consts(ctx);
+  cudaEvent_t e0, e1;
+  DNV_CUDA(cudaEventCreate(&e0));
+  DNV_CUDA(cudaEventCreate(&e1));
+  int sgrid = 0;
+  for (int pass = 0; pass < 2 && rc == DNV_OK; pass++) {  // pass 0 warms up (function attributes, clocks)
+    if (pass == 1) cudaEventRecord(e0, ctx->stream);
+    for (int r = 0; r < (pass ? reps : 3) && rc == DNV_OK; r++)
+      rc = count_bytes == 12 ? launch_screen<true>(ctx, ln, ctx->stream, d_counts, n, sk, &sgrid)
+                             : launch_screen<false>(ctx, ln, ctx->stream, d_counts, n, sk, &sgrid);
+    if (pass == 1) cudaEventRecord(e1, ctx->stream);
+  }
+  float ms = 0;
+  if (rc == DNV_OK && (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaEventElapsedTime(&ms, e0, e1) != cudaSuccess)) {
+    set_error(std::string("dnv_measure_screen: ") + cudaGetErrorString(cudaGetLastError()));
+    rc = DNV_E_CUDA;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (rc == DNV_OK) *ms_per_launch = (double)ms / reps;
+  return rc;
+}
 
 // DNV_KTRACE=1: the device-side time line of the chunks run so far, lane by lane: out[lane][kKtraceSlots][6]
 // (screen start / end, list start / end, finish start / end in %globaltimer nanoseconds; a lane's slots wrap) and

@@ -31,7 +31,7 @@ EXPORTS = ["dnv_create", "dnv_destroy", "dnv_last_error", "dnv_abi_version", "dn
            "dnv_gather_wait", "dnv_gather_fetch", "dnv_group_create", "dnv_group_destroy", "dnv_group_infer_counts",
            "dnv_group_infer_counts8", "dnv_group_size", "dnv_group_ctx", "dnv_group_get_stats", "dnv_pileup", "dnv_pileup_device", "dnv_infer_reads", "dnv_infer_reads_device",
            "dnv_mendel_filter", "dnv_mendel_filter_device", "dnv_synth_counts_device", "dnv_synth_counts_at_device",
-           "dnv_synth_counts_at", "dnv_measure_fp64_peak"]
+           "dnv_synth_counts_at", "dnv_measure_fp64_peak", "dnv_measure_screen"]
 
 
 class Params(C.Structure):
@@ -128,6 +128,7 @@ def load():
     L.dnv_synth_counts_at_device.argtypes = [vp, u64, vp, i64, vp, i32, u32, vp]
     L.dnv_synth_counts_at.argtypes = [vp, u64, vp, i64, vp, i32, u32, vp]
     L.dnv_measure_fp64_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.dnv_measure_screen.argtypes = [vp, vp, C.c_int, i64, C.c_int, C.POINTER(C.c_double)]
     for name in EXPORTS:
         if name != "dnv_last_error":
             getattr(L, name).restype = C.c_int

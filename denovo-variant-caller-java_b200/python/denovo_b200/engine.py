@@ -208,6 +208,12 @@ class TrioEngine:
         L.check(self.lib.dnv_measure_fp64_peak(self._h, C.byref(tf), C.byref(ms)))
         return tf.value, ms.value
 
+    def measure_screen(self, d_counts, n, reps=20, u8=False):
+        """Average duration (ms) of `reps` back-to-back launches of the integer screen alone over device counts."""
+        ms = C.c_double(0)
+        L.check(self.lib.dnv_measure_screen(self._h, L.ptr(d_counts), 12 if u8 else 24, n, reps, C.byref(ms)))
+        return ms.value
+
 
 class Gather:
     """One rank's end of the gather of call records to rank `dst` (include/denovo_b200.h: dnv_gather).

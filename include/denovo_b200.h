@@ -367,6 +367,11 @@ int dnv_free_pinned(void *p);
 /* Dependent-free DFMA chains on every SM: measured FP64 peak in TFLOP/s
  * (MEASURED_PEAKS.json has no FP64 figure). */
 int dnv_measure_fp64_peak(dnv_ctx *ctx, double *tflops, double *ms);
+/* `reps` back-to-back launches of the exact integer screen ALONE (the dominant kernel of the READ path) over one
+ * chunk of device-resident counts (count_bytes 24: uint16 layout, 12: uint8; n <= 2^27 sites), on the context's
+ * stream between one pair of CUDA events: the kernel's average duration with the launch latency of an idle stream
+ * amortised.  bench.py's roofline denominator; not part of the caller path. */
+int dnv_measure_screen(dnv_ctx *ctx, const void *d_counts, int count_bytes, int64_t n, int reps, double *ms_per_launch);
 
 #ifdef __cplusplus
 }
