@@ -8,9 +8,9 @@ OUT=$ROOT/denovo-variant-caller-java_b200/lib/variants
 mkdir -p $OUT
 for spec in "$@"; do
   name=${spec%%=*}; flags=${spec#*=}
-  rm -f $CS/trio.o $CS/pileup.o
+  rm -f $CS/trio.o $CS/pileup.o $CS/mendel.o
   make -s -C $CS EXTRA="$flags" OUT=$OUT/$name.so > /dev/null
   echo "built $name ($flags)"
 done
-rm -f $CS/trio.o $CS/pileup.o
+rm -f $CS/trio.o $CS/pileup.o $CS/mendel.o
 make -s -C $CS > /dev/null

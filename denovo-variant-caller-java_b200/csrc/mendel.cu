@@ -46,7 +46,10 @@ __device__ __forceinline__ int geno_of(int x, int y) {  // Genotype.valueOfPairA
 }
 
 constexpr int kMB = 256;  // records (kernel A) / child SNPs (kernel B) per block
-constexpr int kJI = 2;                 // child SNPs per thread in kernel B
+#ifndef DNV_MENDEL_JI
+#define DNV_MENDEL_JI 2
+#endif
+constexpr int kJI = DNV_MENDEL_JI;     // child SNPs per thread in kernel B
 constexpr int kJTile = kJI * kMB;      // 512 children per block
 
 struct MendelArrays {
@@ -321,7 +324,11 @@ __device__ __forceinline__ int64_t upper_bound_le(const int64_t* __restrict__ a,
   return lo;  // first index with a[idx] > key
 }
 
-constexpr int kJCap = 1536;            // parent entries staged per parent (start + running max as 32-bit offsets, code: 13.5 KB)
+#ifndef DNV_MENDEL_JCAP
+#define DNV_MENDEL_JCAP 1536
+#endif
+constexpr int kJCap = DNV_MENDEL_JCAP;  // parent entries staged per parent (start + running max as 32-bit offsets, code: 13.5 KB)
+static_assert(kJI * (kMB / 32) <= 32, "one warp scans the per-(round, warp) counts of kernel B");
 
 __device__ __forceinline__ int smem_upper_bound_le32(const uint32_t* a, int lo, int hi, uint32_t key) {
   while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] <= key) lo = mid + 1; else hi = mid; }
@@ -515,7 +522,8 @@ int dnv_mendel_filter_device(dnv_ctx* ctx, const dnv_vcall* d_calls, int64_t n, 
   size_t o_start[3], o_rmax[3], o_code[3];
   for (int p = 0; p < 3; p++) { o_start[p] = take((size_t)n * 8); o_rmax[p] = take((size_t)n * 8); o_code[p] = take((size_t)n); }
   const size_t o_ref = take((size_t)n), o_src = take((size_t)n * 8);
-  const size_t status_bytes = (size_t)((n + kJTile - 1) / kJTile + 1) * 8;  // sized for the finer of the two grids
+  constexpr int kFiner = kJTile < kMTile ? kJTile : kMTile;
+  const size_t status_bytes = (size_t)((n + kFiner - 1) / kFiner + 1) * 8;  // sized for the finer of the two grids
   const size_t win_bytes = (size_t)((n + kJTile - 1) / kJTile + 1) * 4 * 8;  // kernel B's window records
   const size_t o_status = take(7 * status_bytes + 64 + win_bytes);  // 3 sums, 3 maxima (child unused), found, the totals, the windows
   int rc = ensure_scratch(ctx, off);

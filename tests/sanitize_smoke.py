@@ -45,6 +45,14 @@ def main():
         for i in range(3):
             eng.infer_device_async(buf, 5003 - 100 * i, out, 5003, h_nc.data_ptr() + 8 * i)
         eng.sync()
+        # synchronous device calls: the first eager, the third a graph replay; the finish kernel's last CTA hands the
+        # statistics to pinned host memory (one-chunk call)
+        for i in range(3):
+            k = eng.infer_device(buf, 5003, out, 5003)
+        assert eng.stats()["n_calls"] == k
+        eng.measure_screen(buf, 5003, reps=2)
+        # reads -> calls: pileup chained to the READ pipeline with one host wait
+        eng.infer_reads(rs, bo, ba, pe, np.arange(950, 3600, dtype=np.int64))
         with D.DeviceGroup([0, 0]) as grp:
             grp.infer(buf.cpu().numpy().view(np.uint16).reshape(-1, 3, 4))
     print("sanitize_smoke OK")
