@@ -512,7 +512,7 @@ static int infer_device_async_impl(dnv_ctx* ctx, const void* d_counts, int bps, 
   }
   // A batch of one chunk on the calls-only path is replayable: the second time its arguments are seen it is
   // captured on its lane's stream, from then on it costs the host one wait + one graph launch.
-  const bool graphable = ctx->use_graphs_async && !ctx->dense_mode && n > 0 && n <= device_chunk() && will_screen(ctx, false) && true;
+  const bool graphable = ctx->use_graphs_async && !ctx->dense_mode && n > 0 && n <= device_chunk() && will_screen(ctx, false);
   if (graphable) {
     TrioLane& ln = ctx->lane[ctx->lane_next];
     const GraphKey key{d_counts, d_calls, n_calls_out, nullptr, n, site_base, cap, bps};
