@@ -73,6 +73,9 @@ struct MendelArrays {
 constexpr unsigned long long kErrUnsorted = 1, kErrBadBase = 2;
 constexpr unsigned long long kStAgg = 1ull << 62, kStPre = 2ull << 62, kStVal = (1ull << 62) - 1;
 
+#ifndef DNV_MENDEL_SPIN_NS
+#define DNV_MENDEL_SPIN_NS 0
+#endif
 // one warp: exclusive combination (sum or max) of all predecessor blocks' values
 template <bool kMax>
 __device__ __forceinline__ unsigned long long lookback(unsigned long long* status, unsigned int b,
@@ -85,7 +88,13 @@ __device__ __forceinline__ unsigned long long lookback(unsigned long long* statu
       const int p = hi - lane;
       unsigned long long v = kStPre;  // before block 0: empty inclusive prefix
       if (p >= 0) {
-        do { v = *(volatile unsigned long long*)&status[p]; } while ((v >> 62) == 0);
+        // a lane whose predecessor has not published yet backs off: the kernels are bound by integer issue slots,
+        // which a tight polling loop would take from the warps that still have records to decode (DNV_MENDEL_SPIN_NS)
+        for (;;) {
+          v = *(volatile unsigned long long*)&status[p];
+          if ((v >> 62) != 0) break;
+          if (DNV_MENDEL_SPIN_NS > 0) __nanosleep(DNV_MENDEL_SPIN_NS);
+        }
       }
       const uint32_t is_pre = __ballot_sync(0xffffffffu, (v >> 62) == 2ull);
       const int stop = is_pre ? __ffs(is_pre) - 1 : 31;
