@@ -9,8 +9,9 @@
 // Layout: reads sorted by (person, start); per person the reads overlapping a position are a
 // contiguous window found by binary search, so the kernel is a GATHER: every (site, person)
 // count vector is accumulated in registers by one thread and written once — no atomics, no
-// inter-thread contention, deterministic.  The kernel itself lives in pileup_stage.cuh; this
-// file holds the validation / metadata pass over the read descriptors and the C entry points.
+// inter-thread contention, deterministic.  The kernels live in pileup_pipe.cuh (default: producer /
+// consumer pipeline over dense tiles), pileup_stage.cuh and pileup_scatter.cuh; this file holds the
+// validation / metadata pass over the read descriptors and the C entry points.
 #include <stdlib.h>
 #include <algorithm>
 #include "dnv_internal.cuh"
