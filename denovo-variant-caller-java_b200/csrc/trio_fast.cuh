@@ -31,6 +31,9 @@
 namespace dnv {
 
 constexpr int kFastThreads = 128;
+#ifndef DNV_FAST_MINBLOCKS
+#define DNV_FAST_MINBLOCKS 3   // resident CTAs per SM the BAYES / LRT all-sites kernel is compiled for (3: 160 registers)
+#endif
 constexpr int kTileBytes = kFastThreads * 24;
 
 constexpr int kFastWarps = kFastThreads / 32;
@@ -362,7 +365,7 @@ inline int launch_trio_fast(dnv_ctx* ctx, cudaStream_t st, const void* d_counts,
   const bool map = ctx->prm.method == DNV_METHOD_MAP;
   if (d_dense) return launch_fast_variant<true, true, true, 2>(ctx, st, d_counts, n, d_dense, acc);
   if (map) return launch_fast_variant<false, true, false, 4>(ctx, st, d_counts, n, nullptr, acc);
-  return launch_fast_variant<true, false, false, 3>(ctx, st, d_counts, n, nullptr, acc);
+  return launch_fast_variant<true, false, false, DNV_FAST_MINBLOCKS>(ctx, st, d_counts, n, nullptr, acc);
 }
 
 }  // namespace dnv
